@@ -1,0 +1,192 @@
+/*
+ * ipfa_b200.h -- C ABI of the B200-native alignment hot path.
+ *
+ * Drop-in boundary for the numerics behind the reference's aligner calls
+ *   aligner.get_segments(task)        /root/reference/src/iterative_utterance_alignment.py:216
+ *                                     /root/reference/src/word_level_alignment.py:100
+ *                                     /root/reference/src/search_on_speech.py:85
+ * (speechbrain==0.5.11 CTCSegmentation -> ctc-segmentation==1.7.1
+ *  `cython_fill_table` + backtrace + `determine_utterance_segments`,
+ *  /root/reference/requirements.txt:13,87), for the accept/shrink/revert
+ * decision of /root/reference/src/iterative_utterance_alignment.py:221-379,
+ * and for the two standard-CTC comparators BASELINE.json's north_star names
+ * (torch CTC loss, torchaudio forced align).
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer in a *_device entry point is a
+ *     DEVICE pointer owned by the caller, `stream` is a cudaStream_t passed as
+ *     void*.  Nothing is allocated, freed, retained or synchronised inside a
+ *     *_device call; workspace sizes come from the *_workspace_bytes helpers.
+ *   - *_host entry points take HOST pointers and run the whole
+ *     H2D -> kernels -> D2H sequence on an internal stream and an internal,
+ *     grow-only device arena (this is what a cgo/ctypes binding that only has
+ *     host buffers calls, and what bench.py's `e2e` times).
+ *   - return value: 0 = IPFA_OK, otherwise an IPFA_ERR_* code; the text is in
+ *     ipfa_status_string().  There is no CPU fallback: without a CUDA device
+ *     every compute call returns IPFA_ERR_CUDA.
+ *   - emissions `lp` are fp32 log-probabilities [N, Tmax, V] addressed through
+ *     element strides (stride_n, stride_t); the vocabulary axis is contiguous.
+ */
+#ifndef IPFA_B200_H_
+#define IPFA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPFA_OK 0
+#define IPFA_ERR_INVALID_ARG 1   /* null pointer, negative size, label out of range */
+#define IPFA_ERR_UNSUPPORTED 2   /* lattice wider than the widest kernel instance */
+#define IPFA_ERR_WORKSPACE 3     /* workspace too small */
+#define IPFA_ERR_CUDA 4          /* CUDA runtime error (ipfa_last_cuda_error()) */
+#define IPFA_ERR_AUDIO_SHORTER_THAN_TEXT 5 /* ctcseg: N > T (reference raises AssertionError) */
+
+/* per-window status bits written to the status_out arrays */
+#define IPFA_WIN_OK 0
+#define IPFA_WIN_INFEASIBLE 1    /* forced_align: T < L + repeats (torchaudio raises) */
+#define IPFA_WIN_BAD_LABEL 2     /* a target id is < 0, >= V or equals blank (Viterbi) */
+#define IPFA_WIN_TEXT_LONGER 4   /* ctcseg: N > T */
+
+int ipfa_version(void);
+const char *ipfa_status_string(int status);
+const char *ipfa_last_cuda_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t ipfa_launch_count(void);
+int ipfa_device_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Kernel (1): batched CTC alpha recursion over the blank-interleaved 2L+1
+ * lattice.  Replaces torch.nn.functional.ctc_loss(..., reduction='none') as
+ * the window scorer (the "acoustic CTC loss" of
+ * /root/reference/README.md:3).
+ *   lp        [N, Tmax, V] fp32 log-probs (strides in elements)
+ *   targets   [N, Lmax] int32 (row stride tgt_stride), no blanks required
+ *   in_len    [N] int32 frames per window, tgt_len [N] int32 labels per window
+ *   nll_out   [N] fp32: -log p(target | window); +inf when infeasible
+ * ------------------------------------------------------------------------- */
+size_t ipfa_ctc_alpha_workspace_bytes(int N, int Tmax, int Lmax, int V);
+int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
+                          const int32_t *targets, int64_t tgt_stride,
+                          const int32_t *in_len, const int32_t *tgt_len,
+                          int N, int Tmax, int Lmax, int V, int blank,
+                          float *nll_out, void *workspace, size_t workspace_bytes,
+                          void *stream);
+int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t stride_t,
+                        const int32_t *targets, int64_t tgt_stride,
+                        const int32_t *in_len, const int32_t *tgt_len,
+                        int N, int Tmax, int Lmax, int V, int blank, float *nll_out);
+
+/* ------------------------------------------------------------------------- *
+ * Kernel (2a): CTC Viterbi forced alignment on the 2L+1 lattice with 2-bit
+ * packed backpointers in HBM, then a warp-parallel backtrace that also emits
+ * per-frame scores and per-token spans/confidences.  Replaces
+ * torchaudio.functional.forced_align + merge_tokens.
+ *   paths_out   [N, Tmax] int32 token id per frame (-1 beyond in_len / on error)
+ *   scores_out  [N, Tmax] fp32 lp[t, paths[t]]
+ *   tok_start/tok_end [N, Lmax] int32 first frame / one-past-last frame per token
+ *   tok_score   [N, Lmax] fp32 mean frame score of the token's span
+ *   total_out   [N] fp32 Viterbi path log-probability (nullable)
+ *   status_out  [N] int32 IPFA_WIN_* bits
+ *   tok_* and total_out may be NULL.
+ * ------------------------------------------------------------------------- */
+size_t ipfa_ctc_viterbi_workspace_bytes(int N, int Tmax, int Lmax, int V);
+int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_t stride_t,
+                            const int32_t *targets, int64_t tgt_stride,
+                            const int32_t *in_len, const int32_t *tgt_len,
+                            int N, int Tmax, int Lmax, int V, int blank,
+                            int32_t *paths_out, float *scores_out,
+                            int32_t *tok_start, int32_t *tok_end, float *tok_score,
+                            float *total_out, int32_t *status_out,
+                            void *workspace, size_t workspace_bytes, void *stream);
+int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
+                          const int32_t *targets, int64_t tgt_stride,
+                          const int32_t *in_len, const int32_t *tgt_len,
+                          int N, int Tmax, int Lmax, int V, int blank,
+                          int32_t *paths_out, float *scores_out,
+                          int32_t *tok_start, int32_t *tok_end, float *tok_score,
+                          float *total_out, int32_t *status_out);
+
+/* ------------------------------------------------------------------------- *
+ * Kernel (2b): CTC-segmentation (Kuerzinger) table fill + backtrace + utterance
+ * scoring -- what `CTCSegmentation.get_segments` runs.  One fill per window
+ * serves EVERY utterance-prefix of the window's text (the shrinking-transcript
+ * iterations of /root/reference/src/iterative_utterance_alignment.py:203-385):
+ * prefix k ends in column utt_begin[k]; its terminal frame is the first argmax
+ * of that column.
+ *   gt          [N, Cmax] int32 ground-truth token column per window:
+ *               -1, blank, tokens..., blank, tokens..., blank (prepare_token_list)
+ *   n_cols      [N] int32 columns used per window
+ *   utt_begin   [N, Kmax+1] int32 utterance begin columns (prepare_token_list's
+ *               utt_begin_indices), n_utts [N] int32
+ *   index_duration  seconds per frame (config.index_duration)
+ *   flags       bit0 blank_transition_cost_zero, bit1 preamble_transition_cost_zero,
+ *               bit2 round-to-nearest frame index in scoring (default floor),
+ *               bit3 align every prefix (else only the full text, prefix K)
+ *   For window w and prefix k (1..K_w; slot k-1 along the prefix axis):
+ *   seg_out       [N, Kmax, Kmax, 3] fp64 (start s, end s, score) of utterance u<k
+ *   term_t_out    [N, Kmax] int32 terminal frame of prefix k
+ *   timing_out    [N, Kmax, Cmax] int32 frame at which column c was entered (-1 unset)
+ *                 (nullable; timings[c] = frame * index_duration)
+ *   char_prob_out [N, Kmax, Tmax] fp32 per-frame path probability (nullable)
+ *   state_out     [N, Kmax, Tmax] int32 per-frame column, -1 = stay ("epsilon"),
+ *                 -2 = frame not on the path (nullable)
+ *   status_out    [N] int32 IPFA_WIN_* bits (IPFA_WIN_TEXT_LONGER <-> AssertionError)
+ *   When bit3 is clear only slot Kmax... see DESIGN.md: slot (K_w - 1) is filled.
+ * ------------------------------------------------------------------------- */
+#define IPFA_SEG_BLANK_COST_ZERO 1
+#define IPFA_SEG_PREAMBLE_COST_ZERO 2
+#define IPFA_SEG_ROUND_NEAREST 4
+#define IPFA_SEG_ALL_PREFIXES 8
+
+size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int V);
+int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t stride_t,
+                       const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                       const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+                       int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+                       double index_duration, int score_len, int flags,
+                       double *seg_out, int32_t *term_t_out, int32_t *timing_out,
+                       float *char_prob_out, int32_t *state_out, int32_t *status_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
+int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t stride_t,
+                     const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                     const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+                     int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+                     double index_duration, int score_len, int flags,
+                     double *seg_out, int32_t *term_t_out, int32_t *timing_out,
+                     float *char_prob_out, int32_t *state_out, int32_t *status_out);
+
+/* ------------------------------------------------------------------------- *
+ * Kernel (3): on-device evaluation of the anchor loop's accept / shrink /
+ * revert state machine (/root/reference/src/iterative_utterance_alignment.py:221-379)
+ * over the K prefix alignments of each window produced by ipfa_ctcseg_device
+ * with IPFA_SEG_ALL_PREFIXES, so only a few bytes per window return to host.
+ *   seg          [N, Kmax, Kmax, 3] fp64 from ipfa_ctcseg_device
+ *   n_utts       [N] int32
+ *   text_len     [N, Kmax] int32 len(text) of each utterance (short-utterance rule)
+ *   is_last      [N] int32 window is the last TSV row of its file (:263)
+ *   threshold    anchor threshold (-2.0 default), short_len (30 default)
+ *   decision_out [N, 4] int32:
+ *       [0] accepted prefix length k (0 = nothing accepted / all discarded)
+ *       [1] iterations the reference loop would have run
+ *       [2] outcome code IPFA_SEL_*
+ *       [3] number of utterances pushed back to discarded_transcripts
+ *   anchor_out   [N] fp64 new_segment_start relative to the window start (seconds),
+ *                NaN when the anchor is rewound to the window start (:277,:329)
+ * ------------------------------------------------------------------------- */
+#define IPFA_SEL_ACCEPT_CURRENT 0
+#define IPFA_SEL_KEEP_PREVIOUS 1
+#define IPFA_SEL_DISCARD_ALL 2
+#define IPFA_SEL_LAST_SEGMENT 3
+
+int ipfa_anchor_select_device(const double *seg, const int32_t *n_utts,
+                              const int32_t *text_len, const int32_t *is_last,
+                              int N, int Kmax, double threshold, int short_len,
+                              int32_t *decision_out, double *anchor_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPFA_B200_H_ */

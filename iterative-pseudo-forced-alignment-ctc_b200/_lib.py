@@ -1,0 +1,97 @@
+"""ctypes binding of libipfa_b200.so (the C ABI declared in include/ipfa_b200.h).
+
+The product path has no CPU fallback: if the shared library cannot be built or
+loaded, importing this module raises."""
+import ctypes
+import os
+import re
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(_HERE, "..", "include", "ipfa_b200.h")
+
+c_void = ctypes.c_void_p
+c_i = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_sz = ctypes.c_size_t
+c_d = ctypes.c_double
+
+_SIGNATURES = {
+    "ipfa_version": (c_i, []),
+    "ipfa_status_string": (ctypes.c_char_p, [c_i]),
+    "ipfa_last_cuda_error": (ctypes.c_char_p, []),
+    "ipfa_launch_count": (ctypes.c_uint64, []),
+    "ipfa_device_count": (c_i, []),
+    "ipfa_ctc_alpha_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "ipfa_ctc_alpha_device": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
+                                    c_i, c_i, c_i, c_i, c_i, c_void, c_void, c_sz, c_void]),
+    "ipfa_ctc_alpha_host": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
+                                  c_i, c_i, c_i, c_i, c_i, c_void]),
+    "ipfa_ctc_viterbi_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "ipfa_ctc_viterbi_device": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
+                                      c_i, c_i, c_i, c_i, c_i,
+                                      c_void, c_void, c_void, c_void, c_void, c_void, c_void,
+                                      c_void, c_sz, c_void]),
+    "ipfa_ctc_viterbi_host": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
+                                    c_i, c_i, c_i, c_i, c_i,
+                                    c_void, c_void, c_void, c_void, c_void, c_void, c_void]),
+    "ipfa_ctcseg_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
+    "ipfa_ctcseg_device": (c_i, [c_void, c_i64, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void,
+                                 c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_i,
+                                 c_void, c_void, c_void, c_void, c_void, c_void,
+                                 c_void, c_sz, c_void]),
+    "ipfa_ctcseg_host": (c_i, [c_void, c_i64, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void,
+                               c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_i,
+                               c_void, c_void, c_void, c_void, c_void, c_void]),
+    "ipfa_anchor_select_device": (c_i, [c_void, c_void, c_void, c_void, c_i, c_i, c_d, c_i,
+                                        c_void, c_void, c_void]),
+}
+
+
+def declared_symbols():
+    """Every function include/ipfa_b200.h declares (used by the CPU-side ABI test)."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ipfa_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not _build.up_to_date():
+            try:
+                path = _build.build()
+            except Exception as exc:  # no nvcc on the box: use the shipped .so if there is one
+                if not os.path.exists(path):
+                    raise ImportError(f"libipfa_b200.so is missing and could not be built: {exc}")
+        L = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class IpfaError(RuntimeError):
+    def __init__(self, status, where):
+        L = lib()
+        msg = L.ipfa_status_string(status).decode()
+        if status == 4:
+            msg += ": " + L.ipfa_last_cuda_error().decode()
+        super().__init__(f"{where}: {msg} (status {status})")
+        self.status = status
+
+
+def check(status, where):
+    if status == 5:
+        # the reference's callers catch AssertionError for this condition
+        # (/root/reference/src/iterative_utterance_alignment.py:390)
+        raise AssertionError("Audio is shorter than text!")
+    if status != 0:
+        raise IpfaError(status, where)

@@ -1,0 +1,73 @@
+"""Builds csrc/*.cu into libipfa_b200.so (sm_100a only, in-tree).
+
+    python iterative-pseudo-forced-alignment-ctc_b200/build.py [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU
+box with the gpurun snapshot."""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libipfa_b200.so")
+OBJ = os.path.join(HERE, "build")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # bit-exact Viterbi scores need the oracle's single-rounding adds: no FMA contraction
+    "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _deps_mtime():
+    files = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(HERE, "..", "include", "*.h")) + [os.path.abspath(__file__)]
+    return max(os.path.getmtime(f) for f in files)
+
+
+def up_to_date():
+    return os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime()
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    procs = []
+    hdr_mtime = max([os.path.getmtime(f) for f in glob.glob(os.path.join(CSRC, "*.cuh")) +
+                     glob.glob(os.path.join(HERE, "..", "include", "*.h"))] + [os.path.getmtime(__file__)])
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_mtime)):
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(f"--- nvcc {os.path.basename(src)} (rc={p.returncode})\n{out}\n")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,436 @@
+// ctc_viterbi.cu -- kernel (2a): CTC Viterbi forced alignment on the 2L+1
+// lattice with 2-bit packed backpointers in HBM + warp-parallel backtrace with
+// per-frame scores and per-token spans / confidences.
+//
+// Replaces torchaudio.functional.forced_align (torchaudio/csrc/forced_align/cpu/
+// compute.cpp::forced_align_impl; Python surface functional/_alignment.py:11-73)
+// and merge_tokens (_alignment.py:94-127); SURVEY.md section 8(a) row A8.  Tie rule
+// mirrored exactly: strict-greater comparisons, ties fall to "stay", final state
+// prefers S-2 on a tie.  torchaudio's start/end band is not restated: states it
+// masks are exactly the ones that cannot lie on a complete path, so the natural
+// -inf propagation yields identical backpointers along every complete path.
+//
+// Fill: same pair-per-thread register layout as ctc_alpha.cu (max-plus instead
+// of log-sum-exp; fp32 single-rounding adds so scores are bit-identical to the
+// CPU).  Every thread packs its 2P states x 2 bits per frame into 32-bit words
+// (8/P frames per word) and stores them lane-contiguous: bp[w][t / SPW][thread],
+// i.e. exactly 2 bits per (padded) lattice cell, written once, coalesced.
+// Backtrace: one warp per window; per 32-frame block the warp fetches the
+// 4P words x (8/P) thread-columns it can possibly touch with ONE coalesced
+// load, then walks the block through warp shuffles.
+#include "emission_pipe.cuh"
+
+namespace ipfa {
+
+extern cudaError_t g_last_cuda_error;
+extern uint64_t g_launch_count;
+bool use_dense_panel(int V, int Lmax);
+
+struct ViterbiParams {
+    const float *lp;
+    int64_t stride_n, stride_t;
+    const int32_t *targets;
+    int64_t tgt_stride;
+    const int32_t *in_len;
+    const int32_t *tgt_len;
+    int N, Tmax, V, blank;
+    int pitch, tc, u_cap, l_cap;
+    size_t group_smem;
+    uint32_t *bp;            // [N][words_per_window]
+    int64_t words_per_window;
+    int32_t *final_state;    // [N]
+    float *total_out;        // [N] nullable
+    int32_t *status_out;     // [N]
+};
+
+template <int P, int WARPS, bool DENSE>
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
+ctc_viterbi_fill_kernel(const ViterbiParams prm) {
+    constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
+    constexpr int NT = 32 * WARPS;
+    constexpr int SPW = 8 / P;  // frames per backpointer word
+    constexpr float NEG = -__builtin_huge_valf();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
+    const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = (WARPS == 1) ? 0 : (threadIdx.x >> 5);
+    const int w = blockIdx.x * GROUPS + group;
+    if (w >= prm.N) return;
+
+    unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
+    float *ring = reinterpret_cast<float *>(gsm);
+    float *xch = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][WARPS]
+    float *fin = xch + 2 * WARPS;                               // [2]
+    int *cnt = reinterpret_cast<int *>(fin + 2);                // [2] repeats, bad labels
+    int *cols = cnt + 2;                                        // [u_cap]
+
+    const int T = prm.in_len[w];
+    const int L = max(0, min(prm.tgt_len[w], prm.l_cap));
+    const int32_t *tg = prm.targets + (int64_t)w * prm.tgt_stride;
+    const int blank = prm.blank;
+
+    if (tid < 2) cnt[tid] = 0;
+    group_sync<WARPS>();
+
+    int col[P];
+    bool skip[P], lab_ok[P], blk_ok[P];
+    int n_rep = 0, n_bad = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int j = tid * P + p;
+        lab_ok[p] = j < L;
+        blk_ok[p] = j <= L;
+        int lab = lab_ok[p] ? tg[j] : blank;
+        if (lab_ok[p] && (lab < 0 || lab >= prm.V || lab == blank)) ++n_bad;
+        if (lab < 0 || lab >= prm.V) lab = blank;
+        const int prev = (j >= 1 && lab_ok[p]) ? tg[j - 1] : -1;
+        skip[p] = lab_ok[p] && j >= 1 && prev != lab;
+        if (lab_ok[p] && j >= 1 && prev == lab) ++n_rep;
+        col[p] = DENSE ? lab : (j + 1);
+    }
+    if (n_rep) atomicAdd(&cnt[0], n_rep);
+    if (n_bad) atomicAdd(&cnt[1], n_bad);
+    const int colb = DENSE ? blank : 0;
+    if constexpr (!DENSE) {
+        for (int j = tid; j <= L; j += NT) {
+            int c = (j == 0) ? blank : tg[j - 1];
+            if (c < 0 || c >= prm.V) c = blank;
+            cols[j] = c;
+        }
+    }
+    group_sync<WARPS>();
+    const int R = cnt[0];
+    int status = cnt[1] ? IPFA_WIN_BAD_LABEL : IPFA_WIN_OK;
+    if (T <= 0 || T < L + R) status |= IPFA_WIN_INFEASIBLE;
+    if (status & IPFA_WIN_INFEASIBLE) {
+        if (tid == 0) {
+            prm.status_out[w] = status;
+            prm.final_state[w] = -1;
+            if (prm.total_out) prm.total_out[w] = NEG;
+        }
+        return;
+    }
+
+    EmissionPipe<WARPS, DENSE> pipe;
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, prm.pitch,
+              prm.tc);
+    pipe.prologue(tid);
+
+    float ab[P], al[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) { ab[p] = NEG; al[p] = NEG; }
+    uint32_t word = 0;
+    uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window + tid;
+
+    for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
+        const float *panel = pipe.acquire(chunk, tid);
+        const int t0 = chunk * pipe.tc;
+        const int rows = min(pipe.tc, T - t0);
+        for (int r = 0; r < rows; ++r) {
+            const float *row = panel + r * prm.pitch;
+            const float eb = row[colb];
+            float el[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) el[p] = row[col[p]];
+            const int t = t0 + r;
+            if (t == 0) {
+                if (tid == 0) {
+                    // torchaudio: start = (T - (L+R) > 0) ? 0 : 1 -- the leading blank is
+                    // off every complete path when T == L+R; keeping it changes nothing.
+                    ab[0] = eb;
+                    if (lab_ok[0]) al[0] = el[0];
+                }
+            } else {
+                float prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+                if constexpr (WARPS > 1) {
+                    if (lane == 0) prev = (warp > 0) ? xch[((t - 1) & 1) * WARPS + warp - 1] : NEG;
+                } else {
+                    if (lane == 0) prev = NEG;
+                }
+                uint32_t bits = 0;
+#pragma unroll
+                for (int p = P - 1; p >= 0; --p) {
+                    const float lm1 = (p == 0) ? prev : al[p - 1];
+                    // label state: x0 stay, x1 from blank, x2 skip
+                    const float x0 = al[p], x1 = ab[p], x2 = skip[p] ? lm1 : NEG;
+                    float res;
+                    uint32_t bl;
+                    if (x2 > x1 && x2 > x0) { res = x2; bl = 2; }
+                    else if (x1 > x0 && x1 > x2) { res = x1; bl = 1; }
+                    else { res = x0; bl = 0; }
+                    const float nl = res + el[p];
+                    // blank state: x0 stay, x1 from previous label
+                    const uint32_t bb = (lm1 > ab[p]) ? 1u : 0u;
+                    const float nb = (bb ? lm1 : ab[p]) + eb;
+                    al[p] = lab_ok[p] ? nl : NEG;
+                    ab[p] = blk_ok[p] ? nb : NEG;
+                    bits |= (bb | (bl << 2)) << (4 * p);
+                }
+                word |= bits << ((t % SPW) * 4 * P);
+            }
+            if ((t % SPW) == SPW - 1 || t == T - 1) {
+                bp_w[(int64_t)(t / SPW) * NT] = word;
+                word = 0;
+            }
+            if constexpr (WARPS > 1) {
+                if (lane == 31) xch[(t & 1) * WARPS + warp] = al[P - 1];
+                __syncthreads();
+            }
+        }
+    }
+
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int j = tid * P + p;
+        if (j == L) fin[0] = ab[p];
+        if (j == L - 1) fin[1] = al[p];
+    }
+    group_sync<WARPS>();
+    if (tid == 0) {
+        const int S = 2 * L + 1;
+        int ltr = 0;
+        float best = fin[0];
+        if (S > 1) {
+            if (fin[0] > fin[1]) { ltr = S - 1; best = fin[0]; }
+            else { ltr = S - 2; best = fin[1]; }
+        }
+        prm.final_state[w] = ltr;
+        prm.status_out[w] = status;
+        if (prm.total_out) prm.total_out[w] = best;
+    }
+}
+
+struct BacktraceParams {
+    const float *lp;
+    int64_t stride_n, stride_t;
+    const int32_t *targets;
+    int64_t tgt_stride;
+    const int32_t *in_len;
+    const int32_t *tgt_len;
+    int N, Tmax, Lmax, V, blank, NT;
+    const uint32_t *bp;
+    int64_t words_per_window;
+    const int32_t *final_state;
+    int32_t *paths_out;
+    float *scores_out;
+    int32_t *tok_start, *tok_end;
+    float *tok_score;
+};
+
+// One warp per window.
+template <int P>
+__global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const BacktraceParams prm) {
+    constexpr int SPW = 8 / P;       // frames per word
+    constexpr int NW = 32 / SPW;     // words per 32-frame block (= 4P)
+    constexpr int NCOL = 32 / NW;    // thread-columns fetched per block (= 8/P)
+    constexpr int SPT = 2 * P;       // states per thread
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= prm.N) return;
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int L = max(0, min(prm.tgt_len[w], prm.Lmax));
+    const int32_t *tg = prm.targets + (int64_t)w * prm.tgt_stride;
+    int32_t *paths = prm.paths_out + (int64_t)w * prm.Tmax;
+    float *scores = prm.scores_out ? prm.scores_out + (int64_t)w * prm.Tmax : nullptr;
+    const float *lp = prm.lp + (int64_t)w * prm.stride_n;
+    int s = prm.final_state[w];
+
+    // tail beyond in_len, or the whole row when infeasible
+    const int t_valid = (s < 0) ? 0 : max(T, 0);
+    for (int t = t_valid + lane; t < prm.Tmax; t += 32) {
+        paths[t] = -1;
+        if (scores) scores[t] = 0.0f;
+    }
+    const bool want_tok = prm.tok_start != nullptr;
+    int32_t *tok_s = want_tok ? prm.tok_start + (int64_t)w * prm.Lmax : nullptr;
+    int32_t *tok_e = want_tok ? prm.tok_end + (int64_t)w * prm.Lmax : nullptr;
+    float *tok_p = (want_tok && prm.tok_score) ? prm.tok_score + (int64_t)w * prm.Lmax : nullptr;
+    if (want_tok) {
+        for (int l = lane; l < prm.Lmax; l += 32) {
+            tok_s[l] = -1;
+            tok_e[l] = -1;
+            if (tok_p) tok_p[l] = 0.0f;
+        }
+        __syncwarp();
+    }
+    if (s < 0 || T <= 0) return;
+
+    const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
+    const int NT = prm.NT;
+    // token bookkeeping while walking backwards (uniform across lanes)
+    if (want_tok && lane == 0 && (s & 1)) tok_e[s >> 1] = T;
+
+    for (int blk = (T - 1) >> 5; blk >= 0; --blk) {
+        const int t_hi = min(T - 1, blk * 32 + 31);
+        const int t_lo = blk * 32;
+        const int icur = s / SPT;  // thread-column of the state at t_hi
+        // lane j holds word (blk*NW + j % NW) of thread-column icur - j / NW
+        const int my_col = icur - lane / NW;
+        const int my_word = blk * NW + (lane % NW);
+        uint32_t wreg = 0;
+        if (my_col >= 0 && (int64_t)my_word * SPW < T) wreg = bp_w[(int64_t)my_word * NT + my_col];
+        int my_state = 0;
+        for (int t = t_hi; t >= t_lo; --t) {
+            if (lane == (t & 31)) my_state = s;
+            if (t == 0) break;
+            const int i = s / SPT, k = s - i * SPT;
+            const int coff = icur - i;
+            const int widx = (t / SPW) - blk * NW;
+            uint32_t word;
+            if (coff < NCOL) {
+                word = __shfl_sync(0xffffffffu, wreg, coff * NW + widx);
+            } else {
+                word = bp_w[(int64_t)(t / SPW) * NT + i];  // rare: > 8/P columns crossed in 32 frames
+            }
+            const int d = (word >> ((t % SPW) * 4 * P + 2 * k)) & 3;
+            if (want_tok && d != 0 && lane == 0) {
+                // state s starts at frame t; state s-d ends at frame t (exclusive end)
+                if (s & 1) tok_s[s >> 1] = t;
+                if ((s - d) & 1) tok_e[(s - d) >> 1] = t;
+            }
+            s -= d;
+        }
+        const int t = t_lo + lane;
+        if (t <= t_hi) {
+            const int lab = (my_state & 1) ? tg[my_state >> 1] : prm.blank;
+            paths[t] = lab;
+            if (scores) scores[t] = lp[(int64_t)t * prm.stride_t + lab];
+        }
+    }
+    if (want_tok) {
+        if (lane == 0 && (s & 1)) tok_s[s >> 1] = 0;
+        __syncwarp();
+        if (tok_p) {
+            for (int l = lane; l < L; l += 32) {
+                const int a = tok_s[l], b = tok_e[l];
+                if (a >= 0 && b > a) {
+                    const int lab = tg[l];
+                    float acc = 0.0f;
+                    for (int t = a; t < b; ++t) acc += lp[(int64_t)t * prm.stride_t + lab];
+                    tok_p[l] = acc / (float)(b - a);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct LatticeShape { int P, WARPS; };
+static bool pick_shape(int pairs, LatticeShape *s) {
+    static const LatticeShape shapes[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}, {8, 16}};
+    for (const auto &c : shapes) {
+        if (32 * c.WARPS * c.P >= pairs) { *s = c; return true; }
+    }
+    return false;
+}
+static int64_t viterbi_words_per_window(int Tmax, LatticeShape s) {
+    const int spw = 8 / s.P;
+    return (int64_t)((Tmax + spw - 1) / spw) * 32 * s.WARPS;
+}
+
+template <int P, int WARPS, bool DENSE>
+static int launch_fill(ViterbiParams prm, int Lmax, cudaStream_t stream) {
+    constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
+    const int U = DENSE ? prm.V : (Lmax + 1);
+    const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
+    PipeGeometry g = pipe_geometry(U, budget);
+    prm.pitch = g.pitch;
+    prm.tc = g.tc;
+    prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
+    prm.l_cap = Lmax;
+    size_t group_smem = g.ring_bytes + (2 * WARPS + 2) * sizeof(float) + 2 * sizeof(int) +
+                        (size_t)prm.u_cap * sizeof(int);
+    group_smem = (group_smem + 15) & ~(size_t)15;
+    prm.group_smem = group_smem;
+    const size_t smem = group_smem * GROUPS;
+    auto kern = ctc_viterbi_fill_kernel<P, WARPS, DENSE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
+    const int blocks = (prm.N + GROUPS - 1) / GROUPS;
+    kern<<<blocks, threads, smem, stream>>>(prm);
+    ++g_launch_count;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
+
+template <bool DENSE>
+static int dispatch_fill(const ViterbiParams &prm, int Lmax, LatticeShape s, cudaStream_t stream) {
+#define IPFA_CASE(P_, W_) \
+    if (s.P == P_ && s.WARPS == W_) return launch_fill<P_, W_, DENSE>(prm, Lmax, stream);
+    IPFA_CASE(1, 1) IPFA_CASE(2, 1) IPFA_CASE(4, 1) IPFA_CASE(4, 2) IPFA_CASE(4, 4) IPFA_CASE(4, 8)
+    IPFA_CASE(8, 8) IPFA_CASE(8, 16)
+#undef IPFA_CASE
+    return IPFA_ERR_UNSUPPORTED;
+}
+
+static int launch_backtrace(const BacktraceParams &prm, int P, cudaStream_t stream) {
+    const int blocks = (prm.N + 3) / 4;
+    switch (P) {
+        case 1: ctc_viterbi_backtrace_kernel<1><<<blocks, 128, 0, stream>>>(prm); break;
+        case 2: ctc_viterbi_backtrace_kernel<2><<<blocks, 128, 0, stream>>>(prm); break;
+        case 4: ctc_viterbi_backtrace_kernel<4><<<blocks, 128, 0, stream>>>(prm); break;
+        case 8: ctc_viterbi_backtrace_kernel<8><<<blocks, 128, 0, stream>>>(prm); break;
+        default: return IPFA_ERR_UNSUPPORTED;
+    }
+    ++g_launch_count;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
+
+}  // namespace ipfa
+
+using namespace ipfa;
+
+extern "C" size_t ipfa_ctc_viterbi_workspace_bytes(int N, int Tmax, int Lmax, int V) {
+    (void)V;
+    LatticeShape s;
+    if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_shape(Lmax + 1, &s)) return 256;
+    const size_t bp = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s) * sizeof(uint32_t);
+    return ((bp + 255) & ~(size_t)255) + (((size_t)N * 4 + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_t stride_t,
+                                       const int32_t *targets, int64_t tgt_stride,
+                                       const int32_t *in_len, const int32_t *tgt_len, int N, int Tmax,
+                                       int Lmax, int V, int blank, int32_t *paths_out, float *scores_out,
+                                       int32_t *tok_start, int32_t *tok_end, float *tok_score,
+                                       float *total_out, int32_t *status_out, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+    if (N == 0) return IPFA_OK;
+    if (!lp || !in_len || !tgt_len || !paths_out || !status_out || N < 0 || Tmax < 0 || V <= 0 ||
+        Lmax < 0 || blank < 0 || blank >= V || (Lmax > 0 && !targets) || !workspace ||
+        ((tok_start == nullptr) != (tok_end == nullptr)))
+        return IPFA_ERR_INVALID_ARG;
+    LatticeShape s;
+    if (!pick_shape(Lmax + 1, &s)) return IPFA_ERR_UNSUPPORTED;
+    if (workspace_bytes < ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V)) return IPFA_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t wpw = viterbi_words_per_window(Tmax, s);
+    uint32_t *bp = static_cast<uint32_t *>(workspace);
+    const size_t bp_bytes = ((size_t)N * (size_t)wpw * sizeof(uint32_t) + 255) & ~(size_t)255;
+    int32_t *final_state = reinterpret_cast<int32_t *>(static_cast<unsigned char *>(workspace) + bp_bytes);
+
+    ViterbiParams fp{};
+    fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t;
+    fp.targets = targets; fp.tgt_stride = tgt_stride; fp.in_len = in_len; fp.tgt_len = tgt_len;
+    fp.N = N; fp.Tmax = Tmax; fp.V = V; fp.blank = blank;
+    fp.bp = bp; fp.words_per_window = wpw; fp.final_state = final_state;
+    fp.total_out = total_out; fp.status_out = status_out;
+    int rc = use_dense_panel(V, Lmax) ? dispatch_fill<true>(fp, Lmax, s, st)
+                                      : dispatch_fill<false>(fp, Lmax, s, st);
+    if (rc) return rc;
+
+    BacktraceParams bt{};
+    bt.lp = lp; bt.stride_n = stride_n; bt.stride_t = stride_t;
+    bt.targets = targets; bt.tgt_stride = tgt_stride; bt.in_len = in_len; bt.tgt_len = tgt_len;
+    bt.N = N; bt.Tmax = Tmax; bt.Lmax = Lmax; bt.V = V; bt.blank = blank; bt.NT = 32 * s.WARPS;
+    bt.bp = bp; bt.words_per_window = wpw; bt.final_state = final_state;
+    bt.paths_out = paths_out; bt.scores_out = scores_out;
+    bt.tok_start = tok_start; bt.tok_end = tok_end; bt.tok_score = tok_score;
+    return launch_backtrace(bt, s.P, st);
+}

@@ -1,0 +1,512 @@
+// ctcseg.cu -- kernel (2b): CTC-segmentation table fill, backtrace and
+// utterance scoring: the numerics behind `aligner.get_segments(task)`
+//   /root/reference/src/iterative_utterance_alignment.py:216
+//   /root/reference/src/word_level_alignment.py:100
+//   /root/reference/src/search_on_speech.py:85
+// i.e. ctc-segmentation==1.7.1 (/root/reference/requirements.txt:13; not vendored):
+//   cython_fill_table            -> ctcseg_fill_kernel       
+//   ctc_segmentation() backtrace -> ctcseg_backtrace_kernel  (A5)
+//   determine_utterance_segments -> same kernel, epilogue    (A6)
+//
+// Differences in STRUCTURE (results are identical):
+//  * the table is filled time-major (row t needs only row t-1) and never
+//    materialised: thread i keeps KC consecutive columns of the current row in
+//    registers; the one cross-thread value per frame (column c-1 of the previous
+//    thread) moves by __shfl_up / one shared word.
+//  * the reference's backtrace re-derives each transition from fp32 table
+//    differences ("|stay - est_stay| > |switch - est_switch|").  Every operand
+//    of that test is in registers when the cell is filled, so the test is
+//    evaluated THERE, with the same fp32 operations, and its outcome is stored
+//    as a 1-bit backpointer (bp[w][t / SPW][thread], 32/KC frames per word).
+//    The backtrace then only follows bits -- bit-identical decisions, 32x less
+//    HBM than the fp32 table.
+//  * one fill serves all utterance-prefixes of the text (the shrinking
+//    transcript iterations of iterative_utterance_alignment.py:203-385): the
+//    per-column first-argmax over t is tracked in registers, each prefix k is
+//    backtraced from (argmax_t table[:, utt_begin[k]], utt_begin[k]).
+// Full-table mode only (T <= min_window_size = 8000 frames); the windowed
+// variant is SURVEY.md section 8(f) rank 2.
+#include "emission_pipe.cuh"
+
+namespace ipfa {
+
+extern cudaError_t g_last_cuda_error;
+extern uint64_t g_launch_count;
+bool use_dense_panel(int V, int Lmax);
+
+constexpr float kProbMax = -1000000000.0f;  // cdef float prob_max = -1000000000
+
+struct SegFillParams {
+    const float *lp;
+    int64_t stride_n, stride_t;
+    const int32_t *in_len;
+    const int32_t *gt;
+    int64_t gt_stride;
+    const int32_t *n_cols;
+    int N, Tmax, Cmax, V, blank, flags;
+    int pitch, tc, u_cap;
+    size_t group_smem;
+    uint32_t *bp;
+    int64_t words_per_window;
+    int32_t *colarg;  // [N][Cmax] first argmax_t of every column
+};
+
+template <int KC, int WARPS, bool DENSE>
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
+ctcseg_fill_kernel(const SegFillParams prm) {
+    constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
+    constexpr int NT = 32 * WARPS;
+    constexpr int SPW = 32 / KC;  // frames per backpointer word
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
+    const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = (WARPS == 1) ? 0 : (threadIdx.x >> 5);
+    const int w = blockIdx.x * GROUPS + group;
+    if (w >= prm.N) return;
+
+    unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
+    float *ring = reinterpret_cast<float *>(gsm);
+    float *xch = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][WARPS]
+    int *cols = reinterpret_cast<int *>(xch + 2 * WARPS);       // [u_cap]
+
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int NC = max(0, min(prm.n_cols[w], prm.Cmax));
+    const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
+    const int blank = prm.blank;
+    const bool blank_cost_zero = prm.flags & IPFA_SEG_BLANK_COST_ZERO;
+    const bool preamble_cost_zero = prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO;
+    int32_t *colarg_w = prm.colarg + (int64_t)w * prm.Cmax;
+
+    if (T <= 0 || NC <= 0) {
+        for (int c = tid; c < prm.Cmax; c += NT) colarg_w[c] = -1;
+        return;
+    }
+
+    int col[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = tid * KC + k;
+        int g = (c >= 1 && c < NC) ? gt[c] : blank;
+        if (g < 0 || g >= prm.V) g = blank;
+        col[k] = DENSE ? g : ((c < NC) ? c : 0);
+    }
+    const int colb = DENSE ? blank : 0;
+    if constexpr (!DENSE) {
+        for (int j = tid; j < NC; j += NT) {
+            int g = (j == 0) ? blank : gt[j];
+            if (g < 0 || g >= prm.V) g = blank;
+            cols[j] = g;
+        }
+        group_sync<WARPS>();
+    }
+
+    EmissionPipe<WARPS, DENSE> pipe;
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, prm.pitch, prm.tc);
+    pipe.prologue(tid);
+
+    float val[KC], cmax[KC];
+    int carg[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = 0.0f; carg[k] = -1; }
+    uint32_t word = 0;
+    uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window + tid;
+
+    for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
+        const float *panel = pipe.acquire(chunk, tid);
+        const int t0 = chunk * pipe.tc;
+        const int rows = min(pipe.tc, T - t0);
+        for (int r = 0; r < rows; ++r) {
+            const float *row = panel + r * prm.pitch;
+            const float eb = row[colb];
+            float ec[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
+            const int t = t0 + r;
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int c = tid * KC + k;
+                    if (c == 0) {
+                        val[k] = 0.0f;  // table[0, 0] = 0; column 0's argmax scan starts at t = 1
+                    } else {
+                        val[k] = kProbMax;  // max(switch = prob_max, stay = prob_max)
+                        cmax[k] = kProbMax;
+                        carg[k] = 0;
+                    }
+                }
+            } else {
+                float prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
+                if constexpr (WARPS > 1) {
+                    if (lane == 0) prev = (warp > 0) ? xch[((t - 1) & 1) * WARPS + warp - 1] : kProbMax;
+                } else {
+                    if (lane == 0) prev = kProbMax;
+                }
+                uint32_t bits = 0;
+#pragma unroll
+                for (int k = KC - 1; k >= 0; --k) {
+                    const int c = tid * KC + k;
+                    const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
+                    const float up = val[k];                          // table[t-1, c]
+                    float v;
+                    uint32_t bit = 0;
+                    if (c == 0) {
+                        const float stay = preamble_cost_zero ? 0.0f : __fadd_rn(up, eb);
+                        v = fmaxf(kProbMax, stay);
+                    } else {
+                        const float sw = __fadd_rn(left, ec[k]);
+                        const float stay_p = fmaxf(eb, ec[k]);
+                        const float st = blank_cost_zero ? up : __fadd_rn(up, stay_p);
+                        v = fmaxf(sw, st);
+                        // the reference backtrace's transition test, on the same fp32 values
+                        const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left)));
+                        const float d_st = fabsf(__fsub_rn(stay_p, __fsub_rn(v, up)));
+                        bit = (d_st > d_sw) ? 1u : 0u;
+                    }
+                    val[k] = v;
+                    if (cmax[k] < v || carg[k] < 0) { cmax[k] = v; carg[k] = t; }
+                    bits |= bit << k;
+                }
+                word |= bits << ((t % SPW) * KC);
+            }
+            if ((t % SPW) == SPW - 1 || t == T - 1) {
+                bp_w[(int64_t)(t / SPW) * NT] = word;
+                word = 0;
+            }
+            if constexpr (WARPS > 1) {
+                if (lane == 31) xch[(t & 1) * WARPS + warp] = val[KC - 1];
+                __syncthreads();
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = tid * KC + k;
+        if (c < prm.Cmax) colarg_w[c] = (c < NC) ? carg[k] : -1;
+    }
+}
+
+// --- numpy-order float64 sums ------------------------------------------------
+// np.ndarray.mean on a contiguous float64 vector = pairwise sum (8 accumulators
+// for n <= 128, recursive halving above) / n.  char_probs is float64 holding
+// fp32 values; mirroring the order keeps the score bit-identical.
+__device__ double np_pairwise_sum(const float *a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = (double)a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], (double)a[i + j]);
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+}
+
+struct SegBackParams {
+    const float *lp;
+    int64_t stride_n, stride_t;
+    const int32_t *in_len;
+    const int32_t *gt;
+    int64_t gt_stride;
+    const int32_t *n_cols;
+    const int32_t *utt_begin;  // [N][Kmax+1]
+    const int32_t *n_utts;
+    int N, Tmax, Cmax, Kmax, V, blank, flags, NT, score_len;
+    double index_duration;
+    const uint32_t *bp;
+    int64_t words_per_window;
+    const int32_t *colarg;
+    double *seg_out;       // [N][Kmax][Kmax][3]
+    int32_t *term_t_out;   // [N][Kmax]
+    int32_t *timing;       // [N][Kmax][Cmax] (output or scratch)
+    float *char_prob;      // [N][Kmax][Tmax] (output or scratch)
+    int32_t *state_out;    // [N][Kmax][Tmax] nullable
+    int32_t *status_out;   // [N]
+};
+
+// One warp per (window, prefix).
+template <int KC>
+__global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackParams prm) {
+    constexpr int SPW = 32 / KC;   // frames per word
+    constexpr int NW = KC;         // words per 32-frame block
+    constexpr int NCOL = 32 / NW;  // thread-columns fetched per block
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= prm.N * prm.Kmax) return;
+    const int w = gw / prm.Kmax;
+    const int kslot = gw - w * prm.Kmax;  // prefix length k = kslot + 1
+    const int K = max(0, min(prm.n_utts[w], prm.Kmax));
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int NC = max(0, min(prm.n_cols[w], prm.Cmax));
+    const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+
+    if (kslot == 0 && lane == 0) prm.status_out[w] = (NC > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+
+    const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
+    const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
+    const float *lp = prm.lp + (int64_t)w * prm.stride_n;
+    const int64_t slot = (int64_t)w * prm.Kmax + kslot;
+    int32_t *timing = prm.timing + slot * prm.Cmax;
+    float *cprob = prm.char_prob + slot * prm.Tmax;
+    int32_t *state = prm.state_out ? prm.state_out + slot * prm.Tmax : nullptr;
+    double *seg = prm.seg_out + slot * prm.Kmax * 3;
+
+    const int c_end = ub[kslot + 1];  // terminal column of this prefix
+    for (int t = lane; t < prm.Tmax; t += 32) {
+        cprob[t] = 0.0f;
+        if (state) state[t] = -2;
+    }
+    for (int c = lane; c < prm.Cmax; c += 32) timing[c] = -1;
+    const bool feasible = T > 0 && c_end >= 1 && c_end < NC && c_end + 1 <= T;
+    int t_term = feasible ? prm.colarg[(int64_t)w * prm.Cmax + c_end] : -1;
+    if (lane == 0) prm.term_t_out[slot] = t_term;
+    if (!feasible || t_term < 0) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+        return;
+    }
+    __syncwarp();
+
+    // ---- walk the 1-bit backpointers from (t_term, c_end) to (0, 0) ----------
+    const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
+    const int NT = prm.NT;
+    int c = c_end;
+    for (int blk = t_term >> 5; blk >= 0; --blk) {
+        const int t_hi = min(t_term, blk * 32 + 31);
+        const int t_lo = blk * 32;
+        const int icur = c / KC;
+        const int my_col = icur - lane / NW;
+        const int my_word = blk * NW + (lane % NW);
+        uint32_t wreg = 0;
+        if (my_col >= 0 && (int64_t)my_word * SPW < T) wreg = bp_w[(int64_t)my_word * NT + my_col];
+        int my_c = -1, my_sw = 0;
+        for (int t = t_hi; t >= t_lo; --t) {
+            if (t == 0) break;  // (0, c): the loop `while t != 0 or c != 0` ends at (0, 0)
+            int sw = 0;
+            if (c > 0) {
+                const int i = c / KC, k = c - i * KC;
+                const int coff = icur - i;
+                const int widx = (t / SPW) - blk * NW;
+                uint32_t word;
+                if (coff < NCOL) word = __shfl_sync(0xffffffffu, wreg, coff * NW + widx);
+                else word = bp_w[(int64_t)(t / SPW) * NT + i];
+                sw = (word >> ((t % SPW) * KC + k)) & 1;
+            }
+            if (lane == (t & 31)) { my_c = c; my_sw = sw; }
+            c -= sw;
+        }
+        const int t = t_lo + lane;
+        if (t <= t_hi && t >= 1 && my_c >= 0) {
+            const float *row = lp + (int64_t)t * prm.stride_t;
+            const float eb = row[prm.blank];
+            float p;
+            if (my_c == 0) {
+                p = eb;
+            } else {
+                int g = gt[my_c];
+                if (g < 0 || g >= prm.V) g = prm.blank;
+                const float ec = row[g];
+                p = my_sw ? ec : fmaxf(eb, ec);
+                if (my_sw) timing[my_c] = t;
+            }
+            cprob[t] = p;
+            if (state) state[t] = my_sw ? my_c : -1;
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // ---- determine_utterance_segments ---------------------------------------
+    const double dur = prm.index_duration;
+    const int n = prm.score_len;
+    const bool round_nearest = prm.flags & IPFA_SEG_ROUND_NEAREST;
+    auto tm = [&](int cc) -> double {
+        if (cc < 0 || cc >= prm.Cmax) return 0.0;
+        const int f = timing[cc];
+        return f < 0 ? 0.0 : __dmul_rn((double)f, dur);
+    };
+    for (int u = 0; u <= kslot; ++u) {
+        const int b = ub[u], e = ub[u + 1];
+        const double mid_b = __ddiv_rn(__dadd_rn(tm(b), tm(b - 1)), 2.0);
+        const double start = fmax(__dadd_rn(tm(b + 1), -0.5), mid_b);
+        const double mid_e = __ddiv_rn(__dadd_rn(tm(e), tm(e - 1)), 2.0);
+        const double end = fmin(__dadd_rn(tm(e - 1), 0.5), mid_e);
+        const double qs = __ddiv_rn(start, dur), qe = __ddiv_rn(end, dur);
+        const long long s_t = (long long)(round_nearest ? rint(qs) : floor(qs));
+        const long long e_t = (long long)(round_nearest ? rint(qe) : floor(qe));
+        double score;
+        if (e_t <= s_t) {
+            score = -10000000000.0;
+        } else if (e_t - s_t <= n) {
+            const int lo = (int)max(0LL, min(s_t, (long long)T));
+            const int hi = (int)max(0LL, min(e_t, (long long)T));
+            const int cnt = hi - lo;
+            score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
+                              : __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            double best = 0.0;
+            bool has_nan = false;
+            for (long long t = s_t + lane; t < e_t - n; t += 32) {
+                const int lo = (int)max(0LL, min(t, (long long)T));
+                const int hi = (int)max(0LL, min(t + n, (long long)T));
+                const int cnt = hi - lo;
+                if (cnt <= 0) { has_nan = true; continue; }
+                const double m = __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt);
+                best = fmin(best, m);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, best, off);
+                best = fmin(best, o);
+            }
+            (void)has_nan;
+            score = best;
+        }
+        if (lane == 0) {
+            seg[u * 3] = start;
+            seg[u * 3 + 1] = end;
+            seg[u * 3 + 2] = score;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct SegShape { int KC, WARPS; };
+static bool pick_seg_shape(int cols, SegShape *s) {
+    static const SegShape shapes[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}, {8, 16}, {8, 32}};
+    for (const auto &c : shapes) {
+        if (32 * c.WARPS * c.KC >= cols) { *s = c; return true; }
+    }
+    return false;
+}
+static int64_t seg_words_per_window(int Tmax, SegShape s) {
+    const int spw = 32 / s.KC;
+    return (int64_t)((Tmax + spw - 1) / spw) * 32 * s.WARPS;
+}
+static inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <int KC, int WARPS, bool DENSE>
+static int launch_seg_fill(SegFillParams prm, cudaStream_t stream) {
+    constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
+    const int U = DENSE ? prm.V : prm.Cmax;
+    const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
+    PipeGeometry g = pipe_geometry(U, budget);
+    prm.pitch = g.pitch;
+    prm.tc = g.tc;
+    prm.u_cap = DENSE ? 0 : ((prm.Cmax + 3) & ~3);
+    size_t group_smem = g.ring_bytes + (2 * WARPS) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
+    group_smem = (group_smem + 15) & ~(size_t)15;
+    prm.group_smem = group_smem;
+    const size_t smem = group_smem * GROUPS;
+    auto kern = ctcseg_fill_kernel<KC, WARPS, DENSE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
+    const int blocks = (prm.N + GROUPS - 1) / GROUPS;
+    kern<<<blocks, threads, smem, stream>>>(prm);
+    ++g_launch_count;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
+
+template <bool DENSE>
+static int dispatch_seg_fill(const SegFillParams &prm, SegShape s, cudaStream_t stream) {
+#define IPFA_CASE(K_, W_) \
+    if (s.KC == K_ && s.WARPS == W_) return launch_seg_fill<K_, W_, DENSE>(prm, stream);
+    IPFA_CASE(1, 1) IPFA_CASE(2, 1) IPFA_CASE(4, 1) IPFA_CASE(4, 2) IPFA_CASE(4, 4) IPFA_CASE(4, 8)
+    IPFA_CASE(8, 8) IPFA_CASE(8, 16) IPFA_CASE(8, 32)
+#undef IPFA_CASE
+    return IPFA_ERR_UNSUPPORTED;
+}
+
+}  // namespace ipfa
+
+using namespace ipfa;
+
+extern "C" size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int V) {
+    (void)V;
+    SegShape s;
+    if (N <= 0 || Tmax < 0 || Cmax <= 0 || Kmax <= 0 || !pick_seg_shape(Cmax, &s)) return 256;
+    size_t b = pad256((size_t)N * (size_t)seg_words_per_window(Tmax, s) * 4);
+    b += pad256((size_t)N * Cmax * 4);                   // colarg
+    b += pad256((size_t)N * Kmax * (size_t)Cmax * 4);    // timing scratch
+    b += pad256((size_t)N * Kmax * (size_t)Tmax * 4);    // char_prob scratch
+    return b + 256;
+}
+
+extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t stride_t,
+                                  const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                                  const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+                                  int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+                                  double index_duration, int score_len, int flags, double *seg_out,
+                                  int32_t *term_t_out, int32_t *timing_out, float *char_prob_out,
+                                  int32_t *state_out, int32_t *status_out, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    if (N == 0) return IPFA_OK;
+    if (!lp || !in_len || !gt || !n_cols || !utt_begin || !n_utts || !seg_out || !term_t_out ||
+        !status_out || !workspace || N < 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || V <= 0 || blank < 0 ||
+        blank >= V || score_len <= 0 || !(index_duration > 0.0))
+        return IPFA_ERR_INVALID_ARG;
+    if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode: not built yet
+    SegShape s;
+    if (!pick_seg_shape(Cmax, &s)) return IPFA_ERR_UNSUPPORTED;
+    if (workspace_bytes < ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V)) return IPFA_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const int64_t wpw = seg_words_per_window(Tmax, s);
+    uint32_t *bp = reinterpret_cast<uint32_t *>(ws);
+    ws += pad256((size_t)N * (size_t)wpw * 4);
+    int32_t *colarg = reinterpret_cast<int32_t *>(ws);
+    ws += pad256((size_t)N * Cmax * 4);
+    int32_t *timing_scratch = reinterpret_cast<int32_t *>(ws);
+    ws += pad256((size_t)N * Kmax * (size_t)Cmax * 4);
+    float *cprob_scratch = reinterpret_cast<float *>(ws);
+
+    SegFillParams fp{};
+    fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t; fp.in_len = in_len;
+    fp.gt = gt; fp.gt_stride = gt_stride; fp.n_cols = n_cols;
+    fp.N = N; fp.Tmax = Tmax; fp.Cmax = Cmax; fp.V = V; fp.blank = blank; fp.flags = flags;
+    fp.bp = bp; fp.words_per_window = wpw; fp.colarg = colarg;
+    int rc = use_dense_panel(V, Cmax) ? dispatch_seg_fill<true>(fp, s, st) : dispatch_seg_fill<false>(fp, s, st);
+    if (rc) return rc;
+
+    SegBackParams bk{};
+    bk.lp = lp; bk.stride_n = stride_n; bk.stride_t = stride_t; bk.in_len = in_len;
+    bk.gt = gt; bk.gt_stride = gt_stride; bk.n_cols = n_cols; bk.utt_begin = utt_begin; bk.n_utts = n_utts;
+    bk.N = N; bk.Tmax = Tmax; bk.Cmax = Cmax; bk.Kmax = Kmax; bk.V = V; bk.blank = blank; bk.flags = flags;
+    bk.NT = 32 * s.WARPS; bk.score_len = score_len; bk.index_duration = index_duration;
+    bk.bp = bp; bk.words_per_window = wpw; bk.colarg = colarg;
+    bk.seg_out = seg_out; bk.term_t_out = term_t_out;
+    bk.timing = timing_out ? timing_out : timing_scratch;
+    bk.char_prob = char_prob_out ? char_prob_out : cprob_scratch;
+    bk.state_out = state_out; bk.status_out = status_out;
+    const int warps = N * Kmax;
+    const int blocks = (warps + 3) / 4;
+    switch (s.KC) {
+        case 1: ctcseg_backtrace_kernel<1><<<blocks, 128, 0, st>>>(bk); break;
+        case 2: ctcseg_backtrace_kernel<2><<<blocks, 128, 0, st>>>(bk); break;
+        case 4: ctcseg_backtrace_kernel<4><<<blocks, 128, 0, st>>>(bk); break;
+        case 8: ctcseg_backtrace_kernel<8><<<blocks, 128, 0, st>>>(bk); break;
+        default: return IPFA_ERR_UNSUPPORTED;
+    }
+    ++g_launch_count;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}

@@ -1,0 +1,116 @@
+// emission_pipe.cuh -- time-chunked staging of one window's emission columns
+// into shared memory (cp.async ring), shared by the alpha / Viterbi / ctcseg
+// lattice kernels.
+//
+// A "group" is the set of threads that owns one window: a single warp
+// (WARPS == 1, several windows per CTA, no CTA barrier anywhere) or the whole
+// CTA (WARPS > 1).  Two panel layouts:
+//   DENSE  : the panel row is the full vocabulary row lp[t, 0:V] (V small);
+//            16-byte cp.async when alignment allows, fully coalesced.
+//   gather : the panel row holds only the window's own columns,
+//            panel[t][j] = lp[t, cols[j]] with cols[0] = blank; 4-byte cp.async.
+#pragma once
+#include "ipfa_common.cuh"
+
+namespace ipfa {
+
+constexpr int kStages = 3;
+
+template <int WARPS>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (WARPS == 1) {
+        __syncwarp();
+    } else {
+        __syncthreads();
+    }
+}
+
+template <int WARPS, bool DENSE>
+struct EmissionPipe {
+    static constexpr int NT = 32 * WARPS;
+    float *ring;          // [kStages][tc][pitch]
+    const int *cols;      // smem column list (gather mode)
+    const float *base;    // &lp[w, 0, 0]
+    int64_t stride_t;
+    int T, U, V, pitch, tc, nchunks;
+    bool vec16;
+
+    __device__ __forceinline__ void init(float *ring_, const int *cols_, const float *base_,
+                                         int64_t stride_t_, int T_, int U_, int V_, int pitch_, int tc_) {
+        ring = ring_; cols = cols_; base = base_; stride_t = stride_t_;
+        T = T_; U = U_; V = V_; pitch = pitch_; tc = tc_;
+        nchunks = (T + tc - 1) / tc;
+        vec16 = DENSE && (V % 4 == 0) && (stride_t % 4 == 0) &&
+                ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    }
+
+    __device__ __forceinline__ float *stage_ptr(int chunk) const {
+        return ring + (size_t)(chunk % kStages) * tc * pitch;
+    }
+
+    // All threads of the group call this; always followed by a commit.
+    __device__ __forceinline__ void issue(int chunk, int tid) {
+        if (chunk < nchunks) {
+            float *dst = stage_ptr(chunk);
+            const int t0 = chunk * tc;
+            const int rows = min(tc, T - t0);
+            if constexpr (DENSE) {
+                if (vec16) {
+                    const int v4 = V >> 2;
+                    const int pieces = rows * v4;
+                    for (int q = tid; q < pieces; q += NT) {
+                        const int r = q / v4, c4 = q - r * v4;
+                        cp_async_16(dst + r * pitch + c4 * 4, base + (int64_t)(t0 + r) * stride_t + c4 * 4);
+                    }
+                } else {
+                    const int total = rows * V;
+                    for (int q = tid; q < total; q += NT) {
+                        const int r = q / V, c = q - r * V;
+                        cp_async_4(dst + r * pitch + c, base + (int64_t)(t0 + r) * stride_t + c);
+                    }
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const float *src = base + (int64_t)(t0 + r) * stride_t;
+                    float *d = dst + r * pitch;
+                    for (int j = tid; j < U; j += NT) cp_async_4(d + j, src + cols[j]);
+                }
+            }
+        }
+        cp_async_commit();
+    }
+
+    __device__ __forceinline__ void prologue(int tid) {
+#pragma unroll
+        for (int c = 0; c < kStages - 1; ++c) issue(c, tid);
+    }
+
+    // Make chunk `chunk` visible to the group and refill the stage freed by chunk-1.
+    __device__ __forceinline__ const float *acquire(int chunk, int tid) {
+        cp_async_wait<kStages - 2>();
+        group_sync<WARPS>();
+        issue(chunk + kStages - 1, tid);
+        return stage_ptr(chunk);
+    }
+};
+
+// Host-side sizing shared by the launchers.
+struct PipeGeometry {
+    int pitch;      // floats per panel row
+    int tc;         // frames per chunk
+    size_t ring_bytes;
+};
+
+inline PipeGeometry pipe_geometry(int U_panel, size_t budget_bytes) {
+    PipeGeometry g;
+    g.pitch = (U_panel + 3) & ~3;
+    size_t per_frame = (size_t)kStages * g.pitch * sizeof(float);
+    int tc = (int)(budget_bytes / per_frame);
+    if (tc > 32) tc = 32;
+    if (tc < 2) tc = 2;
+    g.tc = tc;
+    g.ring_bytes = per_frame * tc;
+    return g;
+}
+
+}  // namespace ipfa

@@ -1,0 +1,197 @@
+"""GPU parity of kernels (1) and (2a) against the pinned oracle and the committed
+torch / torchaudio golden vectors, through the C ABI (device and host entry points).
+
+Tolerances (BASELINE.json north_star): loss and confidences within 1e-4 relative
+in fp32; alignment paths, frame indices and per-frame scores bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+from cases import ctc_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ipfa():
+    import ipfa_b200
+    return ipfa_b200
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _check_nll(got, ref):
+    assert np.array_equal(np.isinf(got), np.isinf(ref)), (got, ref)
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_alpha_golden(ipfa, golden, name):
+    lp, tg = golden[f"{name}/lp"], golden[f"{name}/targets"]
+    il, tl = golden[f"{name}/in_len"], golden[f"{name}/tgt_len"]
+    nll = ipfa.ctc_alpha_nll(_dev(lp), _dev(tg), _dev(il), _dev(tl)).cpu().numpy()
+    _check_nll(nll, golden[f"{name}/nll"])
+    nll_h = ipfa.ctc_alpha_nll_host(lp, tg, il, tl)
+    assert np.array_equal(nll_h, nll, equal_nan=True)
+
+
+def test_alpha_empty_target(ipfa, golden):
+    lp = golden["empty/lp"]
+    n = lp.shape[0]
+    nll = ipfa.ctc_alpha_nll(_dev(lp), _dev(np.zeros((n, 0), np.int32)), _dev(golden["empty/in_len"]),
+                             _dev(np.zeros(n, np.int32))).cpu().numpy()
+    np.testing.assert_allclose(nll, golden["empty/nll"], rtol=1e-5)
+
+
+# (n, t, l, v, ragged, repeats, peaked): every (P, WARPS) lattice shape and both panel layouts
+ALPHA_SHAPES = [
+    (5, 40, 10, 32, True, True, False),       # P=1
+    (5, 90, 50, 32, True, True, False),       # P=2
+    (9, 300, 100, 32, False, False, False),   # P=4 (BASELINE config 2 lattice)
+    (3, 500, 200, 32, True, True, True),      # 2 warps
+    (3, 700, 400, 40, True, False, True),     # 4 warps
+    (2, 1200, 900, 48, True, False, True),    # 8 warps
+    (2, 400, 130, 700, True, True, True),     # gather panel, 2 warps
+    (3, 150, 60, 5000, True, True, False),    # gather panel, 1 warp (config 4 vocabulary)
+    (1, 2500, 1800, 64, False, False, True),  # P=8, 8 warps
+]
+
+
+@pytest.mark.parametrize("shape", ALPHA_SHAPES)
+def test_alpha_vs_oracle(ipfa, shape):
+    from oracle import ctc as octc
+    n, t, l, v, ragged, repeats, peaked = shape
+    lp, tg, il, tl = ctc_case(11, n, t, l, v, ragged, repeats, peaked)
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    nll = ipfa.ctc_alpha_nll(_dev(lp), _dev(tg), _dev(il), _dev(tl)).cpu().numpy()
+    _check_nll(nll, ref)
+
+
+def test_alpha_time_major_strides(ipfa):
+    """[T, N, V] input (torch ctc_loss layout) goes through strides, not a copy."""
+    import torch
+    from oracle import ctc as octc
+    lp, tg, il, tl = ctc_case(12, 6, 70, 20, 32, True, True)
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    lp_tm = torch.from_numpy(lp).cuda().transpose(0, 1).contiguous()
+    nll = ipfa.ctc_alpha_nll(lp_tm, _dev(tg), _dev(il), _dev(tl), batch_first=False).cpu().numpy()
+    _check_nll(nll, ref)
+
+
+def test_alpha_infeasible_and_zero_length(ipfa):
+    from oracle import ctc as octc
+    lp, tg, il, tl = ctc_case(13, 4, 6, 6, 5, repeats=True)
+    il = np.array([6, 3, 0, 6], np.int32)
+    tl = np.array([6, 6, 2, 0], np.int32)
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    nll = ipfa.ctc_alpha_nll(_dev(lp), _dev(tg), _dev(il), _dev(tl)).cpu().numpy()
+    _check_nll(nll, ref)
+
+
+def _check_viterbi(res, ref_paths, ref_scores, ref_status, in_len, to_np=lambda x: x.cpu().numpy()):
+    paths, scores, status = to_np(res.paths), to_np(res.scores), to_np(res.status)
+    assert np.array_equal(status & 1, ref_status), (status, ref_status)
+    for i in range(len(in_len)):
+        t = int(in_len[i])
+        if ref_status[i]:
+            assert np.all(paths[i] == -1)
+            continue
+        assert np.array_equal(paths[i, :t], ref_paths[i, :t]), i      # bit-exact
+        assert np.array_equal(scores[i, :t], ref_scores[i, :t]), i    # bit-exact fp32 gather
+        assert np.all(paths[i, t:] == -1)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_viterbi_golden(ipfa, golden, name):
+    lp, tg = golden[f"{name}/lp"], golden[f"{name}/targets"]
+    il, tl = golden[f"{name}/in_len"], golden[f"{name}/tgt_len"]
+    res = ipfa.ctc_forced_align(_dev(lp), _dev(tg), _dev(il), _dev(tl))
+    _check_viterbi(res, golden[f"{name}/paths"], golden[f"{name}/scores"], golden[f"{name}/fa_status"], il)
+    res_h = ipfa.ctc_forced_align_host(lp, tg, il, tl)
+    _check_viterbi(res_h, golden[f"{name}/paths"], golden[f"{name}/scores"], golden[f"{name}/fa_status"], il,
+                   to_np=lambda x: x)
+
+
+def test_viterbi_tie_rules(ipfa, golden):
+    """Exact ties resolve like torchaudio."""
+    for i in range(int(golden["ties/count"])):
+        lp = golden[f"ties/{i}/lp"][None]
+        tg = golden[f"ties/{i}/targets"][None]
+        res = ipfa.ctc_forced_align(_dev(lp), _dev(tg), [lp.shape[1]], [tg.shape[1]])
+        assert int(res.status[0]) == 0
+        assert np.array_equal(res.paths[0].cpu().numpy(), golden[f"ties/{i}/paths"]), i
+        assert np.array_equal(res.scores[0].cpu().numpy(), golden[f"ties/{i}/scores"]), i
+
+
+@pytest.mark.parametrize("shape", ALPHA_SHAPES)
+def test_viterbi_vs_oracle(ipfa, shape):
+    from oracle import ctc as octc
+    n, t, l, v, ragged, repeats, peaked = shape
+    lp, tg, il, tl = ctc_case(21, n, t, l, v, ragged, repeats, peaked)
+    ref_paths, ref_scores, ref_status = octc.ctc_viterbi(lp, tg, il, tl)
+    res = ipfa.ctc_forced_align(_dev(lp), _dev(tg), _dev(il), _dev(tl))
+    _check_viterbi(res, ref_paths, ref_scores, ref_status, il)
+    # token spans / confidences against merge_tokens on the oracle's path
+    ts, te, tp = res.tok_start.cpu().numpy(), res.tok_end.cpu().numpy(), res.tok_score.cpu().numpy()
+    total = res.total.cpu().numpy()
+    for i in range(n):
+        if ref_status[i]:
+            continue
+        ti, li = int(il[i]), int(tl[i])
+        spans = octc.merge_tokens(ref_paths[i, :ti], ref_scores[i, :ti])
+        # merge_tokens fuses a repeated label only across a blank, so spans == tokens
+        assert len(spans) == li
+        assert [s[1] for s in spans] == ts[i, :li].tolist()
+        assert [s[2] for s in spans] == te[i, :li].tolist()
+        np.testing.assert_allclose(tp[i, :li], [s[3] for s in spans], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(total[i], ref_scores[i, :ti].astype(np.float64).sum(), rtol=1e-4)
+
+
+def test_viterbi_tight_and_infeasible(ipfa):
+    """T == L + repeats (single feasible path) and T < L + repeats (rejected)."""
+    from oracle import ctc as octc
+    rng = np.random.default_rng(5)
+    n, l, v = 12, 9, 6
+    lp, tg, il, tl = ctc_case(31, n, 20, l, v, repeats=True)
+    rep = (tg[:, 1:] == tg[:, :-1]).sum(1)
+    il = (l + rep + rng.integers(-1, 2, n)).astype(np.int32)
+    ref_paths, ref_scores, ref_status = octc.ctc_viterbi(lp, tg, il, tl)
+    assert ref_status.any() and not ref_status.all()
+    res = ipfa.ctc_forced_align(_dev(lp), _dev(tg), _dev(il), _dev(tl))
+    _check_viterbi(res, ref_paths, ref_scores, ref_status, il)
+
+
+def test_full_size_config2_properties(ipfa):
+    """BASELINE config 2 at full size (1024 x T=1000 x L=100, V=32): size-independent
+    properties -- (i) the Viterbi path score never exceeds the total log-likelihood,
+    (ii) each path collapses to its target, (iii) frame scores sum to the path score,
+    (iv) a sample of windows matches the oracle."""
+    import torch
+    from oracle import ctc as octc
+    n, t, l, v = 1024, 1000, 100, 32
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lp = torch.randn(n, t, v, generator=g, device="cuda").log_softmax(-1)
+    tg = torch.randint(1, v, (n, l), generator=g, device="cuda", dtype=torch.int32)
+    il = torch.full((n,), t, dtype=torch.int32, device="cuda")
+    tl = torch.full((n,), l, dtype=torch.int32, device="cuda")
+    nll = ipfa.ctc_alpha_nll(lp, tg, il, tl)
+    res = ipfa.ctc_forced_align(lp, tg, il, tl)
+    assert torch.isfinite(nll).all() and int(res.status.abs().sum()) == 0
+    assert bool((res.total <= -nll + 1e-3).all())
+    np.testing.assert_allclose(res.scores.double().sum(1).cpu().numpy(), res.total.cpu().numpy(), rtol=1e-5)
+    paths = res.paths.cpu().numpy()
+    tgn = tg.cpu().numpy()
+    for i in range(0, n, 37):
+        p = paths[i]
+        keep = np.concatenate([[True], p[1:] != p[:-1]]) & (p != 0)
+        assert np.array_equal(p[keep], tgn[i])
+    idx = np.arange(0, n, 128)
+    lps = lp[idx].cpu().numpy()
+    ref = octc.ctc_alpha_nll(lps, tgn[idx], np.full(len(idx), t, np.int32), np.full(len(idx), l, np.int32))
+    _check_nll(nll[idx].cpu().numpy(), ref)
+    rp, rs, rst = octc.ctc_viterbi(lps, tgn[idx], np.full(len(idx), t, np.int32), np.full(len(idx), l, np.int32))
+    assert np.array_equal(paths[idx], rp)
