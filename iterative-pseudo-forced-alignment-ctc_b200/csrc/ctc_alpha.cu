@@ -17,6 +17,7 @@
 // The T-serial chain is MUFU/latency bound (2 ex2 + 1 lg2 per label state,
 // 1 + 1 per blank state), not HBM bound; see DESIGN.md.
 #include "emission_pipe.cuh"
+#include "lattice_shapes.cuh"
 
 namespace ipfa {
 
@@ -45,17 +46,15 @@ ctc_alpha_kernel(const AlphaParams prm) {
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int warp = (WARPS == 1) ? 0 : (threadIdx.x >> 5);
     int w = blockIdx.x * GROUPS + group;
     if (w >= prm.N) return;  // WARPS==1: whole warp leaves; WARPS>1: whole CTA leaves
     if (prm.order) w = prm.order[w];
 
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
-    float *xch = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][WARPS]
-    float *fin = xch + 2 * WARPS;                               // [2]
-    int *cols = reinterpret_cast<int *>(fin + 2);               // [u_cap] (gather mode)
+    float *xline = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][NT + 1] neighbour exchange (WARPS > 1)
+    float *fin = xline + 2 * (NT + 1);                            // [2]
+    int *cols = reinterpret_cast<int *>(fin + 2);                 // [u_cap] (gather mode)
 
     const int T = prm.in_len[w];
     const int L = max(0, min(prm.tgt_len[w], prm.l_cap));
@@ -70,19 +69,18 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // per-thread lattice constants
     int col[P];      // panel column of label_p
     bool skip[P];    // s-2 transition allowed into label_p
-    bool lab_ok[P];  // label state exists
-    bool blk_ok[P];  // blank state exists
     bool bad = false;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int j = tid * P + p;  // target index of this pair's label
-        lab_ok[p] = j < L;
-        blk_ok[p] = j <= L;
-        int lab = lab_ok[p] ? tg[j] : blank;
+        // States past the end of the target (j >= L) are left to run on garbage: they only
+        // feed states further right, never a real one, and every value stays finite.
+        const bool lab_ok = j < L;
+        int lab = lab_ok ? tg[j] : blank;
         if (lab < 0 || lab >= prm.V) { bad = true; lab = blank; }
-        const int prev = (j >= 1 && lab_ok[p]) ? tg[j - 1] : -1;
-        skip[p] = lab_ok[p] && j >= 1 && prev != lab;
-        col[p] = DENSE ? lab : (j + 1);
+        const int prev = (j >= 1 && lab_ok) ? tg[j - 1] : -1;
+        skip[p] = lab_ok && j >= 1 && prev != lab;
+        col[p] = DENSE ? lab : (lab_ok ? j + 1 : 0);
     }
     const int colb = DENSE ? blank : 0;
     if constexpr (!DENSE) {
@@ -91,8 +89,11 @@ ctc_alpha_kernel(const AlphaParams prm) {
             if (c < 0 || c >= prm.V) c = blank;
             cols[j] = c;
         }
-        group_sync<WARPS>();
     }
+    if constexpr (WARPS > 1) {
+        if (tid < 2) xline[tid * (NT + 1)] = kNegBig;  // left neighbour of thread 0: log(0)
+    }
+    group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
     pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, prm.pitch,
@@ -103,44 +104,74 @@ ctc_alpha_kernel(const AlphaParams prm) {
 #pragma unroll
     for (int p = 0; p < P; ++p) { ab[p] = kNegBig; al[p] = kNegBig; }
 
+    // One frame of the recursion.  `rd`/`wr`: this frame's read / write lines of the
+    // cross-warp exchange (WARPS > 1); inside a warp the neighbour comes by shuffle.
+    auto frame = [&](const float *row, const float *rd, float *wr) {
+        const float eb = row[colb];
+        float el[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) el[p] = row[col[p]];
+        float prev;
+        if constexpr (WARPS > 1) {
+            prev = rd[tid];
+        } else {
+            prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+            if (tid == 0) prev = kNegBig;
+        }
+#pragma unroll
+        for (int p = P - 1; p >= 0; --p) {
+            const float lm1 = (p == 0) ? prev : al[p - 1];
+            // blank_p <- lse(blank_p, label_{p-1});  label_p <- lse(label_p, blank_p [, label_{p-1}])
+            // and lse(blank_p, label_{p-1}) is shared between the two when the skip is allowed.
+            const float nb = lse2_2(ab[p], lm1);
+            const float x = skip[p] ? nb : ab[p];
+            al[p] = lse2_2(al[p], x) + el[p];
+            ab[p] = nb + eb;
+        }
+        if constexpr (WARPS > 1) {
+            wr[tid + 1] = al[P - 1];
+            __syncthreads();
+        }
+    };
+
+    float *line0 = xline, *line1 = xline + NT + 1;
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
-        const float *panel = pipe.acquire(chunk, tid);
+        float *panel = const_cast<float *>(pipe.acquire(chunk, tid));
         const int t0 = chunk * pipe.tc;
         const int rows = min(pipe.tc, T - t0);
-        for (int r = 0; r < rows; ++r) {
-            const float *row = panel + r * prm.pitch;
-            const float eb = fmaxf(row[colb] * kLog2e, kNegBig);
-            float el[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) el[p] = fmaxf(row[col[p]] * kLog2e, kNegBig);
-            const int t = t0 + r;
-            if (t == 0) {
-                if (tid == 0) {
-                    ab[0] = eb;
-                    if (lab_ok[0]) al[0] = el[0];
-                }
-            } else {
-                // previous thread's last label state at t-1
-                float prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
-                if constexpr (WARPS > 1) {
-                    if (lane == 0) prev = (warp > 0) ? xch[((t - 1) & 1) * WARPS + warp - 1] : kNegBig;
-                } else {
-                    if (lane == 0) prev = kNegBig;
-                }
-#pragma unroll
-                for (int p = P - 1; p >= 0; --p) {
-                    const float lm1 = (p == 0) ? prev : al[p - 1];
-                    const float nl = lse2_3(al[p], ab[p], skip[p] ? lm1 : kNegBig) + el[p];
-                    const float nb = lse2_2(ab[p], lm1) + eb;
-                    al[p] = lab_ok[p] ? nl : kNegBig;
-                    ab[p] = blk_ok[p] ? nb : kNegBig;
-                }
+        // in-place: natural log -> log2, clamp log(0) to the finite stand-in
+        {
+            float4 *p4 = reinterpret_cast<float4 *>(panel);
+            const int n4 = (rows * prm.pitch) >> 2;
+            for (int q = tid; q < n4; q += NT) {
+                float4 v = p4[q];
+                v.x = fmaxf(v.x * kLog2e, kNegBig); v.y = fmaxf(v.y * kLog2e, kNegBig);
+                v.z = fmaxf(v.z * kLog2e, kNegBig); v.w = fmaxf(v.w * kLog2e, kNegBig);
+                p4[q] = v;
+            }
+            group_sync<WARPS>();
+        }
+        int r = 0;
+        if (chunk == 0) {  // frame 0: only states 0 and 1 are alive
+            if (tid == 0) {
+                ab[0] = panel[colb];
+                if (L > 0) al[0] = panel[col[0]];
             }
             if constexpr (WARPS > 1) {
-                if (lane == 31) xch[(t & 1) * WARPS + warp] = al[P - 1];
+                line0[tid + 1] = al[P - 1];
                 __syncthreads();
             }
+            r = 1;
         }
+        // frame t reads line[(t-1)&1] and writes line[t&1]; tc is even, so r has t's parity
+        const float *row = panel + r * prm.pitch;
+        if ((r & 1) && r < rows) { frame(row, line0, line1); row += prm.pitch; ++r; }
+        for (; r + 1 < rows; r += 2) {
+            frame(row, line1, line0);
+            frame(row + prm.pitch, line0, line1);
+            row += 2 * prm.pitch;
+        }
+        if (r < rows) frame(row, line1, line0);
     }
 
     // final states 2L (blank of pair L) and 2L-1 (label of pair L-1)
@@ -166,19 +197,6 @@ ctc_alpha_kernel(const AlphaParams prm) {
 extern cudaError_t g_last_cuda_error;
 extern uint64_t g_launch_count;
 
-struct LatticeShape {
-    int P, WARPS;
-};
-
-// pairs = number of (blank,label) pairs to hold = Lmax + 1
-static bool pick_shape(int pairs, LatticeShape *s) {
-    static const LatticeShape shapes[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}, {8, 16}};
-    for (const auto &c : shapes) {
-        if (32 * c.WARPS * c.P >= pairs) { *s = c; return true; }
-    }
-    return false;
-}
-
 template <int P, int WARPS, bool DENSE>
 static int launch_alpha(AlphaParams prm, int Lmax, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
@@ -190,7 +208,7 @@ static int launch_alpha(AlphaParams prm, int Lmax, cudaStream_t stream) {
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
     prm.l_cap = Lmax;
-    size_t group_smem = g.ring_bytes + (2 * WARPS + 2) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
+    size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
@@ -208,11 +226,10 @@ static int launch_alpha(AlphaParams prm, int Lmax, cudaStream_t stream) {
 
 template <bool DENSE>
 static int dispatch_alpha(const AlphaParams &prm, int Lmax, LatticeShape s, cudaStream_t stream) {
-#define IPFA_CASE(P_, W_) \
-    if (s.P == P_ && s.WARPS == W_) return launch_alpha<P_, W_, DENSE>(prm, Lmax, stream);
-    IPFA_CASE(1, 1) IPFA_CASE(2, 1) IPFA_CASE(4, 1) IPFA_CASE(4, 2) IPFA_CASE(4, 4) IPFA_CASE(4, 8)
-    IPFA_CASE(8, 8) IPFA_CASE(8, 16)
-#undef IPFA_CASE
+#define IPFA_X(P_, W_) \
+    if (s.PER == P_ && s.WARPS == W_) return launch_alpha<P_, W_, DENSE>(prm, Lmax, stream);
+    IPFA_FOR_EACH_SHAPE(IPFA_X)
+#undef IPFA_X
     return IPFA_ERR_UNSUPPORTED;
 }
 
@@ -237,7 +254,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
         (Lmax > 0 && !targets))
         return IPFA_ERR_INVALID_ARG;
     LatticeShape s;
-    if (!pick_shape(Lmax + 1, &s)) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_ALPHA_SHAPE")) return IPFA_ERR_UNSUPPORTED;
     AlphaParams prm{};
     prm.lp = lp; prm.stride_n = stride_n; prm.stride_t = stride_t;
     prm.targets = targets; prm.tgt_stride = tgt_stride;

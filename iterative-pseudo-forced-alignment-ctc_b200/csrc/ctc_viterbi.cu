@@ -19,6 +19,7 @@
 // 4P words x (8/P) thread-columns it can possibly touch with ONE coalesced
 // load, then walks the block through warp shuffles.
 #include "emission_pipe.cuh"
+#include "lattice_shapes.cuh"
 
 namespace ipfa {
 
@@ -75,20 +76,20 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     group_sync<WARPS>();
 
     int col[P];
-    bool skip[P], lab_ok[P], blk_ok[P];
+    bool skip[P];
     int n_rep = 0, n_bad = 0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int j = tid * P + p;
-        lab_ok[p] = j < L;
-        blk_ok[p] = j <= L;
-        int lab = lab_ok[p] ? tg[j] : blank;
-        if (lab_ok[p] && (lab < 0 || lab >= prm.V || lab == blank)) ++n_bad;
+        // states past the end of the target run on garbage: nothing real reads them
+        const bool lab_ok = j < L;
+        int lab = lab_ok ? tg[j] : blank;
+        if (lab_ok && (lab < 0 || lab >= prm.V || lab == blank)) ++n_bad;
         if (lab < 0 || lab >= prm.V) lab = blank;
-        const int prev = (j >= 1 && lab_ok[p]) ? tg[j - 1] : -1;
-        skip[p] = lab_ok[p] && j >= 1 && prev != lab;
-        if (lab_ok[p] && j >= 1 && prev == lab) ++n_rep;
-        col[p] = DENSE ? lab : (j + 1);
+        const int prev = (j >= 1 && lab_ok) ? tg[j - 1] : -1;
+        skip[p] = lab_ok && j >= 1 && prev != lab;
+        if (lab_ok && j >= 1 && prev == lab) ++n_rep;
+        col[p] = DENSE ? lab : (lab_ok ? j + 1 : 0);
     }
     if (n_rep) atomicAdd(&cnt[0], n_rep);
     if (n_bad) atomicAdd(&cnt[1], n_bad);
@@ -140,7 +141,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
                     // torchaudio: start = (T - (L+R) > 0) ? 0 : 1 -- the leading blank is
                     // off every complete path when T == L+R; keeping it changes nothing.
                     ab[0] = eb;
-                    if (lab_ok[0]) al[0] = el[0];
+                    if (L > 0) al[0] = el[0];
                 }
             } else {
                 float prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
@@ -164,8 +165,8 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
                     // blank state: x0 stay, x1 from previous label
                     const uint32_t bb = (lm1 > ab[p]) ? 1u : 0u;
                     const float nb = (bb ? lm1 : ab[p]) + eb;
-                    al[p] = lab_ok[p] ? nl : NEG;
-                    ab[p] = blk_ok[p] ? nb : NEG;
+                    al[p] = nl;
+                    ab[p] = nb;
                     bits |= (bb | (bl << 2)) << (4 * p);
                 }
                 word |= bits << ((t % SPW) * 4 * P);
@@ -317,16 +318,8 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
 }
 
 // ---------------------------------------------------------------------------
-struct LatticeShape { int P, WARPS; };
-static bool pick_shape(int pairs, LatticeShape *s) {
-    static const LatticeShape shapes[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}, {8, 16}};
-    for (const auto &c : shapes) {
-        if (32 * c.WARPS * c.P >= pairs) { *s = c; return true; }
-    }
-    return false;
-}
 static int64_t viterbi_words_per_window(int Tmax, LatticeShape s) {
-    const int spw = 8 / s.P;
+    const int spw = 8 / s.PER;
     return (int64_t)((Tmax + spw - 1) / spw) * 32 * s.WARPS;
 }
 
@@ -359,11 +352,10 @@ static int launch_fill(ViterbiParams prm, int Lmax, cudaStream_t stream) {
 
 template <bool DENSE>
 static int dispatch_fill(const ViterbiParams &prm, int Lmax, LatticeShape s, cudaStream_t stream) {
-#define IPFA_CASE(P_, W_) \
-    if (s.P == P_ && s.WARPS == W_) return launch_fill<P_, W_, DENSE>(prm, Lmax, stream);
-    IPFA_CASE(1, 1) IPFA_CASE(2, 1) IPFA_CASE(4, 1) IPFA_CASE(4, 2) IPFA_CASE(4, 4) IPFA_CASE(4, 8)
-    IPFA_CASE(8, 8) IPFA_CASE(8, 16)
-#undef IPFA_CASE
+#define IPFA_X(P_, W_) \
+    if (s.PER == P_ && s.WARPS == W_) return launch_fill<P_, W_, DENSE>(prm, Lmax, stream);
+    IPFA_FOR_EACH_SHAPE(IPFA_X)
+#undef IPFA_X
     return IPFA_ERR_UNSUPPORTED;
 }
 
@@ -389,7 +381,7 @@ using namespace ipfa;
 extern "C" size_t ipfa_ctc_viterbi_workspace_bytes(int N, int Tmax, int Lmax, int V) {
     (void)V;
     LatticeShape s;
-    if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_shape(Lmax + 1, &s)) return 256;
+    if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE")) return 256;
     const size_t bp = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s) * sizeof(uint32_t);
     return ((bp + 255) & ~(size_t)255) + (((size_t)N * 4 + 255) & ~(size_t)255) + 256;
 }
@@ -407,7 +399,7 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
         ((tok_start == nullptr) != (tok_end == nullptr)))
         return IPFA_ERR_INVALID_ARG;
     LatticeShape s;
-    if (!pick_shape(Lmax + 1, &s)) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE")) return IPFA_ERR_UNSUPPORTED;
     if (workspace_bytes < ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V)) return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t wpw = viterbi_words_per_window(Tmax, s);
@@ -432,5 +424,5 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
     bt.bp = bp; bt.words_per_window = wpw; bt.final_state = final_state;
     bt.paths_out = paths_out; bt.scores_out = scores_out;
     bt.tok_start = tok_start; bt.tok_end = tok_end; bt.tok_score = tok_score;
-    return launch_backtrace(bt, s.P, st);
+    return launch_backtrace(bt, s.PER, st);
 }

@@ -27,6 +27,7 @@
 // Full-table mode only (T <= min_window_size = 8000 frames); the windowed
 // variant is SURVEY.md section 8(f) rank 2.
 #include "emission_pipe.cuh"
+#include "lattice_shapes.cuh"
 
 namespace ipfa {
 
@@ -386,16 +387,12 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
 }
 
 // ---------------------------------------------------------------------------
-struct SegShape { int KC, WARPS; };
-static bool pick_seg_shape(int cols, SegShape *s) {
-    static const SegShape shapes[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}, {8, 16}, {8, 32}};
-    for (const auto &c : shapes) {
-        if (32 * c.WARPS * c.KC >= cols) { *s = c; return true; }
-    }
-    return false;
+using SegShape = LatticeShape;
+static bool pick_seg_shape(int cols, int n_windows, SegShape *s) {
+    return pick_lattice_shape(cols, n_windows, s, "IPFA_SEG_SHAPE");
 }
 static int64_t seg_words_per_window(int Tmax, SegShape s) {
-    const int spw = 32 / s.KC;
+    const int spw = 32 / s.PER;
     return (int64_t)((Tmax + spw - 1) / spw) * 32 * s.WARPS;
 }
 static inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -427,11 +424,10 @@ static int launch_seg_fill(SegFillParams prm, cudaStream_t stream) {
 
 template <bool DENSE>
 static int dispatch_seg_fill(const SegFillParams &prm, SegShape s, cudaStream_t stream) {
-#define IPFA_CASE(K_, W_) \
-    if (s.KC == K_ && s.WARPS == W_) return launch_seg_fill<K_, W_, DENSE>(prm, stream);
-    IPFA_CASE(1, 1) IPFA_CASE(2, 1) IPFA_CASE(4, 1) IPFA_CASE(4, 2) IPFA_CASE(4, 4) IPFA_CASE(4, 8)
-    IPFA_CASE(8, 8) IPFA_CASE(8, 16) IPFA_CASE(8, 32)
-#undef IPFA_CASE
+#define IPFA_X(K_, W_) \
+    if (s.PER == K_ && s.WARPS == W_) return launch_seg_fill<K_, W_, DENSE>(prm, stream);
+    IPFA_FOR_EACH_SHAPE(IPFA_X)
+#undef IPFA_X
     return IPFA_ERR_UNSUPPORTED;
 }
 
@@ -442,7 +438,7 @@ using namespace ipfa;
 extern "C" size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int V) {
     (void)V;
     SegShape s;
-    if (N <= 0 || Tmax < 0 || Cmax <= 0 || Kmax <= 0 || !pick_seg_shape(Cmax, &s)) return 256;
+    if (N <= 0 || Tmax < 0 || Cmax <= 0 || Kmax <= 0 || !pick_seg_shape(Cmax, N, &s)) return 256;
     size_t b = pad256((size_t)N * (size_t)seg_words_per_window(Tmax, s) * 4);
     b += pad256((size_t)N * Cmax * 4);                   // colarg
     b += pad256((size_t)N * Kmax * (size_t)Cmax * 4);    // timing scratch
@@ -465,7 +461,7 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
         return IPFA_ERR_INVALID_ARG;
     if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode: not built yet
     SegShape s;
-    if (!pick_seg_shape(Cmax, &s)) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_seg_shape(Cmax, N, &s)) return IPFA_ERR_UNSUPPORTED;
     if (workspace_bytes < ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V)) return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -498,7 +494,7 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
     bk.state_out = state_out; bk.status_out = status_out;
     const int warps = N * Kmax;
     const int blocks = (warps + 3) / 4;
-    switch (s.KC) {
+    switch (s.PER) {
         case 1: ctcseg_backtrace_kernel<1><<<blocks, 128, 0, st>>>(bk); break;
         case 2: ctcseg_backtrace_kernel<2><<<blocks, 128, 0, st>>>(bk); break;
         case 4: ctcseg_backtrace_kernel<4><<<blocks, 128, 0, st>>>(bk); break;

@@ -107,6 +107,7 @@ inline PipeGeometry pipe_geometry(int U_panel, size_t budget_bytes) {
     size_t per_frame = (size_t)kStages * g.pitch * sizeof(float);
     int tc = (int)(budget_bytes / per_frame);
     if (tc > 32) tc = 32;
+    tc &= ~1;  // even: frame parity == row parity inside a chunk (double-buffered exchange lines)
     if (tc < 2) tc = 2;
     g.tc = tc;
     g.ring_bytes = per_frame * tc;

@@ -224,7 +224,7 @@ def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blan
     cmax = gt.shape[1]
     kmax = utt_begin.shape[1] - 1
     in_len, n_cols, n_utts = _i32(in_len, dev), _i32(n_cols, dev), _i32(n_utts, dev)
-    seg = torch.empty((n, kmax, kmax, 3), dtype=torch.float64, device=dev)
+    seg = torch.full((n, kmax, kmax, 3), float("nan"), dtype=torch.float64, device=dev)
     term_t = torch.empty((n, kmax), dtype=torch.int32, device=dev)
     status = torch.empty(n, dtype=torch.int32, device=dev)
     if details:

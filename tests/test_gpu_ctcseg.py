@@ -108,9 +108,10 @@ def test_all_prefixes_vs_oracle(ipfa, shape):
     res_h = ipfa.ctcseg_align_host(lp, in_len, gt, n_cols, ubs, n_utts, cfg.index_duration,
                                    score_len=score_len, flags=flags)
     for i in range(n):
-        k = int(n_utts[i])
-        assert np.array_equal(res_h.seg[i, :k], to_np(res.seg)[i, :k], equal_nan=True)
-        assert np.array_equal(res_h.timing[i, :k], to_np(res.timing)[i, :k])
+        for k in range(1, int(n_utts[i]) + 1):
+            assert np.array_equal(res_h.seg[i, k - 1, :k], to_np(res.seg)[i, k - 1, :k])
+            assert np.array_equal(res_h.timing[i, k - 1], to_np(res.timing)[i, k - 1])
+            assert np.array_equal(res_h.char_prob[i, k - 1], to_np(res.char_prob)[i, k - 1])
 
 
 def test_flags_and_unpeaked(ipfa):
