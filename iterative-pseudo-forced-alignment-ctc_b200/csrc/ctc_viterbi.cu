@@ -55,15 +55,13 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int warp = (WARPS == 1) ? 0 : (threadIdx.x >> 5);
     const int w = blockIdx.x * GROUPS + group;
     if (w >= prm.N) return;
 
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
-    float *xch = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][WARPS]
-    float *fin = xch + 2 * WARPS;                               // [2]
+    float *xline = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][NT + 1] neighbour exchange
+    float *fin = xline + 2 * (NT + 1);                            // [2]
     int *cnt = reinterpret_cast<int *>(fin + 2);                // [2] repeats, bad labels
     int *cols = cnt + 2;                                        // [u_cap]
 
@@ -72,7 +70,10 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     const int32_t *tg = prm.targets + (int64_t)w * prm.tgt_stride;
     const int blank = prm.blank;
 
-    if (tid < 2) cnt[tid] = 0;
+    if (tid < 2) {
+        cnt[tid] = 0;
+        if constexpr (WARPS > 1) xline[tid * (NT + 1)] = NEG;  // left neighbour of thread 0
+    }
     group_sync<WARPS>();
 
     int col[P];
@@ -123,64 +124,87 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
 #pragma unroll
     for (int p = 0; p < P; ++p) { ab[p] = NEG; al[p] = NEG; }
     uint32_t word = 0;
-    uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window + tid;
+    int shift = 0;  // bit position of the current frame inside `word`
+    uint32_t *bp_ptr = prm.bp + (int64_t)w * prm.words_per_window + tid;
 
+    auto push_bits = [&](uint32_t bits) {
+        word |= bits << shift;
+        shift += 4 * P;
+        if (shift == 32) {
+            *bp_ptr = word;
+            bp_ptr += NT;
+            word = 0;
+            shift = 0;
+        }
+    };
+
+    auto frame = [&](const float *row, const float *rd, float *wr) {
+        const float eb = row[colb];
+        float el[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) el[p] = row[col[p]];
+        float prev;
+        if constexpr (WARPS > 1) {
+            prev = rd[tid];
+        } else {
+            prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+            if (tid == 0) prev = NEG;
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int p = P - 1; p >= 0; --p) {
+            const float lm1 = (p == 0) ? prev : al[p - 1];
+            // label state: x0 stay, x1 from blank, x2 skip (torchaudio's strict comparisons)
+            const float x0 = al[p], x1 = ab[p], x2 = skip[p] ? lm1 : NEG;
+            float res;
+            uint32_t bl;
+            if (x2 > x1 && x2 > x0) { res = x2; bl = 2; }
+            else if (x1 > x0 && x1 > x2) { res = x1; bl = 1; }
+            else { res = x0; bl = 0; }
+            // blank state: x0 stay, x1 from previous label
+            const uint32_t bb = (lm1 > ab[p]) ? 1u : 0u;
+            const float nb = (bb ? lm1 : ab[p]) + eb;
+            al[p] = res + el[p];
+            ab[p] = nb;
+            bits |= (bb | (bl << 2)) << (4 * p);
+        }
+        push_bits(bits);
+        if constexpr (WARPS > 1) {
+            wr[tid + 1] = al[P - 1];
+            __syncthreads();
+        }
+    };
+
+    float *line0 = xline, *line1 = xline + NT + 1;
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
         const float *panel = pipe.acquire(chunk, tid);
         const int t0 = chunk * pipe.tc;
         const int rows = min(pipe.tc, T - t0);
-        for (int r = 0; r < rows; ++r) {
-            const float *row = panel + r * prm.pitch;
-            const float eb = row[colb];
-            float el[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) el[p] = row[col[p]];
-            const int t = t0 + r;
-            if (t == 0) {
-                if (tid == 0) {
-                    // torchaudio: start = (T - (L+R) > 0) ? 0 : 1 -- the leading blank is
-                    // off every complete path when T == L+R; keeping it changes nothing.
-                    ab[0] = eb;
-                    if (L > 0) al[0] = el[0];
-                }
-            } else {
-                float prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
-                if constexpr (WARPS > 1) {
-                    if (lane == 0) prev = (warp > 0) ? xch[((t - 1) & 1) * WARPS + warp - 1] : NEG;
-                } else {
-                    if (lane == 0) prev = NEG;
-                }
-                uint32_t bits = 0;
-#pragma unroll
-                for (int p = P - 1; p >= 0; --p) {
-                    const float lm1 = (p == 0) ? prev : al[p - 1];
-                    // label state: x0 stay, x1 from blank, x2 skip
-                    const float x0 = al[p], x1 = ab[p], x2 = skip[p] ? lm1 : NEG;
-                    float res;
-                    uint32_t bl;
-                    if (x2 > x1 && x2 > x0) { res = x2; bl = 2; }
-                    else if (x1 > x0 && x1 > x2) { res = x1; bl = 1; }
-                    else { res = x0; bl = 0; }
-                    const float nl = res + el[p];
-                    // blank state: x0 stay, x1 from previous label
-                    const uint32_t bb = (lm1 > ab[p]) ? 1u : 0u;
-                    const float nb = (bb ? lm1 : ab[p]) + eb;
-                    al[p] = nl;
-                    ab[p] = nb;
-                    bits |= (bb | (bl << 2)) << (4 * p);
-                }
-                word |= bits << ((t % SPW) * 4 * P);
+        int r = 0;
+        if (chunk == 0) {
+            if (tid == 0) {
+                // torchaudio: start = (T - (L+R) > 0) ? 0 : 1 -- the leading blank is off every
+                // complete path when T == L+R; keeping it changes nothing.
+                ab[0] = panel[colb];
+                if (L > 0) al[0] = panel[col[0]];
             }
-            if ((t % SPW) == SPW - 1 || t == T - 1) {
-                bp_w[(int64_t)(t / SPW) * NT] = word;
-                word = 0;
-            }
+            push_bits(0);
             if constexpr (WARPS > 1) {
-                if (lane == 31) xch[(t & 1) * WARPS + warp] = al[P - 1];
+                line0[tid + 1] = al[P - 1];
                 __syncthreads();
             }
+            r = 1;
         }
+        const float *row = panel + r * prm.pitch;
+        if ((r & 1) && r < rows) { frame(row, line0, line1); row += prm.pitch; ++r; }
+        for (; r + 1 < rows; r += 2) {
+            frame(row, line1, line0);
+            frame(row + prm.pitch, line0, line1);
+            row += 2 * prm.pitch;
+        }
+        if (r < rows) frame(row, line1, line0);
     }
+    if (shift != 0) *bp_ptr = word;
 
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -333,7 +357,7 @@ static int launch_fill(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
     prm.l_cap = Lmax;
-    size_t group_smem = g.ring_bytes + (2 * WARPS + 2) * sizeof(float) + 2 * sizeof(int) +
+    size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2) * sizeof(float) + 2 * sizeof(int) +
                         (size_t)prm.u_cap * sizeof(int);
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;

@@ -62,15 +62,13 @@ ctcseg_fill_kernel(const SegFillParams prm) {
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int warp = (WARPS == 1) ? 0 : (threadIdx.x >> 5);
     const int w = blockIdx.x * GROUPS + group;
     if (w >= prm.N) return;
 
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
-    float *xch = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][WARPS]
-    int *cols = reinterpret_cast<int *>(xch + 2 * WARPS);       // [u_cap]
+    float *xline = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][NT + 1] neighbour exchange
+    int *cols = reinterpret_cast<int *>(xline + 2 * (NT + 1));    // [u_cap]
 
     const int T = min(prm.in_len[w], prm.Tmax);
     const int NC = max(0, min(prm.n_cols[w], prm.Cmax));
@@ -100,8 +98,11 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             if (g < 0 || g >= prm.V) g = blank;
             cols[j] = g;
         }
-        group_sync<WARPS>();
     }
+    if constexpr (WARPS > 1) {
+        if (tid < 2) xline[tid * (NT + 1)] = kProbMax;  // "column -1": switch into column 0 is prob_max
+    }
+    group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
     pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, prm.pitch, prm.tc);
@@ -112,75 +113,99 @@ ctcseg_fill_kernel(const SegFillParams prm) {
 #pragma unroll
     for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = 0.0f; carg[k] = -1; }
     uint32_t word = 0;
-    uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window + tid;
+    int shift = 0;
+    uint32_t *bp_ptr = prm.bp + (int64_t)w * prm.words_per_window + tid;
+    int t = 0;
 
+    auto push_bits = [&](uint32_t bits) {
+        word |= bits << shift;
+        shift += KC;
+        if (shift == 32) {
+            *bp_ptr = word;
+            bp_ptr += NT;
+            word = 0;
+            shift = 0;
+        }
+    };
+
+    auto frame = [&](const float *row, const float *rd, float *wr) {
+        const float eb = row[colb];
+        float ec[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
+        float prev;
+        if constexpr (WARPS > 1) {
+            prev = rd[tid];
+        } else {
+            prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
+            if (tid == 0) prev = kProbMax;
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = KC - 1; k >= 0; --k) {
+            const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
+            const float up = val[k];                          // table[t-1, c]
+            const float sw = __fadd_rn(left, ec[k]);
+            const float stay_p = fmaxf(eb, ec[k]);
+            const float st = blank_cost_zero ? up : __fadd_rn(up, stay_p);
+            float v = fmaxf(sw, st);
+            // the reference backtrace's transition test, on the same fp32 values
+            const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left)));
+            const float d_st = fabsf(__fsub_rn(stay_p, __fsub_rn(v, up)));
+            uint32_t bit = (d_st > d_sw) ? 1u : 0u;
+            if (k == 0 && tid == 0) {  // column 0 (ground truth -1): stay only
+                const float stay0 = preamble_cost_zero ? 0.0f : __fadd_rn(up, eb);
+                v = fmaxf(kProbMax, stay0);
+                bit = 0;
+            }
+            val[k] = v;
+            if (cmax[k] < v || carg[k] < 0) { cmax[k] = v; carg[k] = t; }
+            bits |= bit << k;
+        }
+        push_bits(bits);
+        ++t;
+        if constexpr (WARPS > 1) {
+            wr[tid + 1] = val[KC - 1];
+            __syncthreads();
+        }
+    };
+
+    float *line0 = xline, *line1 = xline + NT + 1;
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
         const float *panel = pipe.acquire(chunk, tid);
-        const int t0 = chunk * pipe.tc;
-        const int rows = min(pipe.tc, T - t0);
-        for (int r = 0; r < rows; ++r) {
-            const float *row = panel + r * prm.pitch;
-            const float eb = row[colb];
-            float ec[KC];
+        const int rows = min(pipe.tc, T - chunk * pipe.tc);
+        int r = 0;
+        if (chunk == 0) {
+            // t = 0: table[0, 0] = 0 (column 0's argmax scan starts at t = 1);
+            // every other column is max(switch = prob_max, stay = prob_max)
 #pragma unroll
-            for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
-            const int t = t0 + r;
-            if (t == 0) {
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const int c = tid * KC + k;
-                    if (c == 0) {
-                        val[k] = 0.0f;  // table[0, 0] = 0; column 0's argmax scan starts at t = 1
-                    } else {
-                        val[k] = kProbMax;  // max(switch = prob_max, stay = prob_max)
-                        cmax[k] = kProbMax;
-                        carg[k] = 0;
-                    }
-                }
-            } else {
-                float prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
-                if constexpr (WARPS > 1) {
-                    if (lane == 0) prev = (warp > 0) ? xch[((t - 1) & 1) * WARPS + warp - 1] : kProbMax;
+            for (int k = 0; k < KC; ++k) {
+                if (tid * KC + k == 0) {
+                    val[k] = 0.0f;
                 } else {
-                    if (lane == 0) prev = kProbMax;
+                    val[k] = kProbMax;
+                    cmax[k] = kProbMax;
+                    carg[k] = 0;
                 }
-                uint32_t bits = 0;
-#pragma unroll
-                for (int k = KC - 1; k >= 0; --k) {
-                    const int c = tid * KC + k;
-                    const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
-                    const float up = val[k];                          // table[t-1, c]
-                    float v;
-                    uint32_t bit = 0;
-                    if (c == 0) {
-                        const float stay = preamble_cost_zero ? 0.0f : __fadd_rn(up, eb);
-                        v = fmaxf(kProbMax, stay);
-                    } else {
-                        const float sw = __fadd_rn(left, ec[k]);
-                        const float stay_p = fmaxf(eb, ec[k]);
-                        const float st = blank_cost_zero ? up : __fadd_rn(up, stay_p);
-                        v = fmaxf(sw, st);
-                        // the reference backtrace's transition test, on the same fp32 values
-                        const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left)));
-                        const float d_st = fabsf(__fsub_rn(stay_p, __fsub_rn(v, up)));
-                        bit = (d_st > d_sw) ? 1u : 0u;
-                    }
-                    val[k] = v;
-                    if (cmax[k] < v || carg[k] < 0) { cmax[k] = v; carg[k] = t; }
-                    bits |= bit << k;
-                }
-                word |= bits << ((t % SPW) * KC);
             }
-            if ((t % SPW) == SPW - 1 || t == T - 1) {
-                bp_w[(int64_t)(t / SPW) * NT] = word;
-                word = 0;
-            }
+            push_bits(0);
+            t = 1;
             if constexpr (WARPS > 1) {
-                if (lane == 31) xch[(t & 1) * WARPS + warp] = val[KC - 1];
+                line0[tid + 1] = val[KC - 1];
                 __syncthreads();
             }
+            r = 1;
         }
+        const float *row = panel + r * prm.pitch;
+        if ((r & 1) && r < rows) { frame(row, line0, line1); row += prm.pitch; ++r; }
+        for (; r + 1 < rows; r += 2) {
+            frame(row, line1, line0);
+            frame(row + prm.pitch, line0, line1);
+            row += 2 * prm.pitch;
+        }
+        if (r < rows) frame(row, line1, line0);
     }
+    if (shift != 0) *bp_ptr = word;
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int c = tid * KC + k;
@@ -406,7 +431,7 @@ static int launch_seg_fill(SegFillParams prm, cudaStream_t stream) {
     prm.pitch = g.pitch;
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((prm.Cmax + 3) & ~3);
-    size_t group_smem = g.ring_bytes + (2 * WARPS) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
+    size_t group_smem = g.ring_bytes + 2 * (32 * WARPS + 1) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;

@@ -11,9 +11,13 @@ cudaError_t g_last_cuda_error = cudaSuccess;
 uint64_t g_launch_count = 0;
 
 namespace {
+constexpr int kMaxChunks = 32;
+
 struct Arena {
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // copy-in stream (H2D)
+    cudaStream_t compute = nullptr;   // kernels + D2H
+    cudaEvent_t ready[kMaxChunks] = {};
     unsigned char *base = nullptr;
     size_t cap = 0, used = 0;
 
@@ -21,9 +25,15 @@ struct Arena {
         if (!stream) {
             cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
             if (e != cudaSuccess) { g_last_cuda_error = e; stream = nullptr; return IPFA_ERR_CUDA; }
+            e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking);
+            if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+            for (int i = 0; i < kMaxChunks; ++i) {
+                e = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming);
+                if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+            }
         }
         if (bytes > cap) {
-            if (base) { cudaStreamSynchronize(stream); cudaFree(base); base = nullptr; cap = 0; }
+            if (base) { cudaStreamSynchronize(stream); cudaStreamSynchronize(compute); cudaFree(base); base = nullptr; cap = 0; }
             size_t want = bytes + (bytes >> 3) + (1 << 20);
             cudaError_t e = cudaMalloc(&base, want);
             if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
@@ -58,6 +68,17 @@ int upload_lp(float *dst, const float *src, int64_t stride_n, int N, int64_t per
                                     per_window * sizeof(float), N, cudaMemcpyHostToDevice, st));
     }
     return IPFA_OK;
+}
+
+// Windows per chunk of the host pipeline: H2D of chunk i+1 overlaps the kernels of chunk i.
+// ~16 MB of emissions per chunk keeps every copy at full PCIe rate and every launch wide.
+int windows_per_chunk(int N, int64_t per_window_floats) {
+    const int64_t bytes = per_window_floats * 4;
+    int64_t c = bytes > 0 ? (16LL << 20) / bytes : N;
+    if (c < 1) c = 1;
+    if (c * kMaxChunks < N) c = (N + kMaxChunks - 1) / kMaxChunks;
+    if (c > N) c = N;
+    return (int)c;
 }
 }  // namespace
 }  // namespace ipfa
@@ -108,18 +129,25 @@ extern "C" int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t st
     int32_t *d_tl = g_arena.take<int32_t>(N);
     float *d_out = g_arena.take<float>(N);
     void *d_ws = g_arena.take<unsigned char>(ws);
-    rc = upload_lp(d_lp, lp, stride_n, N, per_window, st);
-    if (rc) return rc;
     if (Lmax > 0)
         IPFA_CUDA(cudaMemcpy2DAsync(d_tg, (size_t)Lmax * 4, targets, (size_t)tgt_stride * 4, (size_t)Lmax * 4,
                                     N, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_il, in_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_tl, tgt_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    rc = ipfa_ctc_alpha_device(d_lp, per_window, V, d_tg, Lmax, d_il, d_tl, N, Tmax, Lmax, V, blank, d_out,
-                               d_ws, ws, st);
-    if (rc) return rc;
-    IPFA_CUDA(cudaMemcpyAsync(nll_out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-    IPFA_CUDA(cudaStreamSynchronize(st));
+    const int C = windows_per_chunk(N, per_window);
+    cudaStream_t cs = g_arena.compute;
+    for (int w0 = 0, ci = 0; w0 < N; w0 += C, ++ci) {
+        const int n = (N - w0 < C) ? (N - w0) : C;
+        rc = upload_lp(d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
+        if (rc) return rc;
+        IPFA_CUDA(cudaEventRecord(g_arena.ready[ci], st));
+        IPFA_CUDA(cudaStreamWaitEvent(cs, g_arena.ready[ci], 0));
+        rc = ipfa_ctc_alpha_device(d_lp + (int64_t)w0 * per_window, per_window, V, d_tg + (int64_t)w0 * Lmax, Lmax,
+                                   d_il + w0, d_tl + w0, n, Tmax, Lmax, V, blank, d_out + w0, d_ws, ws, cs);
+        if (rc) return rc;
+    }
+    IPFA_CUDA(cudaMemcpyAsync(nll_out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost, cs));
+    IPFA_CUDA(cudaStreamSynchronize(cs));
     return IPFA_OK;
 }
 
@@ -135,7 +163,15 @@ extern "C" int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t 
         return IPFA_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(g_arena.mu);
     const int64_t per_window = (int64_t)Tmax * V;
-    const size_t ws = ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V);
+    size_t ws = ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V);
+    {   // chunks may pick a lattice shape with a different backpointer pitch
+        const int c = windows_per_chunk(N, per_window);
+        const size_t ws_c = ipfa_ctc_viterbi_workspace_bytes(c, Tmax, Lmax, V);
+        const int tail = N % c;
+        const size_t ws_t = tail ? ipfa_ctc_viterbi_workspace_bytes(tail, Tmax, Lmax, V) : 0;
+        if (ws_c > ws) ws = ws_c;
+        if (ws_t > ws) ws = ws_t;
+    }
     const size_t lcap = (size_t)(Lmax > 0 ? Lmax : 1);
     size_t need = pad256((size_t)N * per_window * 4) + pad256((size_t)N * lcap * 4) * 4 +
                   4 * pad256((size_t)N * 4) + 2 * pad256((size_t)N * Tmax * 4) + pad256(ws) + 4096;
@@ -154,30 +190,40 @@ extern "C" int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t 
     float *d_total = g_arena.take<float>(N);
     int32_t *d_status = g_arena.take<int32_t>(N);
     void *d_ws = g_arena.take<unsigned char>(ws);
-    rc = upload_lp(d_lp, lp, stride_n, N, per_window, st);
-    if (rc) return rc;
     if (Lmax > 0)
         IPFA_CUDA(cudaMemcpy2DAsync(d_tg, (size_t)Lmax * 4, targets, (size_t)tgt_stride * 4, (size_t)Lmax * 4,
                                     N, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_il, in_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_tl, tgt_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     const bool tok = tok_start != nullptr && Lmax > 0;
-    rc = ipfa_ctc_viterbi_device(d_lp, per_window, V, d_tg, Lmax, d_il, d_tl, N, Tmax, Lmax, V, blank, d_paths,
-                                 scores_out ? d_scores : nullptr, tok ? d_ts : nullptr, tok ? d_te : nullptr,
-                                 (tok && tok_score) ? d_tp : nullptr, d_total, d_status, d_ws, ws, st);
-    if (rc) return rc;
-    IPFA_CUDA(cudaMemcpyAsync(paths_out, d_paths, (size_t)N * Tmax * 4, cudaMemcpyDeviceToHost, st));
-    if (scores_out)
-        IPFA_CUDA(cudaMemcpyAsync(scores_out, d_scores, (size_t)N * Tmax * 4, cudaMemcpyDeviceToHost, st));
-    if (tok) {
-        IPFA_CUDA(cudaMemcpyAsync(tok_start, d_ts, (size_t)N * Lmax * 4, cudaMemcpyDeviceToHost, st));
-        IPFA_CUDA(cudaMemcpyAsync(tok_end, d_te, (size_t)N * Lmax * 4, cudaMemcpyDeviceToHost, st));
-        if (tok_score)
-            IPFA_CUDA(cudaMemcpyAsync(tok_score, d_tp, (size_t)N * Lmax * 4, cudaMemcpyDeviceToHost, st));
+    const int C = windows_per_chunk(N, per_window);
+    cudaStream_t cs = g_arena.compute;
+    for (int w0 = 0, ci = 0; w0 < N; w0 += C, ++ci) {
+        const int n = (N - w0 < C) ? (N - w0) : C;
+        const int64_t ot = (int64_t)w0 * Tmax, ol = (int64_t)w0 * Lmax;
+        rc = upload_lp(d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
+        if (rc) return rc;
+        IPFA_CUDA(cudaEventRecord(g_arena.ready[ci], st));
+        IPFA_CUDA(cudaStreamWaitEvent(cs, g_arena.ready[ci], 0));
+        rc = ipfa_ctc_viterbi_device(d_lp + (int64_t)w0 * per_window, per_window, V, d_tg + ol, Lmax, d_il + w0,
+                                     d_tl + w0, n, Tmax, Lmax, V, blank, d_paths + ot,
+                                     scores_out ? d_scores + ot : nullptr, tok ? d_ts + ol : nullptr,
+                                     tok ? d_te + ol : nullptr, (tok && tok_score) ? d_tp + ol : nullptr,
+                                     d_total + w0, d_status + w0, d_ws, ws, cs);
+        if (rc) return rc;
+        IPFA_CUDA(cudaMemcpyAsync(paths_out + ot, d_paths + ot, (size_t)n * Tmax * 4, cudaMemcpyDeviceToHost, cs));
+        if (scores_out)
+            IPFA_CUDA(cudaMemcpyAsync(scores_out + ot, d_scores + ot, (size_t)n * Tmax * 4, cudaMemcpyDeviceToHost, cs));
     }
-    if (total_out) IPFA_CUDA(cudaMemcpyAsync(total_out, d_total, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-    IPFA_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-    IPFA_CUDA(cudaStreamSynchronize(st));
+    if (tok) {
+        IPFA_CUDA(cudaMemcpyAsync(tok_start, d_ts, (size_t)N * Lmax * 4, cudaMemcpyDeviceToHost, cs));
+        IPFA_CUDA(cudaMemcpyAsync(tok_end, d_te, (size_t)N * Lmax * 4, cudaMemcpyDeviceToHost, cs));
+        if (tok_score)
+            IPFA_CUDA(cudaMemcpyAsync(tok_score, d_tp, (size_t)N * Lmax * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    if (total_out) IPFA_CUDA(cudaMemcpyAsync(total_out, d_total, (size_t)N * 4, cudaMemcpyDeviceToHost, cs));
+    IPFA_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, cs));
+    IPFA_CUDA(cudaStreamSynchronize(cs));
     return IPFA_OK;
 }
 
