@@ -1,22 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the alignment hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|seg] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2v|c3|c4|seg] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic emissions.
 Default workload = BASELINE.json configs[1] ("c2"): batched CTC-loss window
 scoring, 1024 candidate windows x T=1000 frames x L=100 labels, V=32, fp32.
-Weak scaling: every rank scores its own 1024-window shard (windows are
-independent; no data-path collective -- SURVEY.md section 8(e)).
+Weak scaling: every rank processes its own shard of independent windows (no
+data-path collective -- SURVEY.md section 8(e)); after the timed region the
+per-window results are gathered once over NCCL and checked.
 
 value      whole-job aligned audio-hours/s (20 ms per frame, alignment_utils.py:87
            of the reference) with the emissions already resident in HBM
 e2e        same metric through the host-buffer C-ABI call (ipfa_*_host): pinned
-           host emissions -> H2D -> kernel -> D2H of the scores, every step
-roofline   algorithmic bytes of the dominant kernel / its CUDA-event duration,
+           host emissions -> H2D -> kernels -> D2H of the results, every step
+roofline   algorithmic bytes of the step's kernels / their CUDA-event duration,
            against MEASURED_PEAKS.json's HBM copy bandwidth
-cpu_baseline  the CPU restatement (oracle/, OpenMP over windows) and the installed
-           torch CPU comparator on a bounded sample of the same workload
+cpu_baseline  the CPU restatement (oracle/) and, where it exists, the installed
+           torch / torchaudio CPU comparator, on a bounded sample of the workload,
+           using every host core
 
 --impl reference times the CPU path only (rank 0; other ranks exit 0).
 """
@@ -34,20 +36,6 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FRAME_SECONDS = 0.02
-
-WORKLOADS = {
-    # name: (kind, windows, T, L, V, ragged)
-    "c2": ("alpha", 1024, 1000, 100, 32, False),
-    "c3": ("viterbi", 65536, 500, 40, 32, True),
-    "c4": ("alpha", 256, 3000, 400, 5000, False),
-    "c2v": ("viterbi", 1024, 1000, 100, 32, False),
-}
-WORKLOAD_TEXT = {
-    "c2": "BASELINE configs[1]: batched CTC-loss window scoring, 1024 windows x T=1000 x L=100, V=32, fp32",
-    "c3": "BASELINE configs[2]: Viterbi forced align + backtrace, 65536 utterances, T<=500, L<=40, V=32",
-    "c4": "BASELINE configs[3]: long-window large-vocab scoring, 256 windows x T=3000 x L=400, V=5000",
-    "c2v": "configs[1] shapes through the Viterbi + backtrace path",
-}
 
 
 def peaks():
@@ -95,7 +83,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def result(self):
         if not self.samples:
@@ -104,123 +92,287 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_inputs(workload, seed, device=None):
-    """Synthetic log-softmax emissions + targets."""
-    import torch
-    kind, n, t, l, v, ragged = WORKLOADS[workload]
-    g = torch.Generator(device=device or "cpu").manual_seed(seed)
-    lp = torch.randn(n, t, v, generator=g, device=device or "cpu", dtype=torch.float32)
-    lp = torch.log_softmax(lp, dim=-1)
-    tg = torch.randint(1, v, (n, l), generator=g, device=device or "cpu", dtype=torch.int32)
-    if ragged:
-        il = torch.randint(t // 2, t + 1, (n,), generator=g, device=device or "cpu", dtype=torch.int32)
-        tl = torch.randint(l // 2, l + 1, (n,), generator=g, device=device or "cpu", dtype=torch.int32)
-    else:
-        il = torch.full((n,), t, dtype=torch.int32, device=device or "cpu")
-        tl = torch.full((n,), l, dtype=torch.int32, device=device or "cpu")
-    return lp, tg, il, tl
+# ----------------------------------------------------------------------------- workloads
+class CtcWorkload:
+    """kind 'alpha' (kernel 1) or 'viterbi' (kernel 2a) on the 2L+1 lattice."""
+
+    def __init__(self, name, kind, n, t, l, v, ragged, text):
+        self.name, self.kind, self.n, self.t, self.l, self.v, self.ragged, self.text = \
+            name, kind, n, t, l, v, ragged, text
+        self.api = "ipfa_ctc_alpha_host" if kind == "alpha" else "ipfa_ctc_viterbi_host"
+        self.set_bytes = n * t * v * 4
+        self.shape = {"windows_per_gpu": n, "T": t, "L": l, "V": v}
+
+    def make(self, seed, device=None, n=None):
+        import torch
+        n = n or self.n
+        dev = device or "cpu"
+        g = torch.Generator(device=dev).manual_seed(seed)
+        lp = torch.log_softmax(torch.randn(n, self.t, self.v, generator=g, device=dev), dim=-1)
+        tg = torch.randint(1, self.v, (n, self.l), generator=g, device=dev, dtype=torch.int32)
+        if self.ragged:
+            il = torch.randint(self.t // 2, self.t + 1, (n,), generator=g, device=dev, dtype=torch.int32)
+            tl = torch.randint(self.l // 2, self.l + 1, (n,), generator=g, device=dev, dtype=torch.int32)
+        else:
+            il = torch.full((n,), self.t, dtype=torch.int32, device=dev)
+            tl = torch.full((n,), self.l, dtype=torch.int32, device=dev)
+        return lp, tg, il, tl
+
+    def units(self, inputs):
+        il = inputs[2].cpu().numpy().astype(np.int64)
+        tl = inputs[3].cpu().numpy().astype(np.int64)
+        cells = int((il * (2 * tl + 1)).sum())
+        hours = float(il.sum()) * FRAME_SECONDS / 3600.0
+        read = int((il * np.minimum(tl + 1, self.v) * 4 + tl * 4).sum())
+        if self.kind == "alpha":
+            write = 4 * len(il)
+        else:  # 2-bit backpointers written once and read once + paths + frame scores
+            write = int((2 * ((il * (2 * tl + 1) * 2 + 7) // 8) + il * 8).sum())
+        return cells, hours, read + write
+
+    def step(self, ipfa, inputs):
+        lp, tg, il, tl = inputs
+        if self.kind == "alpha":
+            return ipfa.ctc_alpha_nll(lp, tg, il, tl)
+        return ipfa.ctc_forced_align(lp, tg, il, tl, tokens=False).total
+
+    def to_host(self, inputs):
+        import torch
+        host = [x.cpu().pin_memory().numpy() for x in inputs]
+        n, t = self.n, self.t
+        if self.kind == "alpha":
+            out = {"out": torch.empty(n, dtype=torch.float32).pin_memory().numpy()}
+        else:
+            out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in
+                   (("paths", (n, t), torch.int32), ("scores", (n, t), torch.float32),
+                    ("total", (n,), torch.float32), ("status", (n,), torch.int32))}
+        return host, out
+
+    def e2e_step(self, ipfa, host, out):
+        lp, tg, il, tl = host
+        if self.kind == "alpha":
+            return ipfa.ctc_alpha_nll_host(lp, tg, il, tl, out=out["out"])
+        return ipfa.ctc_forced_align_host(lp, tg, il, tl, tokens=False, out=out)
+
+    def traffic(self):
+        h2d = int(self.set_bytes + self.n * self.l * 4 + 8 * self.n)
+        d2h = int(4 * self.n if self.kind == "alpha" else (8 * self.n * self.t + 8 * self.n))
+        return h2d, d2h
+
+    # CPU legs: name -> callable(k windows); sample arrays prepared once
+    def cpu_setup(self):
+        import torch
+        cap = max(8, min(self.n, (1 << 26) // (self.t * self.v)))
+        lp, tg, il, tl = self.make(1234, n=cap)
+        self._cpu = (lp, tg, il, tl, lp.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+        torch.set_num_threads(os.cpu_count() or 1)
+        return cap
+
+    def cpu_legs(self):
+        import torch
+        from oracle import ctc as octc
+        lp, tg, il, tl, lp_np, tg_np, il_np, tl_np = self._cpu
+
+        def run_oracle(k):
+            if self.kind == "alpha":
+                octc.ctc_alpha_nll(lp_np[:k], tg_np[:k], il_np[:k], tl_np[:k])
+            else:
+                octc.ctc_viterbi(lp_np[:k], tg_np[:k], il_np[:k], tl_np[:k])
+
+        def run_torch(k):
+            if self.kind == "alpha":
+                torch.nn.functional.ctc_loss(lp[:k].transpose(0, 1), tg[:k].long(), il[:k].long(),
+                                             tl[:k].long(), blank=0, reduction="none")
+            else:
+                import torchaudio.functional as AF
+                for i in range(k):
+                    AF.forced_align(lp[i:i + 1, :int(il[i])], tg[i:i + 1, :int(tl[i])].long(), blank=0)
+
+        return {"oracle_port": run_oracle, "torch_cpu": run_torch}
+
+    def cpu_units(self, k):
+        il, tl = self._cpu[6][:k].astype(np.int64), self._cpu[7][:k].astype(np.int64)
+        return float((il * (2 * tl + 1)).sum()), float(il.sum()) * FRAME_SECONDS / 3600.0
 
 
-def work_units(workload, il, tl):
-    """(cells, audio-hours, algorithmic bytes) of one step of one rank."""
-    kind, n, t, l, v, _ = WORKLOADS[workload]
-    il = il.cpu().numpy().astype(np.int64)
-    tl = tl.cpu().numpy().astype(np.int64)
-    cells = int((il * (2 * tl + 1)).sum())
-    hours = float(il.sum()) * FRAME_SECONDS / 3600.0
-    read = int((il * np.minimum(tl + 1, v) * 4 + tl * 4).sum())
-    if kind == "alpha":
-        write = 4 * n
-    else:  # 2-bit backpointers written once and read once + paths + frame scores
-        write = int((2 * ((il * (2 * tl + 1) * 2 + 7) // 8) + il * 8).sum())
-    return cells, hours, read + write
+def _seg_cpu_worker(args):
+    """One window through the reference's algorithm on the CPU (fill in C, backtrace and
+    scoring interpreted, like ctc-segmentation itself)."""
+    from oracle import ctcseg as oseg
+    lp, gt, ub = args
+    cfg = oseg.CtcSegmentationParameters(index_duration=FRAME_SECONDS)
+    oseg.get_segments(cfg, lp, gt.reshape(-1, 1).astype(np.int64), ub.tolist(), [""] * (len(ub) - 1))
+    return 0
+
+
+class SegWorkload:
+    """kind 'seg': one anchor-loop iteration for N files in flight (BASELINE configs[4] unit of
+    work): CTC-segmentation fill + every-prefix backtrace/scoring + on-device selection on
+    70 s windows (T = 3500 frames, the reference's max_window_size) with K utterances."""
+
+    kind = "seg"
+    api = "ipfa_ctcseg_host"
+
+    def __init__(self, name, n, t, k, tokens, v, text):
+        self.name, self.n, self.t, self.k, self.tokens, self.v, self.text = name, n, t, k, tokens, v, text
+        self.set_bytes = n * t * v * 4
+        self.cols = 2 + k * (tokens + 1)
+        self.shape = {"windows_per_gpu": n, "T": t, "K": k, "columns": self.cols, "V": v}
+
+    def make(self, seed, device=None, n=None):
+        import torch
+        n = n or self.n
+        dev = device or "cpu"
+        g = torch.Generator(device=dev).manual_seed(seed)
+        lp = torch.log_softmax(torch.randn(n, self.t, self.v, generator=g, device=dev), dim=-1)
+        toks = torch.randint(1, self.v, (n, self.k, self.tokens), generator=g, device=dev, dtype=torch.int32)
+        gt = torch.zeros((n, self.cols), dtype=torch.int32, device=dev)
+        gt[:, 0] = -1
+        ub = torch.zeros((n, self.k + 1), dtype=torch.int32, device=dev)
+        for u in range(self.k):  # -1, (blank, tokens)*, blank
+            b = 1 + u * (self.tokens + 1)
+            ub[:, u] = b
+            gt[:, b + 1:b + 1 + self.tokens] = toks[:, u]
+        ub[:, self.k] = self.cols - 1
+        il = torch.full((n,), self.t, dtype=torch.int32, device=dev)
+        nc = torch.full((n,), self.cols, dtype=torch.int32, device=dev)
+        nu = torch.full((n,), self.k, dtype=torch.int32, device=dev)
+        tlen = torch.full((n, self.k), 60, dtype=torch.int32, device=dev)
+        last = torch.zeros(n, dtype=torch.int32, device=dev)
+        return lp, il, gt, nc, ub, nu, tlen, last
+
+    def units(self, inputs):
+        cells = int(self.n) * self.t * self.cols
+        hours = self.n * self.t * FRAME_SECONDS / 3600.0
+        read = self.n * self.t * min(self.cols, self.v) * 4 + self.n * self.cols * 4
+        bp = 2 * ((self.n * self.t * self.cols + 7) // 8)  # 1-bit backpointers, written + read once
+        out = self.n * self.k * self.k * 24 + self.n * self.k * self.t * 4
+        return cells, hours, read + bp + out
+
+    def step(self, ipfa, inputs):
+        lp, il, gt, nc, ub, nu, tlen, last = inputs
+        res = ipfa.ctcseg_align(lp, il, gt, nc, ub, nu, FRAME_SECONDS, flags=2 | 8, details=False)
+        dec, anchor = ipfa.anchor_select(res.seg, nu, tlen, last)
+        return dec
+
+    def to_host(self, inputs):
+        host = [x.cpu().pin_memory().numpy() for x in inputs[:6]]
+        return host, {}
+
+    def e2e_step(self, ipfa, host, out):
+        lp, il, gt, nc, ub, nu = host
+        return ipfa.ctcseg_align_host(lp, il, gt, nc, ub, nu, FRAME_SECONDS, flags=2 | 8, details=False)
+
+    def traffic(self):
+        return int(self.set_bytes + self.n * (self.cols + self.k + 4) * 4), int(self.n * self.k * self.k * 24 +
+                                                                              self.n * (self.k + 1) * 4)
+
+    def cpu_setup(self):
+        cap = min(self.n, 4 * (os.cpu_count() or 1))
+        lp, il, gt, nc, ub, nu, _, _ = self.make(1234, n=cap)
+        self._cpu = (lp.numpy(), gt.numpy(), ub.numpy())
+        return cap
+
+    def cpu_legs(self):
+        import multiprocessing as mp
+        lp, gt, ub = self._cpu
+        cores = os.cpu_count() or 1
+        pool = mp.get_context("fork").Pool(cores)
+        self._pool = pool
+
+        def run_oracle(k):
+            pool.map(_seg_cpu_worker, [(lp[i], gt[i], ub[i]) for i in range(k)], chunksize=1)
+
+        return {"oracle_port": run_oracle}
+
+    def cpu_units(self, k):
+        return float(k) * self.t * self.cols, k * self.t * FRAME_SECONDS / 3600.0
+
+
+WORKLOADS = {
+    "c2": CtcWorkload("c2", "alpha", 1024, 1000, 100, 32, False,
+                      "BASELINE configs[1]: batched CTC-loss window scoring, 1024 windows x T=1000 x L=100, V=32, fp32"),
+    "c2v": CtcWorkload("c2v", "viterbi", 1024, 1000, 100, 32, False,
+                       "configs[1] shapes through the Viterbi + backtrace path"),
+    "c3": CtcWorkload("c3", "viterbi", 65536, 500, 40, 32, True,
+                      "BASELINE configs[2]: Viterbi forced align + backtrace, 65536 utterances, T<=500, L<=40, V=32"),
+    "c4": CtcWorkload("c4", "alpha", 256, 3000, 400, 5000, False,
+                      "BASELINE configs[3]: long-window large-vocab scoring, 256 windows x T=3000 x L=400, V=5000"),
+    "seg": SegWorkload("seg", 256, 3500, 6, 150, 32,
+                       "BASELINE configs[4] unit: anchor-loop iteration for 256 files in flight, 70 s windows "
+                       "(T=3500), 6 utterances x 150 chars, all prefixes + on-device selection, V=32"),
+}
 
 
 # ----------------------------------------------------------------------------- CPU legs
-def cpu_leg(workload, budget_s, steps=1, warmup=0):
-    """Times the CPU restatement (oracle/) and torch's CPU comparator on a bounded
-    sample of the workload.  Returns a dict with audio-h/s figures."""
-    import torch
-    from oracle import ctc as octc
-    kind, n, t, l, v, ragged = WORKLOADS[workload]
-    lp, tg, il, tl = make_inputs(workload, 1234) if n * t * v <= (1 << 26) else (None,) * 4
-    if lp is None:  # keep host memory bounded for the big workloads
-        g = torch.Generator().manual_seed(1234)
-        ns = max(8, (1 << 26) // (t * v))
-        lp = torch.log_softmax(torch.randn(ns, t, v, generator=g), dim=-1)
-        tg = torch.randint(1, v, (ns, l), generator=g, dtype=torch.int32)
-        il = torch.full((ns,), t, dtype=torch.int32)
-        tl = torch.full((ns,), l, dtype=torch.int32)
+def cpu_leg(wl, budget_s, steps=1, warmup=0):
+    """Times the CPU path(s) on a bounded sample of the workload, all host cores."""
+    cap = wl.cpu_setup()
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    lp_np, tg_np, il_np, tl_np = lp.numpy(), tg.numpy(), il.numpy(), tl.numpy()
-
-    def run_oracle(k):
-        if kind == "alpha":
-            octc.ctc_alpha_nll(lp_np[:k], tg_np[:k], il_np[:k], tl_np[:k])
-        else:
-            octc.ctc_viterbi(lp_np[:k], tg_np[:k], il_np[:k], tl_np[:k])
-
-    def run_torch(k):
-        if kind == "alpha":
-            torch.nn.functional.ctc_loss(lp[:k].transpose(0, 1), tg[:k].long(), il[:k].long(), tl[:k].long(),
-                                         blank=0, reduction="none")
-        else:
-            import torchaudio.functional as AF
-            for i in range(k):
-                AF.forced_align(lp[i:i + 1, :int(il[i])], tg[i:i + 1, :int(tl[i])].long(), blank=0)
-
-    out = {}
-    n_avail = lp.shape[0]
-    for name, fn in (("oracle_port", run_oracle), ("torch_cpu", run_torch)):
+    out = {"cores": cores}
+    for name, fn in wl.cpu_legs().items():
         try:
-            probe = min(n_avail, max(cores, 16))
+            probe = min(cap, max(cores, 16))
             fn(probe)  # warm-up (thread pools, page faults)
             t0 = time.perf_counter()
             fn(probe)
             per_window = (time.perf_counter() - t0) / probe
             total_steps = max(steps + warmup, 1)
-            k = int(min(n_avail, max(probe, budget_s / total_steps / max(per_window, 1e-9))))
+            k = int(min(cap, max(probe, budget_s / total_steps / max(per_window, 1e-9))))
             for _ in range(warmup):
                 fn(k)
             t0 = time.perf_counter()
             for _ in range(max(steps, 1)):
                 fn(k)
             dt = (time.perf_counter() - t0) / max(steps, 1)
-            hours = float(il_np[:k].astype(np.int64).sum()) * FRAME_SECONDS / 3600.0
-            cells = float((il_np[:k].astype(np.int64) * (2 * tl_np[:k].astype(np.int64) + 1)).sum())
+            cells, hours = wl.cpu_units(k)
             out[name] = {"audio_h_per_s": hours / dt, "cells_per_s": cells / dt, "windows": k,
                          "seconds_per_step": dt}
-        except Exception as exc:  # torchaudio may be absent on some box
+        except Exception as exc:  # e.g. torchaudio absent on some box
             out[name] = {"error": repr(exc)}
-    out["cores"] = cores
-    out["oracle_threads"] = octc.num_threads()
+    if getattr(wl, "_pool", None) is not None:
+        wl._pool.terminate()
+    try:
+        from oracle import ctc as octc
+        out["oracle_threads"] = octc.num_threads()
+    except Exception:
+        pass
     return out
 
 
+def best_cpu(legs):
+    names = [k for k in ("oracle_port", "torch_cpu") if k in legs and "audio_h_per_s" in legs[k]]
+    best = max(names, key=lambda k: legs[k]["audio_h_per_s"])
+    return best, legs[best]
+
+
+def cpu_baseline_obj(legs, what):
+    name, best = best_cpu(legs)
+    obj = {"value": best["audio_h_per_s"], "unit": "audio-h/s", "cores": legs["cores"],
+           "kind": "port" if name == "oracle_port" else "reference",
+           "sample": f"{best['windows']} windows of the workload per step ({what}); fastest CPU leg: {name}"}
+    for k in ("oracle_port", "torch_cpu"):
+        if k in legs:
+            obj[k] = legs[k]
+    return obj
+
+
 def reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    legs = cpu_leg(args.workload, budget_s=150.0, steps=args.steps, warmup=args.warmup)
-    best_name = max((k for k in ("oracle_port", "torch_cpu") if "audio_h_per_s" in legs[k]),
-                    key=lambda k: legs[k]["audio_h_per_s"])
-    best = legs[best_name]
-    kind = WORKLOADS[args.workload][0]
+    wl = WORKLOADS[args.workload]
+    legs = cpu_leg(wl, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    name, best = best_cpu(legs)
+    what = ("oracle/ restatement of ctc-segmentation: C fill + interpreted backtrace/scoring, one process per core"
+            if wl.kind == "seg" else
+            "OpenMP C restatement (oracle/) vs installed torch/torchaudio CPU comparator north_star names")
     line = {
         "impl": "reference", "metric": "aligned_audio_hours_per_s", "value": best["audio_h_per_s"],
         "unit": "audio-h/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": best["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[args.workload], "kernel": kind},
-        "cells_per_s": best["cells_per_s"],
-        "cpu_baseline": {
-            "value": best["audio_h_per_s"], "unit": "audio-h/s", "cores": legs["cores"],
-            "kind": "port" if best_name == "oracle_port" else "reference",
-            "sample": f"{best['windows']} windows of the workload per step; faster of the OpenMP C "
-                      f"restatement (oracle/) and the installed torch/torchaudio CPU comparator "
-                      f"north_star names -- here: {best_name}",
-            "oracle_port": legs["oracle_port"], "torch_cpu": legs["torch_cpu"]},
+        "config": {"workload": wl.text, "kernel": wl.kind},
+        "cells_per_s": best["cells_per_s"], "cpu_baseline": cpu_baseline_obj(legs, what),
         "e2e": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -245,18 +397,11 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    kind, n, t, l, v, ragged = WORKLOADS[args.workload]
-    # rotate over several distinct input sets so no step finds its emissions in L2
-    set_bytes = n * t * v * 4
-    n_sets = max(2, min(8, int(np.ceil(3 * 126e6 / set_bytes)))) if set_bytes < 2e9 else 1
-    sets = [make_inputs(args.workload, 1000 * rank + s, device=dev) for s in range(n_sets)]
-    cells, hours, alg_bytes = work_units(args.workload, sets[0][2], sets[0][3])
-
-    def step(i):
-        lp, tg, il, tl = sets[i % n_sets]
-        if kind == "alpha":
-            return ipfa.ctc_alpha_nll(lp, tg, il, tl)
-        return ipfa.ctc_forced_align(lp, tg, il, tl, tokens=False).paths
+    wl = WORKLOADS[args.workload]
+    # rotate over several distinct input sets so no step finds its emissions in the 126 MB L2
+    n_sets = max(3, min(8, int(np.ceil(3 * 126e6 / wl.set_bytes)))) if wl.set_bytes < 2e9 else 1
+    sets = [wl.make(1000 * rank + s, device=dev) for s in range(n_sets)]
+    cells, hours, alg_bytes = wl.units(sets[0])
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,8 +409,9 @@ def gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        wl.step(ipfa, sets[i % n_sets])
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -273,8 +419,9 @@ def gpu_arm(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     ev[0].record()
+    last = None
     for i in range(args.steps):
-        step(i)
+        last = wl.step(ipfa, sets[i % n_sets])
     ev[1].record()
     barrier()
     elapsed_ms = ev[0].elapsed_time(ev[1])
@@ -282,45 +429,29 @@ def gpu_arm(args):
     sampler.stop_flag = True
     sampler.join()
 
-    # per-launch duration of the dominant kernel (events around single launches)
-    k_ms = []
-    for i in range(min(args.steps, 50)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step(i)
-        b.record()
-        b.synchronize()
-        k_ms.append(a.elapsed_time(b))
-    kernel_ms = float(np.median(k_ms))
+    # the only collective of the job: one gather of the per-window results (not timed)
+    gathered = None
+    if world > 1:
+        from ipfa_b200 import sharding
+        res = last.float().reshape(last.shape[0], -1)
+        full = sharding.gather_rows(res, list(range(rank * res.shape[0], (rank + 1) * res.shape[0])),
+                                    world * res.shape[0])
+        gathered = [int(full.shape[0]), bool(torch.isfinite(full).all())]
 
-    # end-to-end through the host-buffer C ABI: pinned host emissions, H2D inside the timed region
-    lp, tg, il, tl = sets[0]
-    h_sets = []
-    for s in range(min(n_sets, 2)):
-        lp_s, tg_s, il_s, tl_s = sets[s]
-        h_sets.append((lp_s.cpu().pin_memory(), tg_s.cpu().pin_memory(), il_s.cpu().pin_memory(),
-                       tl_s.cpu().pin_memory()))
-    out_host = torch.empty(n, dtype=torch.float32).pin_memory()
-
-    def e2e_step(i):
-        hl, ht, hi, htl = h_sets[i % len(h_sets)]
-        if kind == "alpha":
-            return ipfa.ctc_alpha_nll_host(hl.numpy(), ht.numpy(), hi.numpy(), htl.numpy(), out=out_host.numpy())
-        return ipfa.ctc_forced_align_host(hl.numpy(), ht.numpy(), hi.numpy(), htl.numpy(), tokens=False)
-
+    # end-to-end through the host-buffer C ABI: pinned host buffers, H2D + D2H inside the timed region
+    host_sets = [wl.to_host(sets[s]) for s in range(min(n_sets, 2))]
     e2e_steps = max(3, min(args.steps, 20))
     for i in range(3):
-        e2e_step(i)
+        wl.e2e_step(ipfa, *host_sets[i % len(host_sets)])
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        e2e_step(i)
+        wl.e2e_step(ipfa, *host_sets[i % len(host_sets)])
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    h2d = int(set_bytes + tg.numel() * 4 + 8 * n)
-    d2h = int(4 * n if kind == "alpha" else (8 * n * t + 8 * n))
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    h2d, d2h = wl.traffic()
 
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms = float(times[0]), float(times[1])
@@ -328,41 +459,35 @@ def gpu_arm(args):
     if rank == 0:
         peak, peak_src = peaks()
         ms_per_step = elapsed_ms / args.steps
-        value = world * hours / (ms_per_step * 1e-3)
-        # one launch per step for the alpha workload: its average launch duration over the timed
-        # region is ms_per_step (the GPU never idles: launches are issued ahead of execution)
-        kernel_avg_ms = ms_per_step if world == 1 else float(np.mean(k_ms))
-        achieved = alg_bytes / (kernel_avg_ms * 1e-3) / 1e9
-        legs = cpu_leg(args.workload, budget_s=12.0)
-        best_name = max((k for k in ("oracle_port", "torch_cpu") if "audio_h_per_s" in legs[k]),
-                        key=lambda k: legs[k]["audio_h_per_s"])
+        # launches are issued ahead of execution (the GPU never idles inside the timed region), so
+        # the step's kernels average ms_per_step of device time per step
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        legs = cpu_leg(wl, budget_s=12.0)
+        bound_note = {"alpha": "T-serial log-sum-exp recursion: MUFU/issue bound (4 MUFU per state pair and frame), "
+                               "not HBM bound -- DESIGN.md 5.1",
+                      "viterbi": "T-serial max-plus recursion + latency-bound backtrace: issue bound -- DESIGN.md 5.2",
+                      "seg": "T-serial max-plus recursion with a CTA barrier per frame -- DESIGN.md 5.3"}[wl.kind]
         line = {
-            "metric": "aligned_audio_hours_per_s", "value": value, "unit": "audio-h/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD_TEXT[args.workload], "kernel": kind,
-                       "windows_per_gpu": n, "T": t, "L": l, "V": v,
-                       "l2": f"{n_sets} rotating input sets of {set_bytes / 1e6:.0f} MB per GPU (> 126 MB L2)",
-                       "sharding": "independent windows per rank, no collective on the data path"},
+            "metric": "aligned_audio_hours_per_s", "value": world * hours / (ms_per_step * 1e-3),
+            "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict({"workload": wl.text, "kernel": wl.kind,
+                            "l2": f"{n_sets} rotating input sets of {wl.set_bytes / 1e6:.0f} MB per GPU (> 126 MB L2)",
+                            "sharding": "independent windows per rank, no collective on the data path"}, **wl.shape),
             "cells_per_s": world * cells / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_avg_ms,
-                         "single_launch_median_ms": kernel_ms,
-                         "note": "T-serial log-sum-exp recursion: MUFU/latency bound, see DESIGN.md"},
-            "cpu_baseline": {"value": legs[best_name]["audio_h_per_s"], "unit": "audio-h/s",
-                             "cores": legs["cores"],
-                             "kind": "port" if best_name == "oracle_port" else "reference",
-                             "sample": f"{legs[best_name]['windows']} windows of the same workload, "
-                                       f"faster of oracle port / torch CPU: {best_name}",
-                             "oracle_port": legs["oracle_port"], "torch_cpu": legs["torch_cpu"]},
-            "e2e": {"value": world * hours / (e2e_ms * 1e-3), "unit": "audio-h/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "api": "ipfa_ctc_alpha_host" if kind == "alpha" else "ipfa_ctc_viterbi_host"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
+                         "kernels_per_step": launches / max(args.steps, 1), "note": bound_note},
+            "cpu_baseline": cpu_baseline_obj(legs, "same shapes, same generator"),
+            "e2e": {"value": world * hours / (e2e_ms * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": wl.api},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
         }
+        if gathered is not None:
+            line["final_gather"] = {"rows": gathered[0], "finite": gathered[1], "backend": "nccl"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -244,16 +244,23 @@ struct BacktraceParams {
     float *tok_score;
 };
 
-// One warp per window.
+// One warp per window.  Per 32-frame block the warp stages every backpointer word the walk can
+// reach (63 states -> NCW thread-columns x NW word-rows, <= 160 words) in shared memory with
+// coalesced loads, then walks the block with one LDS per frame and NO branch on the serial
+// chain; token spans are derived afterwards, lane-parallel, from neighbouring frames' states.
 template <int P>
 __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const BacktraceParams prm) {
-    constexpr int SPW = 8 / P;       // frames per word
-    constexpr int NW = 32 / SPW;     // words per 32-frame block (= 4P)
-    constexpr int NCOL = 32 / NW;    // thread-columns fetched per block (= 8/P)
-    constexpr int SPT = 2 * P;       // states per thread
+    constexpr int SPW = 8 / P;                 // frames per word
+    constexpr int NW = 32 / SPW;               // word-rows per 32-frame block (= 4P)
+    constexpr int SPT = 2 * P;                 // states per thread-column
+    constexpr int NCW = 62 / SPT + 2;          // thread-columns reachable inside one block
+    constexpr int NWORDS = NCW * NW;
+    __shared__ uint32_t raw_s[4][NWORDS];
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * (blockDim.x >> 5) + wib;
     if (w >= prm.N) return;
+    uint32_t *raw = raw_s[wib];
     const int T = min(prm.in_len[w], prm.Tmax);
     const int L = max(0, min(prm.tgt_len[w], prm.Lmax));
     const int32_t *tg = prm.targets + (int64_t)w * prm.tgt_stride;
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
     const float *lp = prm.lp + (int64_t)w * prm.stride_n;
     int s = prm.final_state[w];
 
-    // tail beyond in_len, or the whole row when infeasible
+    // tail beyond in_len, or the whole row when the window was rejected
     const int t_valid = (s < 0) ? 0 : max(T, 0);
     for (int t = t_valid + lane; t < prm.Tmax; t += 32) {
         paths[t] = -1;
@@ -284,58 +291,70 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
 
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
-    // token bookkeeping while walking backwards (uniform across lanes)
-    if (want_tok && lane == 0 && (s & 1)) tok_e[s >> 1] = T;
+    int s_above = -1;  // state of frame t_hi + 1 (none above the last frame)
 
     for (int blk = (T - 1) >> 5; blk >= 0; --blk) {
         const int t_hi = min(T - 1, blk * 32 + 31);
         const int t_lo = blk * 32;
-        const int icur = s / SPT;  // thread-column of the state at t_hi
-        // lane j holds word (blk*NW + j % NW) of thread-column icur - j / NW
-        const int my_col = icur - lane / NW;
-        const int my_word = blk * NW + (lane % NW);
-        uint32_t wreg = 0;
-        if (my_col >= 0 && (int64_t)my_word * SPW < T) wreg = bp_w[(int64_t)my_word * NT + my_col];
-        int my_state = 0;
-        for (int t = t_hi; t >= t_lo; --t) {
-            if (lane == (t & 31)) my_state = s;
-            if (t == 0) break;
-            const int i = s / SPT, k = s - i * SPT;
-            const int coff = icur - i;
-            const int widx = (t / SPW) - blk * NW;
-            uint32_t word;
-            if (coff < NCOL) {
-                word = __shfl_sync(0xffffffffu, wreg, coff * NW + widx);
-            } else {
-                word = bp_w[(int64_t)(t / SPW) * NT + i];  // rare: > 8/P columns crossed in 32 frames
+        const int c_hi = s / SPT;  // thread-column of the state at t_hi
+        // stage raw[row][c_hi - col] for every column the walk can reach
+        __syncwarp();
+        {   // all loads in flight before the first store: one exposed memory latency per block
+            constexpr int NQ = (NWORDS + 31) / 32;
+            uint32_t v[NQ];
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                const int q = lane + 32 * u;
+                const int row = q / NCW, crel = q - row * NCW;
+                const int col = c_hi - crel;
+                const int wrow = blk * NW + row;
+                v[u] = 0;
+                if (q < NWORDS && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
             }
-            const int d = (word >> ((t % SPW) * 4 * P + 2 * k)) & 3;
-            if (want_tok && d != 0 && lane == 0) {
-                // state s starts at frame t; state s-d ends at frame t (exclusive end)
-                if (s & 1) tok_s[s >> 1] = t;
-                if ((s - d) & 1) tok_e[(s - d) >> 1] = t;
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                const int q = lane + 32 * u;
+                if (q < NWORDS) raw[q] = v[u];
             }
-            s -= d;
         }
+        __syncwarp();
+        int my_state = 0;
+        const int t_stop = max(t_lo, 1);
+        for (int t = t_hi; t >= t_stop; --t) {
+            my_state = (lane == (t & 31)) ? s : my_state;
+            const int col = s / SPT, k = s & (SPT - 1);
+            const int row = (t / SPW) - blk * NW;
+            const uint32_t word = raw[row * NCW + (c_hi - col)];
+            s = max(s - (int)((word >> ((t % SPW) * 4 * P + 2 * k)) & 3), 0);
+        }
+        if (t_lo == 0 && lane == 0) my_state = s;  // frame 0 has no incoming transition
+        const int s_below = s;                      // state of frame t_lo - 1 (blk > 0)
         const int t = t_lo + lane;
+        // neighbours' states for the token spans
+        int st_up = __shfl_down_sync(0xffffffffu, my_state, 1);
+        int st_dn = __shfl_up_sync(0xffffffffu, my_state, 1);
+        if (t == t_hi) st_up = s_above;
+        if (lane == 0) st_dn = (t_lo == 0) ? -1 : s_below;
         if (t <= t_hi) {
             const int lab = (my_state & 1) ? tg[my_state >> 1] : prm.blank;
             paths[t] = lab;
             if (scores) scores[t] = lp[(int64_t)t * prm.stride_t + lab];
+            if (want_tok && (my_state & 1)) {
+                if (st_dn != my_state) tok_s[my_state >> 1] = t;
+                if (st_up != my_state) tok_e[my_state >> 1] = t + 1;
+            }
         }
+        s_above = __shfl_sync(0xffffffffu, my_state, 0);  // state of frame t_lo
     }
-    if (want_tok) {
-        if (lane == 0 && (s & 1)) tok_s[s >> 1] = 0;
+    if (want_tok && tok_p) {
         __syncwarp();
-        if (tok_p) {
-            for (int l = lane; l < L; l += 32) {
-                const int a = tok_s[l], b = tok_e[l];
-                if (a >= 0 && b > a) {
-                    const int lab = tg[l];
-                    float acc = 0.0f;
-                    for (int t = a; t < b; ++t) acc += lp[(int64_t)t * prm.stride_t + lab];
-                    tok_p[l] = acc / (float)(b - a);
-                }
+        for (int l = lane; l < L; l += 32) {
+            const int a = tok_s[l], b = tok_e[l];
+            if (a >= 0 && b > a) {
+                const int lab = tg[l];
+                float acc = 0.0f;
+                for (int t = a; t < b; ++t) acc += lp[(int64_t)t * prm.stride_t + lab];
+                tok_p[l] = acc / (float)(b - a);
             }
         }
     }

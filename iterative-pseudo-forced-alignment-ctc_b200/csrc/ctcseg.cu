@@ -267,9 +267,11 @@ struct SegBackParams {
 // One warp per (window, prefix).
 template <int KC>
 __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackParams prm) {
-    constexpr int SPW = 32 / KC;   // frames per word
-    constexpr int NW = KC;         // words per 32-frame block
-    constexpr int NCOL = 32 / NW;  // thread-columns fetched per block
+    constexpr int SPW = 32 / KC;        // frames per word
+    constexpr int NW = KC;              // word-rows per 32-frame block
+    constexpr int NCW = 31 / KC + 2;    // thread-columns reachable inside one block
+    constexpr int NWORDS = NCW * NW;
+    __shared__ uint32_t raw_s[4][NWORDS];
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= prm.N * prm.Kmax) return;
@@ -309,32 +311,47 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     __syncwarp();
 
     // ---- walk the 1-bit backpointers from (t_term, c_end) to (0, 0) ----------
+    // Per 32-frame block: stage every word the walk can reach in shared memory (coalesced),
+    // then one LDS per frame, no branch on the serial chain.  Column 0 stores bit 0 (stay).
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
+    uint32_t *raw = raw_s[threadIdx.x >> 5];
     int c = c_end;
     for (int blk = t_term >> 5; blk >= 0; --blk) {
         const int t_hi = min(t_term, blk * 32 + 31);
         const int t_lo = blk * 32;
-        const int icur = c / KC;
-        const int my_col = icur - lane / NW;
-        const int my_word = blk * NW + (lane % NW);
-        uint32_t wreg = 0;
-        if (my_col >= 0 && (int64_t)my_word * SPW < T) wreg = bp_w[(int64_t)my_word * NT + my_col];
-        int my_c = -1, my_sw = 0;
-        for (int t = t_hi; t >= t_lo; --t) {
-            if (t == 0) break;  // (0, c): the loop `while t != 0 or c != 0` ends at (0, 0)
-            int sw = 0;
-            if (c > 0) {
-                const int i = c / KC, k = c - i * KC;
-                const int coff = icur - i;
-                const int widx = (t / SPW) - blk * NW;
-                uint32_t word;
-                if (coff < NCOL) word = __shfl_sync(0xffffffffu, wreg, coff * NW + widx);
-                else word = bp_w[(int64_t)(t / SPW) * NT + i];
-                sw = (word >> ((t % SPW) * KC + k)) & 1;
+        const int i_hi = c / KC;
+        __syncwarp();
+        {   // all loads in flight before the first store: one exposed memory latency per block
+            constexpr int NQ = (NWORDS + 31) / 32;
+            uint32_t v[NQ];
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                const int q = lane + 32 * u;
+                const int row = q / NCW, crel = q - row * NCW;
+                const int col = i_hi - crel;
+                const int wrow = blk * NW + row;
+                v[u] = 0;
+                if (q < NWORDS && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
             }
-            if (lane == (t & 31)) { my_c = c; my_sw = sw; }
-            c -= sw;
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                const int q = lane + 32 * u;
+                if (q < NWORDS) raw[q] = v[u];
+            }
+        }
+        __syncwarp();
+        int my_c = -1, my_sw = 0;
+        const int t_stop = max(t_lo, 1);  // (0, c): the loop `while t != 0 or c != 0` ends at (0, 0)
+        for (int t = t_hi; t >= t_stop; --t) {
+            const int i = c / KC, k = c - i * KC;
+            const int row = (t / SPW) - blk * NW;
+            const uint32_t word = raw[row * NCW + (i_hi - i)];
+            const int sw = (word >> ((t % SPW) * KC + k)) & 1;
+            const bool mine = lane == (t & 31);
+            my_c = mine ? c : my_c;
+            my_sw = mine ? sw : my_sw;
+            c = max(c - sw, 0);
         }
         const int t = t_lo + lane;
         if (t <= t_hi && t >= 1 && my_c >= 0) {

@@ -22,7 +22,7 @@ struct LatticeShape {
     X(1, 1) X(1, 2) X(1, 4) X(1, 8) X(1, 16)                                          \
     X(2, 1) X(2, 2) X(2, 4) X(2, 8) X(2, 16)                                          \
     X(4, 1) X(4, 2) X(4, 4) X(4, 8) X(4, 16)                                          \
-    X(8, 8) X(8, 16) X(8, 32)
+    X(8, 1) X(8, 2) X(8, 4) X(8, 8) X(8, 16) X(8, 32)
 
 inline bool shape_exists(int per, int warps) {
 #define IPFA_X(P_, W_) if (per == P_ && warps == W_) return true;

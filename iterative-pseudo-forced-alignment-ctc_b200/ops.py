@@ -171,7 +171,10 @@ def ctc_forced_align(lp, targets, in_len, tgt_len, blank=0, batch_first=True, to
     return ForcedAlignment(paths, scores, tok_start, tok_end, tok_score, total, status)
 
 
-def ctc_forced_align_host(lp, targets, in_len, tgt_len, blank=0, tokens=True):
+def ctc_forced_align_host(lp, targets, in_len, tgt_len, blank=0, tokens=True, out=None):
+    """Host buffers in / out.  ``out`` may carry preallocated (pinned) ``paths``, ``scores``,
+    ``total`` and ``status`` arrays."""
+    out = out or {}
     lp = _np(lp, np.float32)
     n, t, v = lp.shape
     targets = _np(targets, np.int32)
@@ -179,10 +182,10 @@ def ctc_forced_align_host(lp, targets, in_len, tgt_len, blank=0, tokens=True):
         targets = targets[None]
     lmax = targets.shape[1] if targets.size else 0
     in_len, tgt_len = _np(in_len, np.int32), _np(tgt_len, np.int32)
-    paths = np.empty((n, t), np.int32)
-    scores = np.empty((n, t), np.float32)
-    status = np.empty(n, np.int32)
-    total = np.empty(n, np.float32)
+    paths = out.get("paths") if out.get("paths") is not None else np.empty((n, t), np.int32)
+    scores = out.get("scores") if out.get("scores") is not None else np.empty((n, t), np.float32)
+    status = out.get("status") if out.get("status") is not None else np.empty(n, np.int32)
+    total = out.get("total") if out.get("total") is not None else np.empty(n, np.float32)
     if tokens:
         tok_start = np.empty((n, max(lmax, 1)), np.int32)
         tok_end = np.empty_like(tok_start)

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 import ipfa_b200 as ipfa  # noqa: E402
 
-SHAPES = [(p, w) for p in (1, 2, 4) for w in (1, 2, 4, 8, 16)] + [(8, 8), (8, 16), (8, 32)]
+SHAPES = [(p, w) for p in (1, 2, 4) for w in (1, 2, 4, 8, 16)] + [(8, 1), (8, 2), (8, 4), (8, 8), (8, 16), (8, 32)]
 
 
 def time_fn(fn, reps):
@@ -32,18 +32,16 @@ def main():
     names = sys.argv[1:] or ["c2", "c2v", "c3", "c4"]
     dev = torch.device("cuda:0")
     for name in names:
-        kind, n, t, l, v, ragged = bench.WORKLOADS[name]
-        sets = [bench.make_inputs(name, s, device=dev) for s in range(2 if n * t * v * 4 < 1e9 else 1)]
-        env = "IPFA_ALPHA_SHAPE" if kind == "alpha" else "IPFA_VITERBI_SHAPE"
+        wl = bench.WORKLOADS[name]
+        kind = wl.kind
+        l = wl.cols - 1 if kind == "seg" else wl.l
+        sets = [wl.make(s, device=dev) for s in range(2 if wl.set_bytes < 1e9 else 1)]
+        env = {"alpha": "IPFA_ALPHA_SHAPE", "viterbi": "IPFA_VITERBI_SHAPE", "seg": "IPFA_SEG_SHAPE"}[kind]
         i = [0]
 
         def fn():
-            lp, tg, il, tl = sets[i[0] % len(sets)]
             i[0] += 1
-            if kind == "alpha":
-                ipfa.ctc_alpha_nll(lp, tg, il, tl)
-            else:
-                ipfa.ctc_forced_align(lp, tg, il, tl, tokens=False)
+            wl.step(ipfa, sets[i[0] % len(sets)])
 
         os.environ.pop(env, None)
         base = time_fn(fn, 10)
