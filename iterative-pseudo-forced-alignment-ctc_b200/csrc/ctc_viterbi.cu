@@ -44,7 +44,9 @@ struct ViterbiParams {
     int32_t *status_out;     // [N]
 };
 
-template <int P, int WARPS, bool DENSE>
+// PITCH > 0: compile-time panel pitch (dense rows of <= 32 symbols): the unrolled frames of a
+// backpointer word address the panel with immediate offsets.
+template <int P, int WARPS, bool DENSE, int PITCH>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
@@ -58,9 +60,10 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     const int w = blockIdx.x * GROUPS + group;
     if (w >= prm.N) return;
 
+    const int pitch = PITCH ? PITCH : prm.pitch;
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
-    float *xline = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][NT + 1] neighbour exchange
+    float *xline = ring + (size_t)kStages * prm.tc * pitch;      // [2][NT + 1] neighbour exchange
     float *fin = xline + 2 * (NT + 1);                            // [2]
     int *cnt = reinterpret_cast<int *>(fin + 2);                // [2] repeats, bad labels
     int *cols = cnt + 2;                                        // [u_cap]
@@ -116,8 +119,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     }
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, prm.pitch,
-              prm.tc);
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, pitch, prm.tc);
     pipe.prologue(tid);
 
     float ab[P], al[P];
@@ -138,7 +140,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
         }
     };
 
-    auto frame = [&](const float *row, const float *rd, float *wr) {
+    auto frame = [&](const float *row, const float *rd, float *wr) -> uint32_t {
         const float eb = row[colb];
         float el[P];
 #pragma unroll
@@ -168,11 +170,11 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
             ab[p] = nb;
             bits |= (bb | (bl << 2)) << (4 * p);
         }
-        push_bits(bits);
         if constexpr (WARPS > 1) {
             wr[tid + 1] = al[P - 1];
             __syncthreads();
         }
+        return bits;
     };
 
     float *line0 = xline, *line1 = xline + NT + 1;
@@ -195,14 +197,27 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
             }
             r = 1;
         }
-        const float *row = panel + r * prm.pitch;
-        if ((r & 1) && r < rows) { frame(row, line0, line1); row += prm.pitch; ++r; }
-        for (; r + 1 < rows; r += 2) {
-            frame(row, line1, line0);
-            frame(row + prm.pitch, line0, line1);
-            row += 2 * prm.pitch;
+        const float *row = panel + r * pitch;
+        // frame t reads line[(t-1)&1], writes line[t&1]; tc is even so r has t's parity
+        while (r < rows) {
+            if (SPW > 1 && shift == 0 && !(r & 1) && r + SPW <= rows) {
+                // a whole backpointer word: SPW frames with compile-time shifts and line parity
+                uint32_t acc = 0;
+#pragma unroll
+                for (int f = 0; f < SPW; ++f) {
+                    acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0)
+                           << (f * 4 * P);
+                }
+                *bp_ptr = acc;
+                bp_ptr += NT;
+                row += SPW * pitch;
+                r += SPW;
+            } else {
+                push_bits((r & 1) ? frame(row, line0, line1) : frame(row, line1, line0));
+                row += pitch;
+                ++r;
+            }
         }
-        if (r < rows) frame(row, line1, line0);
     }
     if (shift != 0) *bp_ptr = word;
 
@@ -366,10 +381,10 @@ static int64_t viterbi_words_per_window(int Tmax, LatticeShape s) {
     return (int64_t)((Tmax + spw - 1) / spw) * 32 * s.WARPS;
 }
 
-template <int P, int WARPS, bool DENSE>
-static int launch_fill(ViterbiParams prm, int Lmax, cudaStream_t stream) {
+template <int P, int WARPS, bool DENSE, int PITCH>
+static int launch_fill_p(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
-    const int U = DENSE ? prm.V : (Lmax + 1);
+    const int U = PITCH ? PITCH : (DENSE ? prm.V : (Lmax + 1));
     const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
     PipeGeometry g = pipe_geometry(U, budget);
     prm.pitch = g.pitch;
@@ -381,7 +396,7 @@ static int launch_fill(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
-    auto kern = ctc_viterbi_fill_kernel<P, WARPS, DENSE>;
+    auto kern = ctc_viterbi_fill_kernel<P, WARPS, DENSE, PITCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
@@ -391,6 +406,14 @@ static int launch_fill(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;
+}
+
+template <int P, int WARPS, bool DENSE>
+static int launch_fill(const ViterbiParams &prm, int Lmax, cudaStream_t stream) {
+    if constexpr (DENSE) {
+        if (prm.V <= 32) return launch_fill_p<P, WARPS, true, 32>(prm, Lmax, stream);
+    }
+    return launch_fill_p<P, WARPS, DENSE, 0>(prm, Lmax, stream);
 }
 
 template <bool DENSE>

@@ -44,30 +44,39 @@ struct SegFillParams {
     const int32_t *gt;
     int64_t gt_stride;
     const int32_t *n_cols;
-    int N, Tmax, Cmax, V, blank, flags;
+    const int32_t *utt_begin;  // [N][Kmax+1]
+    const int32_t *n_utts;
+    int N, Tmax, Cmax, Kmax, V, blank, flags;
     int pitch, tc, u_cap;
     size_t group_smem;
     uint32_t *bp;
     int64_t words_per_window;
-    int32_t *colarg;  // [N][Cmax] first argmax_t of every column
+    int32_t *colarg;  // [N][Cmax] first argmax_t of the utterance-boundary columns (-1 elsewhere)
 };
 
-template <int KC, int WARPS, bool DENSE>
+// Lattice column lc of a window = table column lc + 1.  Column 0 (ground truth -1, the free
+// preamble) is not a lattice unit: its value z(t) is 0 for every t (preamble_transition_cost_zero)
+// or a running sum of blank emissions, and only enters as the left neighbour of column 1.
+// PITCH > 0: compile-time panel pitch (dense rows of <= 32 symbols), so the unrolled frames of a
+// backpointer word address the panel with immediate offsets.
+template <int KC, int WARPS, bool DENSE, int PITCH>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctcseg_fill_kernel(const SegFillParams prm) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     constexpr int NT = 32 * WARPS;
     constexpr int SPW = 32 / KC;  // frames per backpointer word
+    constexpr float kNegInf = -__builtin_huge_valf();
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
     const int w = blockIdx.x * GROUPS + group;
     if (w >= prm.N) return;
+    const int pitch = PITCH ? PITCH : prm.pitch;
 
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
-    float *xline = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][NT + 1] neighbour exchange
+    float *xline = ring + (size_t)kStages * prm.tc * pitch;     // [2][NT + 1] neighbour exchange
     int *cols = reinterpret_cast<int *>(xline + 2 * (NT + 1));    // [u_cap]
 
     const int T = min(prm.in_len[w], prm.Tmax);
@@ -78,16 +87,14 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     const bool preamble_cost_zero = prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO;
     int32_t *colarg_w = prm.colarg + (int64_t)w * prm.Cmax;
 
-    if (T <= 0 || NC <= 0) {
-        for (int c = tid; c < prm.Cmax; c += NT) colarg_w[c] = -1;
-        return;
-    }
+    for (int c = tid; c < prm.Cmax; c += NT) colarg_w[c] = -1;
+    if (T <= 0 || NC <= 1) return;
 
     int col[KC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-        const int c = tid * KC + k;
-        int g = (c >= 1 && c < NC) ? gt[c] : blank;
+        const int c = 1 + tid * KC + k;
+        int g = (c < NC) ? gt[c] : blank;
         if (g < 0 || g >= prm.V) g = blank;
         col[k] = DENSE ? g : ((c < NC) ? c : 0);
     }
@@ -99,24 +106,81 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             cols[j] = g;
         }
     }
+    // only the utterance-boundary columns need their first argmax over t; a warp that owns
+    // none of them skips the tracking code altogether
+    bool track = false;
+    {
+        const int K = max(0, min(prm.n_utts[w], prm.Kmax));
+        const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
+        const int c0 = 1 + tid * KC;
+        for (int u = 1; u <= K; ++u) {
+            const int c = ub[u];
+            track |= (c >= c0 && c < c0 + KC);
+        }
+    }
+    const bool warp_tracks = __any_sync(0xffffffffu, track);
     if constexpr (WARPS > 1) {
-        if (tid < 2) xline[tid * (NT + 1)] = kProbMax;  // "column -1": switch into column 0 is prob_max
+        if (tid < 2) xline[tid * (NT + 1)] = 0.0f;  // z(t) = table[t, 0]; table[0, 0] = 0
     }
     group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, prm.pitch, prm.tc);
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, pitch, prm.tc);
     pipe.prologue(tid);
 
     float val[KC], cmax[KC];
     int carg[KC];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = 0.0f; carg[k] = -1; }
+    for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = kNegInf; carg[k] = -1; }
+    float z = 0.0f;  // column 0 at the previous frame
     uint32_t word = 0;
     int shift = 0;
     uint32_t *bp_ptr = prm.bp + (int64_t)w * prm.words_per_window + tid;
     int t = 0;
 
+    // one frame; returns this thread's KC decision bits
+    auto frame = [&](const float *row, const float *rd, float *wr) -> uint32_t {
+        const float eb = row[colb];
+        float ec[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
+        float prev;
+        if constexpr (WARPS > 1) {
+            prev = rd[tid];
+        } else {
+            prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
+            if (tid == 0) prev = z;
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = KC - 1; k >= 0; --k) {
+            const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
+            const float up = val[k];                          // table[t-1, c]
+            const float sw = __fadd_rn(left, ec[k]);
+            const float stay_p = fmaxf(eb, ec[k]);
+            const float st = blank_cost_zero ? up : __fadd_rn(up, stay_p);
+            const float v = fmaxf(sw, st);
+            // the reference backtrace's transition test, on the same fp32 values
+            const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left)));
+            const float d_st = fabsf(__fsub_rn(stay_p, __fsub_rn(v, up)));
+            bits |= (d_st > d_sw) ? (1u << k) : 0u;
+            val[k] = v;
+        }
+        if (warp_tracks) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (cmax[k] < val[k]) { cmax[k] = val[k]; carg[k] = t; }
+            }
+        }
+        ++t;
+        if (!preamble_cost_zero) z = fmaxf(kProbMax, __fadd_rn(z, eb));
+        if constexpr (WARPS > 1) {
+            wr[tid + 1] = val[KC - 1];
+            if (!preamble_cost_zero && tid == 0) wr[0] = z;
+            __syncthreads();
+        }
+        return bits;
+    };
     auto push_bits = [&](uint32_t bits) {
         word |= bits << shift;
         shift += KC;
@@ -128,88 +192,53 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         }
     };
 
-    auto frame = [&](const float *row, const float *rd, float *wr) {
-        const float eb = row[colb];
-        float ec[KC];
-#pragma unroll
-        for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
-        float prev;
-        if constexpr (WARPS > 1) {
-            prev = rd[tid];
-        } else {
-            prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
-            if (tid == 0) prev = kProbMax;
-        }
-        uint32_t bits = 0;
-#pragma unroll
-        for (int k = KC - 1; k >= 0; --k) {
-            const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
-            const float up = val[k];                          // table[t-1, c]
-            const float sw = __fadd_rn(left, ec[k]);
-            const float stay_p = fmaxf(eb, ec[k]);
-            const float st = blank_cost_zero ? up : __fadd_rn(up, stay_p);
-            float v = fmaxf(sw, st);
-            // the reference backtrace's transition test, on the same fp32 values
-            const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left)));
-            const float d_st = fabsf(__fsub_rn(stay_p, __fsub_rn(v, up)));
-            uint32_t bit = (d_st > d_sw) ? 1u : 0u;
-            if (k == 0 && tid == 0) {  // column 0 (ground truth -1): stay only
-                const float stay0 = preamble_cost_zero ? 0.0f : __fadd_rn(up, eb);
-                v = fmaxf(kProbMax, stay0);
-                bit = 0;
-            }
-            val[k] = v;
-            if (cmax[k] < v || carg[k] < 0) { cmax[k] = v; carg[k] = t; }
-            bits |= bit << k;
-        }
-        push_bits(bits);
-        ++t;
-        if constexpr (WARPS > 1) {
-            wr[tid + 1] = val[KC - 1];
-            __syncthreads();
-        }
-    };
-
     float *line0 = xline, *line1 = xline + NT + 1;
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
         const float *panel = pipe.acquire(chunk, tid);
         const int rows = min(pipe.tc, T - chunk * pipe.tc);
         int r = 0;
         if (chunk == 0) {
-            // t = 0: table[0, 0] = 0 (column 0's argmax scan starts at t = 1);
-            // every other column is max(switch = prob_max, stay = prob_max)
+            // t = 0: every column c >= 1 is max(switch = prob_max, stay = prob_max)
+            if (warp_tracks) {
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (tid * KC + k == 0) {
-                    val[k] = 0.0f;
-                } else {
-                    val[k] = kProbMax;
-                    cmax[k] = kProbMax;
-                    carg[k] = 0;
-                }
+                for (int k = 0; k < KC; ++k) { cmax[k] = kProbMax; carg[k] = 0; }
             }
             push_bits(0);
             t = 1;
             if constexpr (WARPS > 1) {
-                line0[tid + 1] = val[KC - 1];
+                line0[tid + 1] = kProbMax;
                 __syncthreads();
             }
             r = 1;
         }
-        const float *row = panel + r * prm.pitch;
-        if ((r & 1) && r < rows) { frame(row, line0, line1); row += prm.pitch; ++r; }
-        for (; r + 1 < rows; r += 2) {
-            frame(row, line1, line0);
-            frame(row + prm.pitch, line0, line1);
-            row += 2 * prm.pitch;
+        const float *row = panel + r * pitch;
+        // frame t reads line[(t-1)&1], writes line[t&1]; tc is even so r has t's parity
+        while (r < rows) {
+            if (shift == 0 && !(r & 1) && r + SPW <= rows) {
+                // a whole backpointer word: SPW frames with compile-time shifts and line parity
+                uint32_t acc = 0;
+#pragma unroll
+                for (int f = 0; f < SPW; ++f) {
+                    acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0) << (f * KC);
+                }
+                *bp_ptr = acc;
+                bp_ptr += NT;
+                row += SPW * pitch;
+                r += SPW;
+            } else {
+                push_bits((r & 1) ? frame(row, line0, line1) : frame(row, line1, line0));
+                row += pitch;
+                ++r;
+            }
         }
-        if (r < rows) frame(row, line1, line0);
     }
     if (shift != 0) *bp_ptr = word;
+    if (warp_tracks) {
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int c = tid * KC + k;
-        if (c < prm.Cmax) colarg_w[c] = (c < NC) ? carg[k] : -1;
+        for (int k = 0; k < KC; ++k) {
+            const int c = 1 + tid * KC + k;
+            if (c < NC) colarg_w[c] = carg[k];
+        }
     }
 }
 
@@ -316,11 +345,15 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
     uint32_t *raw = raw_s[threadIdx.x >> 5];
-    int c = c_end;
+    // The walk runs on the lattice column lc = c - 1 (lc == -1 is table column 0).  Words of
+    // thread-column -1 are staged as zeros, so at lc == -1 the bit reads 0 (stay) and no
+    // clamp or select sits on the serial chain: SHR -> ADD -> LDS -> SHF -> AND -> SUB.
+    constexpr int LOG2KC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
+    int lc = c_end - 1;
     for (int blk = t_term >> 5; blk >= 0; --blk) {
         const int t_hi = min(t_term, blk * 32 + 31);
         const int t_lo = blk * 32;
-        const int i_hi = c / KC;
+        const int i_hi = lc >> LOG2KC;  // arithmetic shift: -1 -> thread-column -1
         __syncwarp();
         {   // all loads in flight before the first store: one exposed memory latency per block
             constexpr int NQ = (NWORDS + 31) / 32;
@@ -344,14 +377,14 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
         int my_c = -1, my_sw = 0;
         const int t_stop = max(t_lo, 1);  // (0, c): the loop `while t != 0 or c != 0` ends at (0, 0)
         for (int t = t_hi; t >= t_stop; --t) {
-            const int i = c / KC, k = c - i * KC;
+            const int i = lc >> LOG2KC, k = lc & (KC - 1);
             const int row = (t / SPW) - blk * NW;
             const uint32_t word = raw[row * NCW + (i_hi - i)];
             const int sw = (word >> ((t % SPW) * KC + k)) & 1;
             const bool mine = lane == (t & 31);
-            my_c = mine ? c : my_c;
+            my_c = mine ? lc + 1 : my_c;
             my_sw = mine ? sw : my_sw;
-            c = max(c - sw, 0);
+            lc -= sw;
         }
         const int t = t_lo + lane;
         if (t <= t_hi && t >= 1 && my_c >= 0) {
@@ -439,10 +472,10 @@ static int64_t seg_words_per_window(int Tmax, SegShape s) {
 }
 static inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-template <int KC, int WARPS, bool DENSE>
-static int launch_seg_fill(SegFillParams prm, cudaStream_t stream) {
+template <int KC, int WARPS, bool DENSE, int PITCH>
+static int launch_seg_fill_p(SegFillParams prm, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
-    const int U = DENSE ? prm.V : prm.Cmax;
+    const int U = PITCH ? PITCH : (DENSE ? prm.V : prm.Cmax);
     const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
     PipeGeometry g = pipe_geometry(U, budget);
     prm.pitch = g.pitch;
@@ -452,7 +485,7 @@ static int launch_seg_fill(SegFillParams prm, cudaStream_t stream) {
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
-    auto kern = ctcseg_fill_kernel<KC, WARPS, DENSE>;
+    auto kern = ctcseg_fill_kernel<KC, WARPS, DENSE, PITCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
@@ -462,6 +495,14 @@ static int launch_seg_fill(SegFillParams prm, cudaStream_t stream) {
     e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;
+}
+
+template <int KC, int WARPS, bool DENSE>
+static int launch_seg_fill(const SegFillParams &prm, cudaStream_t stream) {
+    if constexpr (DENSE) {
+        if (prm.V <= 32) return launch_seg_fill_p<KC, WARPS, true, 32>(prm, stream);
+    }
+    return launch_seg_fill_p<KC, WARPS, DENSE, 0>(prm, stream);
 }
 
 template <bool DENSE>
@@ -518,7 +559,8 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
 
     SegFillParams fp{};
     fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t; fp.in_len = in_len;
-    fp.gt = gt; fp.gt_stride = gt_stride; fp.n_cols = n_cols;
+    fp.gt = gt; fp.gt_stride = gt_stride; fp.n_cols = n_cols; fp.utt_begin = utt_begin; fp.n_utts = n_utts;
+    fp.Kmax = Kmax;
     fp.N = N; fp.Tmax = Tmax; fp.Cmax = Cmax; fp.V = V; fp.blank = blank; fp.flags = flags;
     fp.bp = bp; fp.words_per_window = wpw; fp.colarg = colarg;
     int rc = use_dense_panel(V, Cmax) ? dispatch_seg_fill<true>(fp, s, st) : dispatch_seg_fill<false>(fp, s, st);
