@@ -254,7 +254,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
         (Lmax > 0 && !targets))
         return IPFA_ERR_INVALID_ARG;
     LatticeShape s;
-    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_ALPHA_SHAPE")) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_ALPHA_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return IPFA_ERR_UNSUPPORTED;
     AlphaParams prm{};
     prm.lp = lp; prm.stride_n = stride_n; prm.stride_t = stride_t;
     prm.targets = targets; prm.tgt_stride = tgt_stride;

@@ -447,7 +447,7 @@ using namespace ipfa;
 extern "C" size_t ipfa_ctc_viterbi_workspace_bytes(int N, int Tmax, int Lmax, int V) {
     (void)V;
     LatticeShape s;
-    if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE")) return 256;
+    if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return 256;
     const size_t bp = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s) * sizeof(uint32_t);
     return ((bp + 255) & ~(size_t)255) + (((size_t)N * 4 + 255) & ~(size_t)255) + 256;
 }
@@ -465,7 +465,7 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
         ((tok_start == nullptr) != (tok_end == nullptr)))
         return IPFA_ERR_INVALID_ARG;
     LatticeShape s;
-    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE")) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return IPFA_ERR_UNSUPPORTED;
     if (workspace_bytes < ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V)) return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t wpw = viterbi_words_per_window(Tmax, s);

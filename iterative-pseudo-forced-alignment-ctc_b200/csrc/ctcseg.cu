@@ -463,8 +463,8 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
 
 // ---------------------------------------------------------------------------
 using SegShape = LatticeShape;
-static bool pick_seg_shape(int cols, int n_windows, SegShape *s) {
-    return pick_lattice_shape(cols, n_windows, s, "IPFA_SEG_SHAPE");
+static bool pick_seg_shape(int cols, int n_windows, int V, SegShape *s) {
+    return pick_lattice_shape(cols, n_windows, s, "IPFA_SEG_SHAPE", use_dense_panel(V, cols) ? 3 : 6);
 }
 static int64_t seg_words_per_window(int Tmax, SegShape s) {
     const int spw = 32 / s.PER;
@@ -521,7 +521,7 @@ using namespace ipfa;
 extern "C" size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int V) {
     (void)V;
     SegShape s;
-    if (N <= 0 || Tmax < 0 || Cmax <= 0 || Kmax <= 0 || !pick_seg_shape(Cmax, N, &s)) return 256;
+    if (N <= 0 || Tmax < 0 || Cmax <= 0 || Kmax <= 0 || !pick_seg_shape(Cmax, N, V, &s)) return 256;
     size_t b = pad256((size_t)N * (size_t)seg_words_per_window(Tmax, s) * 4);
     b += pad256((size_t)N * Cmax * 4);                   // colarg
     b += pad256((size_t)N * Kmax * (size_t)Cmax * 4);    // timing scratch
@@ -544,7 +544,7 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
         return IPFA_ERR_INVALID_ARG;
     if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode: not built yet
     SegShape s;
-    if (!pick_seg_shape(Cmax, N, &s)) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_seg_shape(Cmax, N, V, &s)) return IPFA_ERR_UNSUPPORTED;
     if (workspace_bytes < ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V)) return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);

@@ -33,7 +33,8 @@ inline bool shape_exists(int per, int warps) {
 
 // units: lattice units the widest window needs; n_windows: batch size;
 // target_warps: resident warps wanted on the whole GPU before widening PER.
-inline bool pick_lattice_shape(int units, int n_windows, LatticeShape *out, const char *env_name) {
+inline bool pick_lattice_shape(int units, int n_windows, LatticeShape *out, const char *env_name,
+                               int warps_per_smsp = 3) {
     if (const char *e = getenv(env_name)) {  // tuning override "PER,WARPS"
         int p = 0, w = 0;
         if (sscanf(e, "%d,%d", &p, &w) == 2 && shape_exists(p, w) && 32 * w * p >= units) {
@@ -42,9 +43,10 @@ inline bool pick_lattice_shape(int units, int n_windows, LatticeShape *out, cons
         }
     }
     // Candidates: every instance wide enough and at most 2x more padded than the tightest one.
-    // Among those that put >= ~6 warps on every SM sub-partition take the least padded (ties:
-    // more units per thread = fewer barriers/shuffles per unit); when the batch is too small for
-    // that, take the one with the most warps.
+    // Among those that put >= warps_per_smsp warps on every SM sub-partition (measured: 3 is
+    // enough for the dense-panel kernels, the gather panel wants 6 to cover its load latency)
+    // take the least padded (ties: more units per thread = fewer barriers/shuffles per unit);
+    // when the batch is too small for that, take the one with the most warps.
     static const LatticeShape all[] = {
 #define IPFA_X(P_, W_) {P_, W_},
         IPFA_FOR_EACH_SHAPE(IPFA_X)
@@ -56,7 +58,7 @@ inline bool pick_lattice_shape(int units, int n_windows, LatticeShape *out, cons
         if (pad >= units && (min_pad < 0 || pad < min_pad)) min_pad = pad;
     }
     if (min_pad < 0) return false;
-    const long long want_warps = 148LL * 4 * 6;
+    const long long want_warps = 148LL * 4 * warps_per_smsp;
     LatticeShape best{0, 0};
     bool best_ok = false;
     long long best_pad = 0;
