@@ -140,7 +140,9 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
         }
     };
 
-    auto frame = [&](const float *row, const float *rd, float *wr) -> uint32_t {
+    // One frame.  `sh` = bit position of this frame inside the backpointer word: a compile-time
+    // constant after unrolling, so every decision predicate becomes one SEL of a constant.
+    auto frame = [&](const float *row, const float *rd, float *wr, const int sh) -> uint32_t {
         const float eb = row[colb];
         float el[P];
 #pragma unroll
@@ -156,19 +158,21 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
 #pragma unroll
         for (int p = P - 1; p >= 0; --p) {
             const float lm1 = (p == 0) ? prev : al[p - 1];
-            // label state: x0 stay, x1 from blank, x2 skip (torchaudio's strict comparisons)
+            // label state: x0 stay, x1 from blank, x2 skip.  torchaudio's rule
+            //   if (x2 > x1 && x2 > x0) 2; else if (x1 > x0 && x1 > x2) 1; else 0
+            // has mutually exclusive branches (x2 > x1 vs x1 > x2), so both predicates are
+            // evaluated independently.
             const float x0 = al[p], x1 = ab[p], x2 = skip[p] ? lm1 : NEG;
-            float res;
-            uint32_t bl;
-            if (x2 > x1 && x2 > x0) { res = x2; bl = 2; }
-            else if (x1 > x0 && x1 > x2) { res = x1; bl = 1; }
-            else { res = x0; bl = 0; }
+            const bool take2 = (x2 > x1) && (x2 > x0);
+            const bool take1 = (x1 > x0) && (x1 > x2);
+            const float res = take2 ? x2 : (take1 ? x1 : x0);
             // blank state: x0 stay, x1 from previous label
-            const uint32_t bb = (lm1 > ab[p]) ? 1u : 0u;
-            const float nb = (bb ? lm1 : ab[p]) + eb;
+            const bool takeb = lm1 > ab[p];
+            const float nb = (takeb ? lm1 : ab[p]) + eb;
             al[p] = res + el[p];
             ab[p] = nb;
-            bits |= (bb | (bl << 2)) << (4 * p);
+            bits |= (takeb ? (1u << (sh + 4 * p)) : 0u) | (take1 ? (1u << (sh + 4 * p + 2)) : 0u) |
+                    (take2 ? (1u << (sh + 4 * p + 3)) : 0u);
         }
         if constexpr (WARPS > 1) {
             wr[tid + 1] = al[P - 1];
@@ -205,15 +209,14 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
                 uint32_t acc = 0;
 #pragma unroll
                 for (int f = 0; f < SPW; ++f) {
-                    acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0)
-                           << (f * 4 * P);
+                    acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0, f * 4 * P);
                 }
                 *bp_ptr = acc;
                 bp_ptr += NT;
                 row += SPW * pitch;
                 r += SPW;
             } else {
-                push_bits((r & 1) ? frame(row, line0, line1) : frame(row, line1, line0));
+                push_bits((r & 1) ? frame(row, line0, line1, 0) : frame(row, line1, line0, 0));
                 row += pitch;
                 ++r;
             }
