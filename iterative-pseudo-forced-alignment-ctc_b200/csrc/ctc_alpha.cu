@@ -97,7 +97,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
 
     EmissionPipe<WARPS, DENSE> pipe;
     pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, prm.pitch,
-              prm.tc);
+              prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
     pipe.prologue(tid);
 
     float ab[P], al[P];  // blank / label alphas (log2 domain)
@@ -208,7 +208,7 @@ static int launch_alpha(AlphaParams prm, int Lmax, cudaStream_t stream) {
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
     prm.l_cap = Lmax;
-    size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
+    size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2) * sizeof(float) + (size_t)prm.u_cap * sizeof(int) + 40;
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;

@@ -119,7 +119,8 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     }
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, pitch, prm.tc);
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, pitch, prm.tc,
+              reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
     pipe.prologue(tid);
 
     float ab[P], al[P];
@@ -395,7 +396,7 @@ static int launch_fill_p(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
     prm.l_cap = Lmax;
     size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2) * sizeof(float) + 2 * sizeof(int) +
-                        (size_t)prm.u_cap * sizeof(int);
+                        (size_t)prm.u_cap * sizeof(int) + 40;
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;

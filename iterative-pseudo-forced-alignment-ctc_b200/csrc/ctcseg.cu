@@ -125,7 +125,8 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, pitch, prm.tc);
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, pitch, prm.tc,
+              reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
     pipe.prologue(tid);
 
     float val[KC], cmax[KC];
@@ -481,7 +482,7 @@ static int launch_seg_fill_p(SegFillParams prm, cudaStream_t stream) {
     prm.pitch = g.pitch;
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((prm.Cmax + 3) & ~3);
-    size_t group_smem = g.ring_bytes + 2 * (32 * WARPS + 1) * sizeof(float) + (size_t)prm.u_cap * sizeof(int);
+    size_t group_smem = g.ring_bytes + 2 * (32 * WARPS + 1) * sizeof(float) + (size_t)prm.u_cap * sizeof(int) + 40;
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;

@@ -5,8 +5,11 @@
 // A "group" is the set of threads that owns one window: a single warp
 // (WARPS == 1, several windows per CTA, no CTA barrier anywhere) or the whole
 // CTA (WARPS > 1).  Two panel layouts:
-//   DENSE  : the panel row is the full vocabulary row lp[t, 0:V] (V small);
-//            16-byte cp.async when alignment allows, fully coalesced.
+//   DENSE  : the panel row is the full vocabulary row lp[t, 0:V] (V small).
+//            When the rows of a chunk are contiguous in global AND shared memory
+//            (stride_t == V == pitch, 16-byte aligned) the whole chunk moves with ONE
+//            bulk async copy (TMA engine, cp.async.bulk -> SASS UBLKCP) issued by one
+//            thread and completed on an mbarrier; otherwise 16-byte / 4-byte cp.async.
 //   gather : the panel row holds only the window's own columns,
 //            panel[t][j] = lp[t, cols[j]] with cols[0] = blank; 4-byte cp.async.
 #pragma once
@@ -33,15 +36,27 @@ struct EmissionPipe {
     const float *base;    // &lp[w, 0, 0]
     int64_t stride_t;
     int T, U, V, pitch, tc, nchunks;
-    bool vec16;
+    bool vec16, bulk;
+    uint64_t *bars;       // [kStages] mbarriers (bulk mode)
 
+    // All threads of the group call init(); it ends with a group barrier.
     __device__ __forceinline__ void init(float *ring_, const int *cols_, const float *base_,
-                                         int64_t stride_t_, int T_, int U_, int V_, int pitch_, int tc_) {
+                                         int64_t stride_t_, int T_, int U_, int V_, int pitch_, int tc_,
+                                         uint64_t *bars_, int tid) {
         ring = ring_; cols = cols_; base = base_; stride_t = stride_t_;
-        T = T_; U = U_; V = V_; pitch = pitch_; tc = tc_;
+        T = T_; U = U_; V = V_; pitch = pitch_; tc = tc_; bars = bars_;
         nchunks = (T + tc - 1) / tc;
         vec16 = DENSE && (V % 4 == 0) && (stride_t % 4 == 0) &&
                 ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+        bulk = vec16 && stride_t == V && pitch == V;
+        if (bulk) {
+            if (tid == 0) {
+#pragma unroll
+                for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+        }
+        group_sync<WARPS>();
     }
 
     __device__ __forceinline__ float *stage_ptr(int chunk) const {
@@ -55,7 +70,14 @@ struct EmissionPipe {
             const int t0 = chunk * tc;
             const int rows = min(tc, T - t0);
             if constexpr (DENSE) {
-                if (vec16) {
+                if (bulk) {
+                    if (tid == 0) {
+                        const uint32_t bytes = (uint32_t)rows * (uint32_t)V * 4u;
+                        uint64_t *bar = &bars[chunk % kStages];
+                        mbar_expect_tx(bar, bytes);
+                        bulk_copy_g2s(dst, base + (int64_t)t0 * stride_t, bytes, bar);
+                    }
+                } else if (vec16) {
                     const int v4 = V >> 2;
                     const int pieces = rows * v4;
                     for (int q = tid; q < pieces; q += NT) {
@@ -87,7 +109,14 @@ struct EmissionPipe {
 
     // Make chunk `chunk` visible to the group and refill the stage freed by chunk-1.
     __device__ __forceinline__ const float *acquire(int chunk, int tid) {
-        cp_async_wait<kStages - 2>();
+        if (bulk) {
+            mbar_wait(&bars[chunk % kStages], (uint32_t)(chunk / kStages) & 1u);
+            // this thread's generic-proxy accesses to the stage about to be refilled (reads, and
+            // the in-place prescale of the alpha kernel) are ordered before the async-proxy write
+            fence_proxy_async();
+        } else {
+            cp_async_wait<kStages - 2>();
+        }
         group_sync<WARPS>();
         issue(chunk + kStages - 1, tid);
         return stage_ptr(chunk);
