@@ -59,7 +59,9 @@ struct SegFillParams {
 // or a running sum of blank emissions, and only enters as the left neighbour of column 1.
 // PITCH > 0: compile-time panel pitch (dense rows of <= 32 symbols), so the unrolled frames of a
 // backpointer word address the panel with immediate offsets.
-template <int KC, int WARPS, bool DENSE, int PITCH>
+// FAST: the reference's default flags (blank_transition_cost_zero = False,
+// preamble_transition_cost_zero = True) compiled in, so neither costs an instruction per cell.
+template <int KC, int WARPS, bool DENSE, int PITCH, bool FAST>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctcseg_fill_kernel(const SegFillParams prm) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
@@ -83,8 +85,8 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     const int NC = max(0, min(prm.n_cols[w], prm.Cmax));
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
     const int blank = prm.blank;
-    const bool blank_cost_zero = prm.flags & IPFA_SEG_BLANK_COST_ZERO;
-    const bool preamble_cost_zero = prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO;
+    const bool blank_cost_zero = FAST ? false : (prm.flags & IPFA_SEG_BLANK_COST_ZERO) != 0;
+    const bool preamble_cost_zero = FAST ? true : (prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO) != 0;
     int32_t *colarg_w = prm.colarg + (int64_t)w * prm.Cmax;
 
     for (int c = tid; c < prm.Cmax; c += NT) colarg_w[c] = -1;
@@ -473,7 +475,7 @@ static int64_t seg_words_per_window(int Tmax, SegShape s) {
 }
 static inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-template <int KC, int WARPS, bool DENSE, int PITCH>
+template <int KC, int WARPS, bool DENSE, int PITCH, bool FAST>
 static int launch_seg_fill_p(SegFillParams prm, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     const int U = PITCH ? PITCH : (DENSE ? prm.V : prm.Cmax);
@@ -486,7 +488,7 @@ static int launch_seg_fill_p(SegFillParams prm, cudaStream_t stream) {
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
-    auto kern = ctcseg_fill_kernel<KC, WARPS, DENSE, PITCH>;
+    auto kern = ctcseg_fill_kernel<KC, WARPS, DENSE, PITCH, FAST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
@@ -500,10 +502,12 @@ static int launch_seg_fill_p(SegFillParams prm, cudaStream_t stream) {
 
 template <int KC, int WARPS, bool DENSE>
 static int launch_seg_fill(const SegFillParams &prm, cudaStream_t stream) {
+    const bool fast = (prm.flags & (IPFA_SEG_BLANK_COST_ZERO | IPFA_SEG_PREAMBLE_COST_ZERO)) ==
+                      IPFA_SEG_PREAMBLE_COST_ZERO;
     if constexpr (DENSE) {
-        if (prm.V <= 32) return launch_seg_fill_p<KC, WARPS, true, 32>(prm, stream);
+        if (prm.V <= 32 && fast) return launch_seg_fill_p<KC, WARPS, true, 32, true>(prm, stream);
     }
-    return launch_seg_fill_p<KC, WARPS, DENSE, 0>(prm, stream);
+    return launch_seg_fill_p<KC, WARPS, DENSE, 0, false>(prm, stream);
 }
 
 template <bool DENSE>
