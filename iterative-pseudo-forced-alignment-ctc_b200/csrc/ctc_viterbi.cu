@@ -266,20 +266,23 @@ struct BacktraceParams {
 // One warp per window.  Per 32-frame block the warp stages every backpointer word the walk can
 // reach (63 states -> NCW thread-columns x NW word-rows, <= 160 words) in shared memory with
 // coalesced loads, then walks the block with one LDS per frame and NO branch on the serial
-// chain; token spans are derived afterwards, lane-parallel, from neighbouring frames' states.
+// chain.  The targets sit in shared memory; the per-frame score gather of block b is issued
+// before, and stored after, the staging loads of block b-1, so each block exposes one memory
+// latency.  Token spans are derived lane-parallel from neighbouring frames' states.
 template <int P>
 __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const BacktraceParams prm) {
-    constexpr int SPW = 8 / P;                 // frames per word
+    constexpr unsigned SPW = 8 / P;            // frames per word
     constexpr int NW = 32 / SPW;               // word-rows per 32-frame block (= 4P)
     constexpr int SPT = 2 * P;                 // states per thread-column
     constexpr int NCW = 62 / SPT + 2;          // thread-columns reachable inside one block
     constexpr int NWORDS = NCW * NW;
-    __shared__ uint32_t raw_s[4][NWORDS];
+    extern __shared__ __align__(16) unsigned char bt_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * (blockDim.x >> 5) + wib;
     if (w >= prm.N) return;
-    uint32_t *raw = raw_s[wib];
+    uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) + (size_t)wib * (NWORDS + prm.Lmax);
+    int32_t *tg_s = reinterpret_cast<int32_t *>(raw + NWORDS);
     const int T = min(prm.in_len[w], prm.Tmax);
     const int L = max(0, min(prm.tgt_len[w], prm.Lmax));
     const int32_t *tg = prm.targets + (int64_t)w * prm.tgt_stride;
@@ -304,21 +307,27 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
             tok_e[l] = -1;
             if (tok_p) tok_p[l] = 0.0f;
         }
-        __syncwarp();
     }
+    for (int l = lane; l < L; l += 32) tg_s[l] = tg[l];
+    __syncwarp();
     if (s < 0 || T <= 0) return;
 
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
     int s_above = -1;  // state of frame t_hi + 1 (none above the last frame)
+    // outputs of the previous (higher) block, stored one iteration late
+    int pend_t = -1, pend_lab = 0;
+    float pend_sc = 0.0f;
 
     for (int blk = (T - 1) >> 5; blk >= 0; --blk) {
-        const int t_hi = min(T - 1, blk * 32 + 31);
-        const int t_lo = blk * 32;
+        const unsigned t_hi = min(T - 1, blk * 32 + 31);
+        const unsigned t_lo = blk * 32;
         const int c_hi = s / SPT;  // thread-column of the state at t_hi
-        // stage raw[row][c_hi - col] for every column the walk can reach
         __syncwarp();
-        {   // all loads in flight before the first store: one exposed memory latency per block
+        {   // every global load of this iteration is issued here, back to back: the staging words
+            // of block b and the score gather of block b+1 (whose states were found last
+            // iteration).  __syncwarp waits for outstanding loads, so none may be in flight at
+            // the loop-top barrier; this way the block exposes ONE memory latency.
             constexpr int NQ = (NWORDS + 31) / 32;
             uint32_t v[NQ];
 #pragma unroll
@@ -328,8 +337,9 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
                 const int col = c_hi - crel;
                 const int wrow = blk * NW + row;
                 v[u] = 0;
-                if (q < NWORDS && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
+                if (q < NWORDS && col >= 0 && wrow * (int)SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
             }
+            if (pend_t >= 0 && scores) pend_sc = lp[(int64_t)pend_t * prm.stride_t + pend_lab];
 #pragma unroll
             for (int u = 0; u < NQ; ++u) {
                 const int q = lane + 32 * u;
@@ -337,27 +347,32 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
             }
         }
         __syncwarp();
+        if (pend_t >= 0) {
+            paths[pend_t] = pend_lab;
+            if (scores) scores[pend_t] = pend_sc;
+        }
         int my_state = 0;
-        const int t_stop = max(t_lo, 1);
-        for (int t = t_hi; t >= t_stop; --t) {
-            my_state = (lane == (t & 31)) ? s : my_state;
+        const unsigned t_stop = max(t_lo, 1u);
+        for (unsigned t = t_hi; t >= t_stop; --t) {
+            my_state = ((unsigned)lane == (t & 31u)) ? s : my_state;
             const int col = s / SPT, k = s & (SPT - 1);
-            const int row = (t / SPW) - blk * NW;
+            const unsigned row = (t / SPW) - blk * NW;
             const uint32_t word = raw[row * NCW + (c_hi - col)];
             s = max(s - (int)((word >> ((t % SPW) * 4 * P + 2 * k)) & 3), 0);
         }
         if (t_lo == 0 && lane == 0) my_state = s;  // frame 0 has no incoming transition
         const int s_below = s;                      // state of frame t_lo - 1 (blk > 0)
-        const int t = t_lo + lane;
+        const int t = (int)t_lo + lane;
         // neighbours' states for the token spans
         int st_up = __shfl_down_sync(0xffffffffu, my_state, 1);
         int st_dn = __shfl_up_sync(0xffffffffu, my_state, 1);
-        if (t == t_hi) st_up = s_above;
+        if (t == (int)t_hi) st_up = s_above;
         if (lane == 0) st_dn = (t_lo == 0) ? -1 : s_below;
-        if (t <= t_hi) {
-            const int lab = (my_state & 1) ? tg[my_state >> 1] : prm.blank;
-            paths[t] = lab;
-            if (scores) scores[t] = lp[(int64_t)t * prm.stride_t + lab];
+        pend_t = -1;
+        if (t <= (int)t_hi) {
+            const int lab = (my_state & 1) ? tg_s[my_state >> 1] : prm.blank;
+            pend_t = t;
+            pend_lab = lab;
             if (want_tok && (my_state & 1)) {
                 if (st_dn != my_state) tok_s[my_state >> 1] = t;
                 if (st_up != my_state) tok_e[my_state >> 1] = t + 1;
@@ -365,12 +380,16 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
         }
         s_above = __shfl_sync(0xffffffffu, my_state, 0);  // state of frame t_lo
     }
+    if (pend_t >= 0) {
+        paths[pend_t] = pend_lab;
+        if (scores) scores[pend_t] = lp[(int64_t)pend_t * prm.stride_t + pend_lab];
+    }
     if (want_tok && tok_p) {
         __syncwarp();
         for (int l = lane; l < L; l += 32) {
             const int a = tok_s[l], b = tok_e[l];
             if (a >= 0 && b > a) {
-                const int lab = tg[l];
+                const int lab = tg_s[l];
                 float acc = 0.0f;
                 for (int t = a; t < b; ++t) acc += lp[(int64_t)t * prm.stride_t + lab];
                 tok_p[l] = acc / (float)(b - a);
@@ -429,19 +448,30 @@ static int dispatch_fill(const ViterbiParams &prm, int Lmax, LatticeShape s, cud
     return IPFA_ERR_UNSUPPORTED;
 }
 
-static int launch_backtrace(const BacktraceParams &prm, int P, cudaStream_t stream) {
-    const int blocks = (prm.N + 3) / 4;
-    switch (P) {
-        case 1: ctc_viterbi_backtrace_kernel<1><<<blocks, 128, 0, stream>>>(prm); break;
-        case 2: ctc_viterbi_backtrace_kernel<2><<<blocks, 128, 0, stream>>>(prm); break;
-        case 4: ctc_viterbi_backtrace_kernel<4><<<blocks, 128, 0, stream>>>(prm); break;
-        case 8: ctc_viterbi_backtrace_kernel<8><<<blocks, 128, 0, stream>>>(prm); break;
-        default: return IPFA_ERR_UNSUPPORTED;
+template <int P>
+static int launch_backtrace_p(const BacktraceParams &prm, cudaStream_t stream) {
+    constexpr int NWORDS = (62 / (2 * P) + 2) * (4 * P);
+    const size_t smem = (size_t)4 * (NWORDS + prm.Lmax) * sizeof(uint32_t);
+    auto kern = ctc_viterbi_backtrace_kernel<P>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     }
+    kern<<<(prm.N + 3) / 4, 128, smem, stream>>>(prm);
     ++g_launch_count;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;
+}
+
+static int launch_backtrace(const BacktraceParams &prm, int P, cudaStream_t stream) {
+    switch (P) {
+        case 1: return launch_backtrace_p<1>(prm, stream);
+        case 2: return launch_backtrace_p<2>(prm, stream);
+        case 4: return launch_backtrace_p<4>(prm, stream);
+        case 8: return launch_backtrace_p<8>(prm, stream);
+        default: return IPFA_ERR_UNSUPPORTED;
+    }
 }
 
 }  // namespace ipfa

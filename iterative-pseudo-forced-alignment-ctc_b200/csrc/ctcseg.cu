@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     constexpr int NW = KC;              // word-rows per 32-frame block
     constexpr int NCW = 31 / KC + 2;    // thread-columns reachable inside one block
     constexpr int NWORDS = NCW * NW;
-    __shared__ uint32_t raw_s[4][NWORDS];
+    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: raw[NWORDS] + gt[Cmax]
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= prm.N * prm.Kmax) return;
@@ -347,7 +347,25 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     // then one LDS per frame, no branch on the serial chain.  Column 0 stores bit 0 (stay).
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
-    uint32_t *raw = raw_s[threadIdx.x >> 5];
+    uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) + (size_t)(threadIdx.x >> 5) * (NWORDS + prm.Cmax);
+    int32_t *gt_s = reinterpret_cast<int32_t *>(raw + NWORDS);
+    for (int cc = lane; cc <= c_end; cc += 32) {
+        int g = gt[cc];
+        if (g < 0 || g >= prm.V) g = prm.blank;
+        gt_s[cc] = g;
+    }
+    // outputs of the previous (higher) block are stored one iteration late, so their emission
+    // gathers overlap the next block's staging loads
+    int pend_t = -1, pend_c = 0, pend_sw = 0;
+    float pend_eb = 0.0f, pend_ec = 0.0f;
+    auto flush_pending = [&]() {
+        if (pend_t >= 0) {
+            const float p = (pend_c == 0) ? pend_eb : (pend_sw ? pend_ec : fmaxf(pend_eb, pend_ec));
+            cprob[pend_t] = p;
+            if (pend_sw && pend_c > 0) timing[pend_c] = pend_t;
+            if (state) state[pend_t] = pend_sw ? pend_c : -1;
+        }
+    };
     // The walk runs on the lattice column lc = c - 1 (lc == -1 is table column 0).  Words of
     // thread-column -1 are staged as zeros, so at lc == -1 the bit reads 0 (stay) and no
     // clamp or select sits on the serial chain: SHR -> ADD -> LDS -> SHF -> AND -> SUB.
@@ -370,6 +388,14 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
                 v[u] = 0;
                 if (q < NWORDS && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
             }
+            // the emission gather of the previous block's frames rides along with the staging
+            // loads: __syncwarp waits for outstanding loads, so none may be in flight at the
+            // loop-top barrier
+            if (pend_t >= 0) {
+                const float *row = lp + (int64_t)pend_t * prm.stride_t;
+                pend_eb = row[prm.blank];
+                pend_ec = row[gt_s[pend_c]];
+            }
 #pragma unroll
             for (int u = 0; u < NQ; ++u) {
                 const int q = lane + 32 * u;
@@ -377,6 +403,7 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
             }
         }
         __syncwarp();
+        flush_pending();
         int my_c = -1, my_sw = 0;
         const int t_stop = max(t_lo, 1);  // (0, c): the loop `while t != 0 or c != 0` ends at (0, 0)
         for (int t = t_hi; t >= t_stop; --t) {
@@ -390,23 +417,19 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
             lc -= sw;
         }
         const int t = t_lo + lane;
+        pend_t = -1;
         if (t <= t_hi && t >= 1 && my_c >= 0) {
-            const float *row = lp + (int64_t)t * prm.stride_t;
-            const float eb = row[prm.blank];
-            float p;
-            if (my_c == 0) {
-                p = eb;
-            } else {
-                int g = gt[my_c];
-                if (g < 0 || g >= prm.V) g = prm.blank;
-                const float ec = row[g];
-                p = my_sw ? ec : fmaxf(eb, ec);
-                if (my_sw) timing[my_c] = t;
-            }
-            cprob[t] = p;
-            if (state) state[t] = my_sw ? my_c : -1;
+            pend_t = t;
+            pend_c = my_c;
+            pend_sw = my_sw;
         }
     }
+    if (pend_t >= 0) {
+        const float *row = lp + (int64_t)pend_t * prm.stride_t;
+        pend_eb = row[prm.blank];
+        pend_ec = row[gt_s[pend_c]];
+    }
+    flush_pending();
     __syncwarp();
     __threadfence_block();
 
@@ -583,12 +606,20 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
     bk.state_out = state_out; bk.status_out = status_out;
     const int warps = N * Kmax;
     const int blocks = (warps + 3) / 4;
-    switch (s.PER) {
-        case 1: ctcseg_backtrace_kernel<1><<<blocks, 128, 0, st>>>(bk); break;
-        case 2: ctcseg_backtrace_kernel<2><<<blocks, 128, 0, st>>>(bk); break;
-        case 4: ctcseg_backtrace_kernel<4><<<blocks, 128, 0, st>>>(bk); break;
-        case 8: ctcseg_backtrace_kernel<8><<<blocks, 128, 0, st>>>(bk); break;
-        default: return IPFA_ERR_UNSUPPORTED;
+    {
+        const int kc = s.PER;
+        const size_t bt_smem = (size_t)4 * ((31 / kc + 2) * kc + Cmax) * sizeof(uint32_t);
+        cudaError_t ea = cudaSuccess;
+#define IPFA_BT(K_)                                                                                     \
+    if (kc == K_) {                                                                                     \
+        if (bt_smem > 48 * 1024)                                                                        \
+            ea = cudaFuncSetAttribute(ctcseg_backtrace_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)bt_smem);                                                    \
+        if (ea == cudaSuccess) ctcseg_backtrace_kernel<K_><<<blocks, 128, bt_smem, st>>>(bk);           \
+    }
+        IPFA_BT(1) IPFA_BT(2) IPFA_BT(4) IPFA_BT(8)
+#undef IPFA_BT
+        if (ea != cudaSuccess) { g_last_cuda_error = ea; return IPFA_ERR_CUDA; }
     }
     ++g_launch_count;
     cudaError_t e = cudaGetLastError();

@@ -195,3 +195,11 @@ def test_full_size_config2_properties(ipfa):
     _check_nll(nll[idx].cpu().numpy(), ref)
     rp, rs, rst = octc.ctc_viterbi(lps, tgn[idx], np.full(len(idx), t, np.int32), np.full(len(idx), l, np.int32))
     assert np.array_equal(paths[idx], rp)
+    # host-buffer entry points (chunked H2D / kernel overlap, other lattice instances per chunk):
+    # same bytes as the device entry points
+    lp_h = lp.cpu().numpy()
+    il_h, tl_h = np.full(n, t, np.int32), np.full(n, l, np.int32)
+    nll_h = ipfa.ctc_alpha_nll_host(lp_h, tgn, il_h, tl_h)
+    np.testing.assert_allclose(nll_h, nll.cpu().numpy(), rtol=2e-6)
+    res_h = ipfa.ctc_forced_align_host(lp_h, tgn, il_h, tl_h, tokens=False)
+    assert np.array_equal(res_h.paths, paths) and np.array_equal(res_h.scores, res.scores.cpu().numpy())
