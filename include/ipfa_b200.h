@@ -134,7 +134,9 @@ int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
  *   state_out     [N, Kmax, Tmax] int32 per-frame column, -1 = stay ("epsilon"),
  *                 -2 = frame not on the path (nullable)
  *   status_out    [N] int32 IPFA_WIN_* bits (IPFA_WIN_TEXT_LONGER <-> AssertionError)
- *   When bit3 is clear only slot Kmax... see DESIGN.md: slot (K_w - 1) is filled.
+ *   With IPFA_SEG_ALL_PREFIXES clear only the full text is aligned: slot K_w - 1 is
+ *   written, the other prefix slots are left untouched.  Slot k-1 fills seg[., k-1, 0..k-1].
+ *   Tmax > 8000 frames (the reference's windowed table mode) returns IPFA_ERR_UNSUPPORTED.
  * ------------------------------------------------------------------------- */
 #define IPFA_SEG_BLANK_COST_ZERO 1
 #define IPFA_SEG_PREAMBLE_COST_ZERO 2
@@ -169,12 +171,16 @@ int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t stride_t,
  *   is_last      [N] int32 window is the last TSV row of its file (:263)
  *   threshold    anchor threshold (-2.0 default), short_len (30 default)
  *   decision_out [N, 4] int32:
- *       [0] accepted prefix length k (0 = nothing accepted / all discarded)
+ *       [0] accepted prefix length k (0 = everything discarded); the rows the reference keeps
+ *           are the k segments of prefix k, the K - k dropped utterances go back to
+ *           discarded_transcripts (last utterance first)
  *       [1] iterations the reference loop would have run
  *       [2] outcome code IPFA_SEL_*
- *       [3] number of utterances pushed back to discarded_transcripts
- *   anchor_out   [N] fp64 new_segment_start relative to the window start (seconds),
- *                NaN when the anchor is rewound to the window start (:277,:329)
+ *       [3] index of the utterance (of prefix k) whose end is the new anchor;
+ *           -1 = rewind to the window start (:277, :329), -2 = anchor unchanged (:263 with no
+ *           segment above the threshold)
+ *   anchor_out   [N] fp64 that utterance's end in seconds from the window start, rounded to
+ *                0.01 like the `{end:.2f}` field the reference parses; NaN for -1 / -2
  * ------------------------------------------------------------------------- */
 #define IPFA_SEL_ACCEPT_CURRENT 0
 #define IPFA_SEL_KEEP_PREVIOUS 1
