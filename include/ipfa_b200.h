@@ -192,6 +192,109 @@ int ipfa_anchor_select_device(const double *seg, const int32_t *n_utts,
                               int N, int Kmax, double threshold, int short_len,
                               int32_t *decision_out, double *anchor_out, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * ipfa_ctcseg_device for windows that are SLICES of resident emissions: window w
+ * starts at lp + win_off[w] (elements; device array) instead of lp + w * stride_n.
+ * Everything else as ipfa_ctcseg_device.
+ * ------------------------------------------------------------------------- */
+int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_off, int64_t stride_t,
+                               const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                               const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+                               int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+                               double index_duration, int score_len, int flags,
+                               double *seg_out, int32_t *term_t_out, int32_t *timing_out,
+                               float *char_prob_out, int32_t *state_out, int32_t *status_out,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Anchor sweep: the iterative anchor loop of many files, resident on the device
+ * (BASELINE.json configs[4]).  Restates the per-row control flow of
+ * /root/reference/src/iterative_utterance_alignment.py:67-402 over emissions that
+ * were computed once per file; a window is the frame slice
+ *   [int(clip_start * sample_rate) / frame_shift, + int(audio_samples / frame_shift))
+ * of its file.  One lock-step iteration = window construction (:67-192), the
+ * all-prefix CTC segmentation (:208-219), the accept/shrink/revert decision
+ * (:221-379) and the anchor / pending-text update, for one window of every active
+ * file; nothing returns to the host in between.
+ *
+ * Corpus (device arrays, read only).  File f owns rows [row_first[f], row_first[f+1])
+ * and utterance slots utt_first[f] + i, i = 0..U_f (U_f utterances + one closing slot).
+ * ------------------------------------------------------------------------- */
+typedef struct ipfa_sweep_corpus {
+    const float *lp;             /* [total frames, V] log-probs of all files, file after file */
+    int64_t stride_t;            /* elements between frames (>= V) */
+    int32_t V, blank, n_files, reserved;
+    const int64_t *file_frame0;  /* [F] first frame of the file inside lp */
+    const int32_t *file_frames;  /* [F] frames of the file */
+    const int64_t *file_samples; /* [F] audio samples of the file (torchaudio.info num_frames) */
+    const int32_t *row_first;    /* [F+1] */
+    const int32_t *row_type;     /* [R] 0 = speech row, 1 = 'Non-Speech' row (:73) */
+    const double *row_start;     /* [R] seconds (TSV 'Start' after fix_time_reference) */
+    const double *row_end;       /* [R] seconds */
+    const int32_t *row_utt_end;  /* [R] file-relative index one past the row's last utterance */
+    const int32_t *utt_first;    /* [F+1] */
+    const int32_t *utt_col;      /* [slots] position in the file's token stream of the blank in front
+                                    of utterance i; slot U_f: the closing blank */
+    const int32_t *utt_chars;    /* [slots] len(text) of utterance i (short-utterance rule, text length) */
+    const int64_t *file_tok0;    /* [F] start of the file's token stream inside tokens */
+    const int32_t *tokens;       /* per file: blank, tokens(utt 0), blank, tokens(utt 1), ..., blank
+                                    (prepare_token_list without its leading -1) */
+} ipfa_sweep_corpus;
+
+/* Per-file loop state (device arrays [F], read and written by the sweep).  Initial values:
+ * row = utt = exc = next_ns = n_windows = cells = 0, anchor = follow_start = NaN (None),
+ * prop = 0.0, status = IPFA_SWEEP_ACTIVE, recalc_row = -1. */
+typedef struct ipfa_sweep_state {
+    int32_t *row;          /* next TSV row of the file */
+    int32_t *utt;          /* first utterance not accepted yet (the pending/discarded ones follow) */
+    double *anchor;        /* new_segment_start in seconds, NaN = None (:37) */
+    double *prop;          /* last text_to_audio_proportion (kept across rows like the reference) */
+    int32_t *next_ns;      /* last next_row_is_non_speech (:113) */
+    double *follow_start;  /* last following_row['Start'] (:112), NaN = none yet */
+    int32_t *exc;          /* consecutive AssertionError count (:396) */
+    int32_t *status;       /* IPFA_SWEEP_* */
+    int32_t *need;         /* [F][3] (frames, columns, utterances) wanted when status == CAPACITY */
+    int32_t *recalc_row;   /* row whose times the host already re-spread (:127-146), -1 = none */
+    int32_t *n_windows;    /* windows aligned so far */
+    int64_t *cells;        /* trellis cells (frames x columns) filled so far */
+} ipfa_sweep_state;
+
+typedef struct ipfa_sweep_params {
+    double threshold;               /* -2.0 */
+    double max_window_size;         /* 70.0 s  (:119) */
+    double window_to_stop;          /* 500.0 s (:125) */
+    double min_text_to_audio_prop;  /* 0.8     (:176) */
+    double samples_to_frames_ratio; /* aligner.estimate_samples_to_frames_ratio() (:420) */
+    double index_duration;          /* seconds per frame = samples_to_frames_ratio / fs */
+    int32_t short_len;              /* 30 (:241) */
+    int32_t max_exceptions;         /* 10 (:397) */
+    int32_t sample_rate;            /* 16000 */
+    int32_t frame_shift;            /* audio samples per emission frame (slicing of lp) */
+    int32_t score_len;              /* 30 (scoring_length) */
+    int32_t seg_flags;              /* IPFA_SEG_* (IPFA_SEG_ALL_PREFIXES is added) */
+} ipfa_sweep_params;
+
+#define IPFA_SWEEP_ACTIVE 0
+#define IPFA_SWEEP_DONE 1            /* all rows consumed */
+#define IPFA_SWEEP_STOP_WINDOW 2     /* clip_length >= window_to_stop (:125 break) */
+#define IPFA_SWEEP_STOP_EXCEPTIONS 3 /* max_text_to_audio_prop_exec consecutive AssertionErrors (:397) */
+#define IPFA_SWEEP_NEEDS_RECALC 4    /* :119-146 fix_text_to_time_proportion is host policy: re-spread the
+                                        rows, upload them, set recalc_row = row, status = ACTIVE */
+#define IPFA_SWEEP_CAPACITY 5        /* window exceeds (Tmax, Cmax, Kmax): see need[], grow and continue */
+
+/* out_seg [slots][4] fp64: (clip_start, start, end, score) of every accepted utterance --
+ * start/end rounded to 0.01 s and score to 1e-4 like the `str(task)` round trip (:219-230), the
+ * short-utterance penalty already added (:241); absolute times are clip_start + start / end.
+ * out_info [slots][2] int32: (iteration that accepted the utterance, file-relative TSV row that was
+ * being aligned -- the row whose Channel / Speaker_ID / Database the result row carries, :258);
+ * the caller initialises it to -1.
+ * Runs n_steps iterations numbered first_step...; status words say when every file is finished. */
+size_t ipfa_sweep_workspace_bytes(int n_files, int Tmax, int Cmax, int Kmax, int V);
+int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipfa_sweep_params *params,
+                           const ipfa_sweep_state *state, double *out_seg, int32_t *out_info,
+                           int first_step, int n_steps, int Tmax, int Cmax, int Kmax,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

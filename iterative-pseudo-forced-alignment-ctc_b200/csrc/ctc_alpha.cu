@@ -82,13 +82,22 @@ ctc_alpha_kernel(const AlphaParams prm) {
         skip[p] = lab_ok && j >= 1 && prev != lab;
         col[p] = DENSE ? lab : (lab_ok ? j + 1 : 0);
     }
-    const int colb = DENSE ? blank : 0;
+    int colb = DENSE ? blank : 0;
+    int U = L + 1;  // panel columns
     if constexpr (!DENSE) {
         for (int j = tid; j <= L; j += NT) {
             int c = (j == 0) ? blank : tg[j - 1];
             if (c < 0 || c >= prm.V) c = blank;
             cols[j] = c;
         }
+        group_sync<WARPS>();
+        // ascending, unique column list; the emission ring (idle until the prologue) is scratch
+        int *scratch = reinterpret_cast<int *>(ring);
+        U = sort_unique_columns<WARPS>(cols, L + 1, scratch, tid);
+        const int *pos = scratch + 2 * (L + 1);
+#pragma unroll
+        for (int p = 0; p < P; ++p) col[p] = pos[col[p]];
+        colb = pos[0];
     }
     if constexpr (WARPS > 1) {
         if (tid < 2) xline[tid * (NT + 1)] = kNegBig;  // left neighbour of thread 0: log(0)
@@ -96,7 +105,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
     group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, prm.pitch,
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, U, prm.V, prm.pitch,
               prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
     pipe.prologue(tid);
 

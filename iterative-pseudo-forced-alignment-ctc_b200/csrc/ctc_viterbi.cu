@@ -97,13 +97,22 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     }
     if (n_rep) atomicAdd(&cnt[0], n_rep);
     if (n_bad) atomicAdd(&cnt[1], n_bad);
-    const int colb = DENSE ? blank : 0;
+    int colb = DENSE ? blank : 0;
+    int U = L + 1;  // panel columns
     if constexpr (!DENSE) {
         for (int j = tid; j <= L; j += NT) {
             int c = (j == 0) ? blank : tg[j - 1];
             if (c < 0 || c >= prm.V) c = blank;
             cols[j] = c;
         }
+        group_sync<WARPS>();
+        // ascending, unique column list; the emission ring (idle until the prologue) is scratch
+        int *scratch = reinterpret_cast<int *>(ring);
+        U = sort_unique_columns<WARPS>(cols, L + 1, scratch, tid);
+        const int *pos = scratch + 2 * (L + 1);
+#pragma unroll
+        for (int p = 0; p < P; ++p) col[p] = pos[col[p]];
+        colb = pos[0];
     }
     group_sync<WARPS>();
     const int R = cnt[0];
@@ -119,7 +128,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     }
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, L + 1, prm.V, pitch, prm.tc,
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, U, prm.V, pitch, prm.tc,
               reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
     pipe.prologue(tid);
 

@@ -39,6 +39,7 @@ constexpr float kProbMax = -1000000000.0f;  // cdef float prob_max = -1000000000
 
 struct SegFillParams {
     const float *lp;
+    const int64_t *win_off;  // optional per-window element offset into lp (replaces w * stride_n)
     int64_t stride_n, stride_t;
     const int32_t *in_len;
     const int32_t *gt;
@@ -100,13 +101,22 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         if (g < 0 || g >= prm.V) g = blank;
         col[k] = DENSE ? g : ((c < NC) ? c : 0);
     }
-    const int colb = DENSE ? blank : 0;
+    int colb = DENSE ? blank : 0;
+    int U = NC;  // panel columns
     if constexpr (!DENSE) {
         for (int j = tid; j < NC; j += NT) {
             int g = (j == 0) ? blank : gt[j];
             if (g < 0 || g >= prm.V) g = blank;
             cols[j] = g;
         }
+        group_sync<WARPS>();
+        // ascending, unique column list; the emission ring (idle until the prologue) is scratch
+        int *scratch = reinterpret_cast<int *>(ring);
+        U = sort_unique_columns<WARPS>(cols, NC, scratch, tid);
+        const int *pos = scratch + 2 * NC;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) col[k] = pos[col[k]];
+        colb = pos[0];
     }
     // only the utterance-boundary columns need their first argmax over t; a warp that owns
     // none of them skips the tracking code altogether
@@ -127,7 +137,8 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, NC, prm.V, pitch, prm.tc,
+    pipe.init(ring, cols, prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n), prm.stride_t, T, U,
+              prm.V, pitch, prm.tc,
               reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
     pipe.prologue(tid);
 
@@ -276,6 +287,7 @@ __device__ double np_pairwise_sum(const float *a, int n) {
 
 struct SegBackParams {
     const float *lp;
+    const int64_t *win_off;
     int64_t stride_n, stride_t;
     const int32_t *in_len;
     const int32_t *gt;
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
 
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
-    const float *lp = prm.lp + (int64_t)w * prm.stride_n;
+    const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
     const int64_t slot = (int64_t)w * prm.Kmax + kslot;
     int32_t *timing = prm.timing + slot * prm.Cmax;
     float *cprob = prm.char_prob + slot * prm.Tmax;
@@ -557,14 +569,17 @@ extern "C" size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kma
     return b + 256;
 }
 
-extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t stride_t,
-                                  const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
-                                  const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
-                                  int N, int Tmax, int Cmax, int Kmax, int V, int blank,
-                                  double index_duration, int score_len, int flags, double *seg_out,
-                                  int32_t *term_t_out, int32_t *timing_out, float *char_prob_out,
-                                  int32_t *state_out, int32_t *status_out, void *workspace,
-                                  size_t workspace_bytes, void *stream) {
+namespace ipfa {
+// Shared by ipfa_ctcseg_device (windows at w * stride_n) and ipfa_ctcseg_windows_device /
+// the anchor sweep (windows at win_off[w], slices of corpus-resident emissions).
+int ctcseg_run(const float *lp, const int64_t *win_off, int64_t stride_n, int64_t stride_t,
+               const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+               const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+               int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+               double index_duration, int score_len, int flags, double *seg_out,
+               int32_t *term_t_out, int32_t *timing_out, float *char_prob_out,
+               int32_t *state_out, int32_t *status_out, void *workspace,
+               size_t workspace_bytes, void *stream) {
     if (N == 0) return IPFA_OK;
     if (!lp || !in_len || !gt || !n_cols || !utt_begin || !n_utts || !seg_out || !term_t_out ||
         !status_out || !workspace || N < 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || V <= 0 || blank < 0 ||
@@ -586,7 +601,7 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
     float *cprob_scratch = reinterpret_cast<float *>(ws);
 
     SegFillParams fp{};
-    fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t; fp.in_len = in_len;
+    fp.lp = lp; fp.win_off = win_off; fp.stride_n = stride_n; fp.stride_t = stride_t; fp.in_len = in_len;
     fp.gt = gt; fp.gt_stride = gt_stride; fp.n_cols = n_cols; fp.utt_begin = utt_begin; fp.n_utts = n_utts;
     fp.Kmax = Kmax;
     fp.N = N; fp.Tmax = Tmax; fp.Cmax = Cmax; fp.V = V; fp.blank = blank; fp.flags = flags;
@@ -595,7 +610,7 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
     if (rc) return rc;
 
     SegBackParams bk{};
-    bk.lp = lp; bk.stride_n = stride_n; bk.stride_t = stride_t; bk.in_len = in_len;
+    bk.lp = lp; bk.win_off = win_off; bk.stride_n = stride_n; bk.stride_t = stride_t; bk.in_len = in_len;
     bk.gt = gt; bk.gt_stride = gt_stride; bk.n_cols = n_cols; bk.utt_begin = utt_begin; bk.n_utts = n_utts;
     bk.N = N; bk.Tmax = Tmax; bk.Cmax = Cmax; bk.Kmax = Kmax; bk.V = V; bk.blank = blank; bk.flags = flags;
     bk.NT = 32 * s.WARPS; bk.score_len = score_len; bk.index_duration = index_duration;
@@ -625,4 +640,32 @@ extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t str
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;
+}
+}  // namespace ipfa
+
+extern "C" int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t stride_t,
+                                  const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                                  const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+                                  int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+                                  double index_duration, int score_len, int flags, double *seg_out,
+                                  int32_t *term_t_out, int32_t *timing_out, float *char_prob_out,
+                                  int32_t *state_out, int32_t *status_out, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    return ipfa::ctcseg_run(lp, nullptr, stride_n, stride_t, in_len, gt, gt_stride, n_cols, utt_begin, n_utts, N,
+                            Tmax, Cmax, Kmax, V, blank, index_duration, score_len, flags, seg_out, term_t_out,
+                            timing_out, char_prob_out, state_out, status_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_off, int64_t stride_t,
+                                          const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                                          const int32_t *n_cols, const int32_t *utt_begin,
+                                          const int32_t *n_utts, int N, int Tmax, int Cmax, int Kmax, int V,
+                                          int blank, double index_duration, int score_len, int flags,
+                                          double *seg_out, int32_t *term_t_out, int32_t *timing_out,
+                                          float *char_prob_out, int32_t *state_out, int32_t *status_out,
+                                          void *workspace, size_t workspace_bytes, void *stream) {
+    if (N > 0 && !win_off) return IPFA_ERR_INVALID_ARG;
+    return ipfa::ctcseg_run(lp, win_off, 0, stride_t, in_len, gt, gt_stride, n_cols, utt_begin, n_utts, N, Tmax,
+                            Cmax, Kmax, V, blank, index_duration, score_len, flags, seg_out, term_t_out,
+                            timing_out, char_prob_out, state_out, status_out, workspace, workspace_bytes, stream);
 }

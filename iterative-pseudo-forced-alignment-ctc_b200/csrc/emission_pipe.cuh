@@ -28,6 +28,40 @@ __device__ __forceinline__ void group_sync() {
     }
 }
 
+
+// Gather mode: sort + dedup a window's column list so that the lanes of one gather
+// instruction walk ascending addresses (a warp touches a handful of 128-byte lines of the
+// vocabulary row instead of 32 -- the L1 wavefront count is what bounds the V = 5000 gather).
+// In : cols[0..U) raw column ids (>= 0).  scratch: 3*U ints (the emission ring, not yet in use).
+// Out: cols[0..U') ascending and unique; scratch[2U + j] = panel position of raw column j.
+// Returns U'.  All threads of the group call it; ends with a group barrier.
+template <int WARPS>
+__device__ __forceinline__ int sort_unique_columns(int *cols, int U, int *scratch, int tid) {
+    constexpr int NT = 32 * WARPS;
+    int *raw = scratch, *first = scratch + U, *pos = scratch + 2 * U;
+    for (int j = tid; j < U; j += NT) raw[j] = cols[j];
+    group_sync<WARPS>();
+    for (int j = tid; j < U; j += NT) {
+        const int v = raw[j];
+        int f = 1;
+        for (int k = 0; k < j; ++k)
+            if (raw[k] == v) { f = 0; break; }
+        first[j] = f;
+    }
+    group_sync<WARPS>();
+    int n_unique = 0;
+    for (int k = 0; k < U; ++k) n_unique += first[k];
+    for (int j = tid; j < U; j += NT) {
+        const int v = raw[j];
+        int r = 0;
+        for (int k = 0; k < U; ++k) r += (first[k] != 0) & (raw[k] < v);
+        pos[j] = r;
+        if (first[j]) cols[r] = v;
+    }
+    group_sync<WARPS>();
+    return n_unique;
+}
+
 template <int WARPS, bool DENSE>
 struct EmissionPipe {
     static constexpr int NT = 32 * WARPS;

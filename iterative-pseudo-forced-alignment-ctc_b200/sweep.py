@@ -1,0 +1,303 @@
+"""Corpus-resident anchor sweep: the iterative anchor loop of many files in lock step.
+
+Drives ``ipfa_sweep_step_device`` (``csrc/anchor_sweep.cu``), which restates the per-row
+control flow of /root/reference/src/iterative_utterance_alignment.py:67-402 on the device
+for files whose emissions were computed once and stay in
+HBM.  One iteration aligns one window of every active file -- window construction, the
+all-prefix CTC segmentation, the accept / shrink / revert decision and the anchor update
+-- with no host round trip; the host polls the per-file status words every few iterations.
+
+The result rows are the ``file_alignments`` entries the reference appends (:258-260),
+``RESULT_COLUMNS`` order, ready for ``to_csv(sep='\\t')``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import hostglue as hg
+from ._lib import check, lib
+
+ACTIVE, DONE, STOP_WINDOW, STOP_EXCEPTIONS, NEEDS_RECALC, CAPACITY = range(6)
+STATUS_NAMES = ["active", "done", "window_to_stop", "exceptions_limit", "needs_recalc", "capacity"]
+
+_vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+
+
+class _Corpus(ctypes.Structure):
+    _fields_ = [("lp", _vp), ("stride_t", _i64), ("V", _i32), ("blank", _i32), ("n_files", _i32),
+                ("reserved", _i32), ("file_frame0", _vp), ("file_frames", _vp), ("file_samples", _vp),
+                ("row_first", _vp), ("row_type", _vp), ("row_start", _vp), ("row_end", _vp),
+                ("row_utt_end", _vp), ("utt_first", _vp), ("utt_col", _vp), ("utt_chars", _vp),
+                ("file_tok0", _vp), ("tokens", _vp)]
+
+
+class _State(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("row", "utt", "anchor", "prop", "next_ns", "follow_start", "exc", "status",
+                                   "need", "recalc_row", "n_windows", "cells")]
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [("threshold", _f64), ("max_window_size", _f64), ("window_to_stop", _f64),
+                ("min_text_to_audio_prop", _f64), ("samples_to_frames_ratio", _f64), ("index_duration", _f64),
+                ("short_len", _i32), ("max_exceptions", _i32), ("sample_rate", _i32), ("frame_shift", _i32),
+                ("score_len", _i32), ("seg_flags", _i32)]
+
+
+class SweepFile:
+    """One audio file of the corpus.
+
+    ``lpz``: fp32 [T, V] log-posteriors of the WHOLE file (torch tensor, any device);
+    ``n_samples``: audio samples (``torchaudio.info(...).num_frames``);
+    ``rows``: the file's TSV rows after ``fix_time_reference`` (:52-57), each a dict with
+    ``Type`` ('Speech' / 'Non-Speech'), ``Start``, ``End``, ``utterances`` (list of str, the
+    output of ``prepare_text`` at :89) and the metadata the result rows carry
+    (``Channel``, ``Speaker_ID``, ``Database``)."""
+
+    def __init__(self, file_id, audio_path, lpz, n_samples, rows):
+        self.file_id, self.audio_path, self.lpz, self.n_samples, self.rows = \
+            file_id, audio_path, lpz, int(n_samples), rows
+
+
+def rows_from_dataframe(file_df, max_words_sequence=24):
+    """TSV rows (after ``fix_time_reference``) -> ``SweepFile.rows`` (:79-89)."""
+    rows = []
+    for _, row in file_df.iterrows():
+        if row['Type'] == 'Non-Speech':
+            rows.append({"Type": 'Non-Speech', "Start": float(row['Start']), "End": float(row['End']),
+                         "utterances": []})
+            continue
+        transcript = hg.prepare_text(str(row['Transcription']).upper(), max_words_sequence=max_words_sequence)
+        if isinstance(transcript, str):
+            transcript = [transcript]
+        rows.append({"Type": row['Type'], "Start": float(row['Start']), "End": float(row['End']),
+                     "utterances": list(transcript), "Channel": row['Channel'],
+                     "Speaker_ID": row['Speaker_ID'], "Database": row['Database']})
+    return rows
+
+
+def pack_files(files, tokenizer, blank=0):
+    """Flat host arrays of ``ipfa_sweep_corpus`` (include/ipfa_b200.h) + per-file utterance texts.
+
+    File f's token stream is ``blank, tokens(u0), blank, tokens(u1), ..., blank``: the
+    ground-truth column ``prepare_token_list`` builds for utterances [a, b) of the file is
+    ``[-1] + stream[utt_col[a] : utt_col[b] + 1]``."""
+    unk = tokenizer.unk_id() if hasattr(tokenizer, "unk_id") else -1
+    a = {k: [] for k in ("file_frame0", "file_frames", "file_samples", "row_type", "row_start", "row_end",
+                         "row_utt_end", "utt_col", "utt_chars", "file_tok0", "tokens")}
+    a["row_first"], a["utt_first"] = [0], [0]
+    all_texts = []
+    frame0 = 0
+    for f in files:
+        a["file_frame0"].append(frame0)
+        a["file_frames"].append(int(f.lpz.shape[0]))
+        frame0 += int(f.lpz.shape[0])
+        a["file_samples"].append(f.n_samples)
+        a["file_tok0"].append(len(a["tokens"]))
+        texts = []
+        col = 0
+        for row in f.rows:
+            speech = row["Type"] != 'Non-Speech'
+            a["row_type"].append(0 if speech else 1)
+            a["row_start"].append(float(row["Start"]))
+            a["row_end"].append(float(row["End"]))
+            if speech:
+                for utt in row["utterances"]:
+                    ids = np.asarray(tokenizer.encode_as_ids(utt), dtype=np.int64)
+                    ids = ids[ids != unk] if ids.size else ids
+                    if ids.size == 0 or ids[-1] == blank or ids[0] == blank:
+                        # prepare_token_list would merge the neighbouring blanks; such windows are
+                        # not slices of one token stream
+                        raise ValueError(f"utterance without tokens in {f.file_id!r}: {utt!r}")
+                    a["utt_col"].append(col)
+                    a["utt_chars"].append(len(utt))
+                    a["tokens"].append(blank)
+                    a["tokens"].extend(int(i) for i in ids)
+                    col += 1 + ids.size
+                    texts.append(utt)
+            a["row_utt_end"].append(len(texts))
+        a["utt_col"].append(col)   # closing blank
+        a["utt_chars"].append(0)
+        a["tokens"].append(blank)
+        a["row_first"].append(len(a["row_type"]))
+        a["utt_first"].append(len(a["utt_col"]))
+        all_texts.append(texts)
+    dtypes = dict(file_frame0=np.int64, file_samples=np.int64, file_tok0=np.int64, row_start=np.float64,
+                  row_end=np.float64)
+    return {k: np.asarray(v, dtype=dtypes.get(k, np.int32)) for k, v in a.items()}, all_texts
+
+
+class SweepCorpus:
+    """Files packed into the device arrays of ``ipfa_sweep_corpus``; emissions resident in HBM."""
+
+    def __init__(self, files, tokenizer, blank=0, device=None):
+        if not files:
+            raise ValueError("empty corpus")
+        self.files = files
+        device = torch.device(device) if device is not None else files[0].lpz.device
+        if device.type != "cuda":
+            raise ValueError("the anchor sweep runs on a CUDA device (no CPU fallback)")
+        self.device = device
+        self.blank = blank
+        self.host, self.texts = pack_files(files, tokenizer, blank)
+        self.lp = torch.cat([f.lpz.to(device=device, dtype=torch.float32) for f in files], dim=0).contiguous()
+        self.V = int(self.lp.shape[1])
+        self.n_slots = len(self.host["utt_col"])
+        self.arrays = {k: torch.as_tensor(v, device=device) for k, v in self.host.items()}
+
+    def struct(self):
+        c = _Corpus()
+        c.lp = self.lp.data_ptr()
+        c.stride_t = self.lp.stride(0)
+        c.V, c.blank, c.n_files = self.V, self.blank, len(self.files)
+        for k, t in self.arrays.items():
+            setattr(c, k, t.data_ptr())
+        return c
+
+    def total_frames(self):
+        return int(self.lp.shape[0])
+
+
+class AnchorSweep:
+    """Runs the anchor loop of every file of a :class:`SweepCorpus` on its device."""
+
+    def __init__(self, corpus, index_duration, samples_to_frames_ratio, frame_shift=None, sample_rate=16000,
+                 threshold=-2.0, short_utterance_len=30, max_window_size=70.0, window_to_stop=500.0,
+                 min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, scoring_length=30, seg_flags=2,
+                 capacity=None):
+        self.corpus = corpus
+        dev = corpus.device
+        n = len(corpus.files)
+        p = _Params()
+        p.threshold, p.max_window_size, p.window_to_stop = threshold, max_window_size, window_to_stop
+        p.min_text_to_audio_prop = min_text_to_audio_prop
+        p.samples_to_frames_ratio = float(samples_to_frames_ratio)
+        p.index_duration = float(index_duration)
+        p.short_len, p.max_exceptions, p.sample_rate = short_utterance_len, max_text_to_audio_prop_exec, sample_rate
+        p.frame_shift = int(frame_shift if frame_shift is not None else round(samples_to_frames_ratio))
+        p.score_len, p.seg_flags = scoring_length, seg_flags
+        self.params = p
+        nan = float("nan")
+        self.state = dict(
+            row=torch.zeros(n, dtype=torch.int32, device=dev), utt=torch.zeros(n, dtype=torch.int32, device=dev),
+            anchor=torch.full((n,), nan, dtype=torch.float64, device=dev),
+            prop=torch.zeros(n, dtype=torch.float64, device=dev),
+            next_ns=torch.zeros(n, dtype=torch.int32, device=dev),
+            follow_start=torch.full((n,), nan, dtype=torch.float64, device=dev),
+            exc=torch.zeros(n, dtype=torch.int32, device=dev),
+            status=torch.zeros(n, dtype=torch.int32, device=dev),
+            need=torch.zeros((n, 3), dtype=torch.int32, device=dev),
+            recalc_row=torch.full((n,), -1, dtype=torch.int32, device=dev),
+            n_windows=torch.zeros(n, dtype=torch.int32, device=dev),
+            cells=torch.zeros(n, dtype=torch.int64, device=dev))
+        self.out_seg = torch.zeros((corpus.n_slots, 4), dtype=torch.float64, device=dev)
+        self.out_info = torch.full((corpus.n_slots, 2), -1, dtype=torch.int32, device=dev)
+        self.steps = 0
+        self.capacity = list(capacity) if capacity else self._initial_capacity()
+        self._ws = None
+        self._ws_cap = None
+
+    def _initial_capacity(self):
+        """(Tmax, Cmax, Kmax) that holds every single row's own window."""
+        c, p = self.corpus, self.params
+        h = c.host
+        t_max, c_max, k_max = 64, 16, 2
+        for f in range(len(c.files)):
+            u_prev = 0
+            for r in range(h["row_first"][f], h["row_first"][f + 1]):
+                if h["row_type"][r] == 1:
+                    continue
+                u1 = int(h["row_utt_end"][r])
+                s0 = int(h["utt_first"][f])
+                c_max = max(c_max, int(h["utt_col"][s0 + u1] - h["utt_col"][s0 + u_prev]) + 2)
+                k_max = max(k_max, u1 - u_prev)
+                t_max = max(t_max, int((h["row_end"][r] - h["row_start"][r]) * p.sample_rate) // p.frame_shift + 1)
+                u_prev = u1
+        # head-room for pending utterances and anchors that lag behind the row start
+        return [min(8000, int(t_max * 1.5) + 8), int(c_max * 2) + 8, int(k_max * 2) + 2]
+
+    def _state_struct(self):
+        s = _State()
+        for k, t in self.state.items():
+            setattr(s, k, t.data_ptr())
+        return s
+
+    def _workspace(self):
+        cap = tuple(self.capacity)
+        if self._ws_cap != cap:
+            nbytes = lib().ipfa_sweep_workspace_bytes(len(self.corpus.files), cap[0], cap[1], cap[2], self.corpus.V)
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.corpus.device)
+            self._ws_cap = cap
+        return self._ws
+
+    def step(self, n_steps=1):
+        """``n_steps`` lock-step iterations, asynchronous on the current stream."""
+        c = self.corpus
+        ws = self._workspace()
+        cs, ss = c.struct(), self._state_struct()
+        with torch.cuda.device(c.device):
+            rc = lib().ipfa_sweep_step_device(
+                ctypes.byref(cs), ctypes.byref(self.params), ctypes.byref(ss), self.out_seg.data_ptr(),
+                self.out_info.data_ptr(), self.steps, n_steps, self.capacity[0], self.capacity[1],
+                self.capacity[2], ws.data_ptr(), ws.numel(), torch.cuda.current_stream(c.device).cuda_stream)
+        check(rc, "ipfa_sweep_step_device")
+        self.steps += n_steps
+
+    def run(self, steps_per_poll=8, max_steps=100000, recalc_fn=None):
+        """Iterate until no file is active.  ``recalc_fn(sweep, file_index)`` may re-spread the rows
+        of a file that stopped with NEEDS_RECALC (the reference's ``fix_text_to_time_proportion``,
+        :127-146) and return True to resume it.  Returns the per-file status array (host)."""
+        while self.steps < max_steps:
+            self.step(steps_per_poll)
+            status = self.state["status"].cpu().numpy()
+            if (status == CAPACITY).any():
+                need = self.state["need"].cpu().numpy()[status == CAPACITY].max(axis=0)
+                grew = False
+                for i in range(3):
+                    if need[i] > self.capacity[i]:
+                        self.capacity[i] = int(need[i] * 1.25) + 4
+                        grew = True
+                self.capacity[0] = min(self.capacity[0], 8000)
+                if need[0] > 8000 or not grew:
+                    # windowed table mode (T > 8000 frames) is not on the device path
+                    break
+                self.state["status"][self.state["status"] == CAPACITY] = ACTIVE
+                continue
+            if recalc_fn is not None and (status == NEEDS_RECALC).any():
+                resumed = False
+                for f in np.nonzero(status == NEEDS_RECALC)[0]:
+                    resumed |= bool(recalc_fn(self, int(f)))
+                if resumed:
+                    continue
+            if not (status == ACTIVE).any():
+                break
+        return self.state["status"].cpu().numpy()
+
+    # ------------------------------------------------------------------ results
+    def file_rows(self):
+        """Per file: the rows the reference would have appended to ``file_alignments`` (:258-260)."""
+        c = self.corpus
+        seg = self.out_seg.cpu().numpy()
+        info = self.out_info.cpu().numpy()
+        out = []
+        for f, sf in enumerate(c.files):
+            s0 = int(c.host["utt_first"][f])
+            rows = []
+            for u, text in enumerate(c.texts[f]):
+                if info[s0 + u, 0] < 0:
+                    continue
+                clip_start, start, end, score = (float(x) for x in seg[s0 + u])
+                meta = sf.rows[int(info[s0 + u, 1])]
+                abs_start, abs_end = clip_start + start, clip_start + end
+                segment_id = "_".join([sf.file_id, str(abs_start), str(abs_end)])
+                rows.append([segment_id, sf.audio_path, meta.get("Channel"), end - start, abs_start, abs_end,
+                             score, text, meta.get("Speaker_ID"), meta.get("Database")])
+            out.append(rows)
+        return out
+
+    def stats(self):
+        return {"steps": self.steps, "windows": int(self.state["n_windows"].sum().item()),
+                "cells": int(self.state["cells"].sum().item()),
+                "status": {STATUS_NAMES[k]: int(v) for k, v in
+                           zip(*np.unique(self.state["status"].cpu().numpy(), return_counts=True))}}

@@ -1,0 +1,148 @@
+"""Device-resident anchor sweep (BASELINE configs[4]) vs the per-file host loop driven by the
+CPU oracle: identical ``file_alignments`` rows for every file of a small synthetic corpus.
+
+The acoustic model is a test double whose emissions are a pure function of the absolute
+frame index, so "re-encode the clip" (the reference, :149-201) and "slice the file's
+emissions" (the sweep) see the same log-probabilities."""
+import importlib
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from scripted_asr import ScriptedASR, make_schedule
+from test_gpu_pipeline import _utterances, oracle_window_fn
+
+pytestmark = pytest.mark.gpu
+
+PKG = "iterative-pseudo-forced-alignment-ctc_b200"
+hg = importlib.import_module(PKG + ".hostglue")
+anchor = importlib.import_module(PKG + ".anchor")
+cs = importlib.import_module(PKG + ".ctc_segmentation")
+sweep = importlib.import_module(PKG + ".sweep")
+stub = importlib.import_module(PKG + ".stub_asr")
+
+
+class ExactASR(ScriptedASR):
+    """The synthetic 'audio' carries its absolute sample index exactly (float64)."""
+
+    @torch.no_grad()
+    def encode_batch(self, wavs, wav_lens=None):
+        x = wavs[0].double()
+        n = x.shape[0] // self.stride
+        if n == 0:
+            return torch.zeros(1, 0, self.logits.shape[1], device=self.device)
+        f0 = int(x[0].item()) // self.stride
+        idx = torch.arange(f0, f0 + n).clamp(max=self.logits.shape[0] - 1)
+        return self.logits[idx].unsqueeze(0).to(self.device)
+
+
+def _corpus_file(name, n_utts, seed, corrupt=(), vad_gap=None):
+    rng = np.random.default_rng(seed)
+    utts = _utterances(rng, n_utts)
+    tok = stub.CharTokenizer()
+    frames, spans = make_schedule([u.upper() for u in utts], tok, rng)
+    total = (len(frames) + 40) * 320
+    dur = total / 16000
+    wav = f"/synthetic/{name}.wav"
+    df = pd.DataFrame({'Sample_ID': [f"{name}_{i}" for i in range(n_utts)], 'Sample_Path': [wav] * n_utts,
+                       'Channel': [1] * n_utts, 'Audio_Length': [dur / n_utts] * n_utts,
+                       'Start': [0.0] * n_utts, 'End': [dur] * n_utts, 'Transcription': utts,
+                       'Speaker_ID': ['spk' + name] * n_utts, 'Database': ['synthetic'] * n_utts})
+    if vad_gap is None:
+        vad = pd.DataFrame({'Sample_Path': [wav], 'Start': [0.0], 'End': [dur], 'Segment_Length': [dur]})
+    else:
+        a, b = vad_gap
+        vad = pd.DataFrame({'Sample_Path': [wav] * 2, 'Start': [0.0, b], 'End': [a, dur],
+                            'Segment_Length': [a, dur - b]})
+    asr = ExactASR(frames, total, device="cuda", corrupt=corrupt, seed=seed)
+    return dict(name=name, wav=wav, df=df, vad=vad, total=total, asr=asr)
+
+
+@pytest.fixture()
+def exact_audio(monkeypatch):
+    """audio_info / audio_load stand-ins: sample i of every synthetic file has the value i."""
+    totals = {}
+
+    def info(path):
+        return hg.AudioInfo(totals[path], 16000, 1)
+
+    def load(path, frame_offset=0, num_frames=-1, channels_first=False):
+        total = totals[path]
+        frame_offset = max(0, min(int(frame_offset), total))
+        n = total - frame_offset if num_frames is None or num_frames < 0 else \
+            max(0, min(int(num_frames), total - frame_offset))
+        audio = torch.arange(frame_offset, frame_offset + n, dtype=torch.float64).reshape(-1, 1)
+        return (audio.t().contiguous() if channels_first else audio), 16000
+
+    monkeypatch.setattr(hg, "audio_info", info)
+    monkeypatch.setattr(hg, "audio_load", load)
+    return totals
+
+
+KW = dict(threshold=-2.0, short_utterance_len=30, max_words_sequence=8, max_window_size=70.0)
+
+
+def _reference_rows(spec, tmp, window_fn):
+    aligner = cs.CTCSegmentation(spec["asr"], kaldi_style_text=False, time_stamps="fixed", scoring_length=30)
+    aligner.samples_to_frames_ratio = 320.0
+    return anchor.get_file_iterative_segmentation(spec["asr"], aligner, spec["wav"], spec["df"].copy(),
+                                                  spec["vad"].copy(), 320.0, str(tmp), window_fn=window_fn, **KW)
+
+
+def _sweep_files(specs):
+    files = []
+    for s in specs:
+        n_segments = len(s["df"].index)
+        fixed = hg.fix_time_reference(s["df"], s["vad"], s["total"] / 16000, n_segments)
+        lpz = torch.log_softmax(s["asr"].logits[: s["total"] // 320].float(), dim=-1).cuda()
+        files.append(sweep.SweepFile(s["name"], s["wav"], lpz, s["total"],
+                                     sweep.rows_from_dataframe(fixed, KW["max_words_sequence"])))
+    return files
+
+
+def test_sweep_rows_equal_the_per_file_loop(exact_audio, tmp_path):
+    specs = [_corpus_file("a", 14, 11),
+             _corpus_file("b", 22, 12, corrupt=((300, 420), (900, 960))),
+             _corpus_file("c", 9, 13, corrupt=((150, 260),)),
+             _corpus_file("d", 18, 14, vad_gap=(20.0, 24.0)),
+             _corpus_file("e", 3, 15)]
+    for s in specs:
+        exact_audio[s["wav"]] = s["total"]
+    ref = [_reference_rows(s, tmp_path, oracle_window_fn) for s in specs]
+    assert sum(len(r) for r in ref) > 40
+
+    corpus = sweep.SweepCorpus(_sweep_files(specs), stub.CharTokenizer())
+    sw = sweep.AnchorSweep(corpus, index_duration=320.0 / 16000, samples_to_frames_ratio=320.0,
+                           threshold=KW["threshold"], short_utterance_len=KW["short_utterance_len"],
+                           max_window_size=KW["max_window_size"])
+    status = sw.run(steps_per_poll=4)
+    got = sw.file_rows()
+    st = sw.stats()
+    assert st["windows"] > 0 and st["cells"] > 0
+    for f, s in enumerate(specs):
+        if status[f] == sweep.NEEDS_RECALC:
+            # the host-policy hand-off: rows up to the hand-off point must still agree
+            assert got[f] == ref[f][:len(got[f])], s["name"]
+        else:
+            assert status[f] == sweep.DONE, (s["name"], status[f])
+            assert got[f] == ref[f], s["name"]
+    assert (status == sweep.DONE).sum() >= 3
+
+
+def test_sweep_is_independent_of_batching_and_capacity(exact_audio, tmp_path):
+    """One file alone == the same file inside a corpus; a tiny initial capacity only costs
+    CAPACITY round trips."""
+    specs = [_corpus_file("a", 12, 21), _corpus_file("b", 16, 22, corrupt=((200, 300),))]
+    files = _sweep_files(specs)
+    tok = stub.CharTokenizer()
+    kw = dict(index_duration=0.02, samples_to_frames_ratio=320.0)
+    both = sweep.AnchorSweep(sweep.SweepCorpus(files, tok), **kw)
+    both.run()
+    rows_both = both.file_rows()
+    for i in range(2):
+        solo = sweep.AnchorSweep(sweep.SweepCorpus([files[i]], tok), capacity=(64, 16, 1), **kw)
+        status = solo.run(steps_per_poll=1)
+        assert solo.file_rows()[0] == rows_both[i]
+        assert status[0] == both.state["status"].cpu().numpy()[i]
