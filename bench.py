@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the alignment hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2v|c3|c4|seg] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2v|c3|c4|seg|c5] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic emissions.
 Default workload = BASELINE.json configs[1] ("c2"): batched CTC-loss window
@@ -304,6 +304,213 @@ WORKLOADS = {
 }
 
 
+
+# ----------------------------------------------------------------------------- configs[4]: anchor sweep
+C5_TEXT = ("BASELINE configs[4]: full anchor-loop sweep over {h:g} h of synthetic emissions (files of 5-60 min, "
+           "rows of 20-60 words, V=32), sharded by file (LPT) over the ranks, on-device window construction, "
+           "all-prefix segmentation, selection and anchor update")
+
+
+def _c5_specs(hours, world, rank):
+    """Every rank derives the same corpus description and keeps its own LPT shard of the files."""
+    import sweep_corpus
+    from ipfa_b200 import sharding
+    rng = np.random.default_rng(2024)
+    minutes, left = [], hours * 60.0
+    while left > 1e-9:
+        m = min(float(rng.uniform(5.0, 60.0)), left)
+        minutes.append(max(m, 0.5))
+        left -= m
+    shards = sharding.lpt_shards(minutes, world)
+    mine = sorted(shards[rank])
+    specs = [sweep_corpus.make_spec(f"f{i:04d}", minutes[i], 7000 + i, corrupt_frac=0.06, non_speech_every=9)
+             for i in mine]
+    return specs, minutes, mine
+
+
+def _c5_cpu_worker(args):
+    from oracle import sweep as osweep
+    import importlib
+    stub = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+    spec, lp = args
+    t0 = time.perf_counter()
+    rows, status, stats = osweep.sweep_file(spec.file_id, spec.audio_path, lp, spec.n_samples, spec.rows,
+                                            stub.CharTokenizer())
+    return time.perf_counter() - t0, stats["cells"], len(rows)
+
+
+def c5_cpu_leg(budget_s):
+    """The CPU restatement (oracle/sweep.py: C table fill + interpreted backtrace / scoring / loop,
+    one alignment per shrinking-transcript iteration) on a bounded sample: one short file per core."""
+    import multiprocessing as mp
+    import sweep_corpus
+    cores = os.cpu_count() or 1
+    minutes = max(0.5, min(6.0, budget_s / 6.0))   # ~4 s of CPU per audio minute and process
+    specs = [sweep_corpus.make_spec(f"cpu{i:03d}", minutes, 9000 + i, corrupt_frac=0.06, non_speech_every=9)
+             for i in range(cores)]
+    jobs = [(s, sweep_corpus.emissions(s, "cpu", seed=i).numpy()) for i, s in enumerate(specs)]
+    pool = mp.get_context("fork").Pool(cores)
+    try:
+        t0 = time.perf_counter()
+        res = pool.map(_c5_cpu_worker, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    finally:
+        pool.terminate()
+    hours = sum(s.n_samples for s in specs) / 16000 / 3600.0
+    return {"cores": cores, "oracle_port": {"audio_h_per_s": hours / dt, "cells_per_s": sum(r[1] for r in res) / dt,
+                                            "windows": len(specs), "seconds_per_step": dt,
+                                            "files": len(specs), "minutes_per_file": minutes}}
+
+
+def c5_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    legs = c5_cpu_leg(budget_s=60.0)
+    best = legs["oracle_port"]
+    sample = (f"{best['files']} synthetic files of {best['minutes_per_file']:g} min (one per core) through "
+              "oracle/sweep.py: the reference's per-file anchor loop, C table fill + interpreted backtrace")
+    line = {"impl": "reference", "metric": "aligned_audio_hours_per_s", "value": best["audio_h_per_s"],
+            "unit": "audio-h/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": best["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": C5_TEXT.format(h=args.hours), "kernel": "sweep"},
+            "cells_per_s": best["cells_per_s"],
+            "cpu_baseline": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "cores": legs["cores"],
+                             "kind": "port", "sample": sample},
+            "e2e": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def c5_arm(args):
+    """A step = the whole anchor loop of this rank's files (state reset, run until every file stops)."""
+    import torch
+    import torch.distributed as dist
+    import ipfa_b200 as ipfa
+    import sweep_corpus
+    from ipfa_b200 import sweep as sw_mod
+    stub = __import__("importlib").import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    specs, minutes, mine = _c5_specs(args.hours, world, rank)
+    files = [sw_mod.SweepFile(s.file_id, s.audio_path, sweep_corpus.emissions(s, dev, seed=i), s.n_samples, s.rows)
+             for i, s in zip(mine, specs)]
+    corpus = sw_mod.SweepCorpus(files, stub.CharTokenizer())
+    for f in files:
+        f.lpz = None  # the corpus holds the only copy
+    sweep = sw_mod.AnchorSweep(corpus, index_duration=FRAME_SECONDS, samples_to_frames_ratio=320.0)
+    hours_mine = sum(s.n_samples for s in specs) / 16000 / 3600.0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_sweep():
+        sweep.reset()
+        return sweep.run(steps_per_poll=16)
+
+    steps = min(args.steps, 10)
+    warm = max(min(args.warmup, 3), 3)
+    for _ in range(warm):   # also settles the launch capacity (CAPACITY round trips happen here)
+        status = one_sweep()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ipfa.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(steps):
+        status = one_sweep()
+    ev[1].record()
+    barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[1])
+    launches = ipfa.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    st = sweep.stats()
+
+    # end to end: emissions start in pinned host memory; corpus upload + sweep + result rows back
+    host_lp = corpus.lp.cpu().pin_memory()
+    out_seg_h = torch.empty(sweep.out_seg.shape, dtype=torch.float64).pin_memory()
+    out_info_h = torch.empty(sweep.out_info.shape, dtype=torch.int32).pin_memory()
+    e2e_steps = max(2, min(steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        corpus.lp.copy_(host_lp, non_blocking=True)
+        one_sweep()
+        out_seg_h.copy_(sweep.out_seg, non_blocking=True)
+        out_info_h.copy_(sweep.out_info, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+
+    vals = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([hours_mine, float(st["cells"]), float(st["frames"]), float(st["windows"]),
+                         float(len(files)), float((status == sw_mod.DONE).sum()), float(launches),
+                         float(host_lp.numel() * 4), float(out_seg_h.numel() * 8 + out_info_h.numel() * 4)],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        # the job's only collective on results: per-utterance rows to rank 0 (not timed)
+        from ipfa_b200 import sharding
+        gathered = sharding.gather_objects([len(r) for r in sweep.file_rows()])
+    elapsed_ms, e2e_ms = float(vals[0]), float(vals[1])
+    hours, cells, frames, windows, n_files, n_done, launches_all, h2d, d2h = (float(x) for x in sums)
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_per_step = elapsed_ms / steps
+        alg_bytes = frames * 32 * 4 + 2 * cells / 8  # emission panel rows + 1-bit backpointers written and read
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        legs = c5_cpu_leg(budget_s=20.0)
+        best = legs["oracle_port"]
+        line = {
+            "metric": "aligned_audio_hours_per_s", "value": hours / (ms_per_step * 1e-3), "unit": "audio-h/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": C5_TEXT.format(h=args.hours), "kernel": "sweep",
+                       "l2": f"corpus emissions {h2d / 1e6:.0f} MB over all ranks, every window read once per sweep",
+                       "sharding": "files sharded by duration (LPT), no collective on the data path",
+                       "files": int(n_files), "files_done": int(n_done), "hours": hours,
+                       "iterations_rank0": st["steps"], "windows": int(windows),
+                       "capacity_T_C_K_rank0": sweep.capacity, "V": 32},
+            "cells_per_s": cells / (ms_per_step * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
+                         "kernels_per_step": launches_all / max(steps, 1) / world,
+                         "note": "lock-step iterations of T-serial kernels over <= files-in-flight windows: "
+                                 "latency bound, see DESIGN.md 5.6"},
+            "cpu_baseline": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "cores": legs["cores"],
+                             "kind": "port",
+                             "sample": f"{best['files']} files of {best['minutes_per_file']:g} min, one per core, "
+                                       "through oracle/sweep.py (C table fill + interpreted backtrace/loop)",
+                             "oracle_port": best},
+            "e2e": {"value": hours / (e2e_ms * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "api": "ipfa_sweep_step_device"},
+            "gpu_launches": int(launches_all), "clocks": sampler.result(),
+        }
+        if world > 1:
+            line["final_gather"] = {"files": int(sum(len(g) for g in gathered)), "backend": "nccl"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ----------------------------------------------------------------------------- CPU legs
 def cpu_leg(wl, budget_s, steps=1, warmup=0):
     """Times the CPU path(s) on a bounded sample of the workload, all host cores."""
@@ -499,9 +706,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--hours", type=float, default=100.0, help="c5: hours of audio in the corpus (all ranks)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    if args.workload == "c5":
+        return c5_reference_arm(args) if args.impl == "reference" else c5_arm(args)
     if args.impl == "reference":
         return reference_arm(args)
     return gpu_arm(args)

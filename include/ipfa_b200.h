@@ -242,7 +242,7 @@ typedef struct ipfa_sweep_corpus {
 } ipfa_sweep_corpus;
 
 /* Per-file loop state (device arrays [F], read and written by the sweep).  Initial values:
- * row = utt = exc = next_ns = n_windows = cells = 0, anchor = follow_start = NaN (None),
+ * row = utt = exc = next_ns = n_windows = cells = frames = 0, anchor = follow_start = NaN (None),
  * prop = 0.0, status = IPFA_SWEEP_ACTIVE, recalc_row = -1. */
 typedef struct ipfa_sweep_state {
     int32_t *row;          /* next TSV row of the file */
@@ -257,6 +257,7 @@ typedef struct ipfa_sweep_state {
     int32_t *recalc_row;   /* row whose times the host already re-spread (:127-146), -1 = none */
     int32_t *n_windows;    /* windows aligned so far */
     int64_t *cells;        /* trellis cells (frames x columns) filled so far */
+    int64_t *frames;       /* window frames aligned so far */
 } ipfa_sweep_state;
 
 typedef struct ipfa_sweep_params {

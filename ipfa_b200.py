@@ -11,7 +11,7 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 _PKG = "iterative-pseudo-forced-alignment-ctc_b200"
 _pkg = importlib.import_module(_PKG)
-for _name in ("_lib", "build", "ops", "ctc_segmentation", "hostglue", "anchor", "words", "sharding", "stub_asr"):
+for _name in ("_lib", "build", "ops", "ctc_segmentation", "hostglue", "anchor", "words", "sharding", "stub_asr", "sweep"):
     _mod = importlib.import_module(f"{_PKG}.{_name}")
     sys.modules[f"{__name__}.{_name}"] = _mod
     setattr(_pkg, _name, _mod)

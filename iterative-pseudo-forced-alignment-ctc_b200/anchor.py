@@ -146,10 +146,11 @@ def get_file_iterative_segmentation(asr_model, aligner, audio_path, file_df, vad
             transcript = discarded_transcripts[::-1] + transcript
             discarded_transcripts = []
         text_length = hg.count_text_length(transcript)
-        if clip_length != 0:
+        try:  # :101-109 (a clip shorter than one sample divides by zero; the value of the previous row stays)
             text_to_audio_proportion = hg.get_text_to_audio_proportion(
-                int(clip_length * info.sample_rate), text_length, info.sample_rate) \
-                if int(clip_length * info.sample_rate) != 0 else float('inf')
+                int(clip_length * info.sample_rate), text_length, info.sample_rate)
+        except ZeroDivisionError:
+            pass
         if not is_last_segment:
             following_row = file_df.iloc[row_index + 1]
             next_row_is_non_speech = following_row['Type'] == 'Non-Speech'

@@ -149,9 +149,9 @@ sweep_build_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const i
                 for (int u = u0; u < u1; ++u) text_length += c.utt_chars[slot0 + u];
                 const bool resumed = (r == recalc_row);  // host already re-spread this row (:127-146)
                 if (!resumed) {
-                    if (clip_length != 0.0) {  // :101-109
+                    {   // :101-109 (ZeroDivisionError is swallowed there: the previous value stays)
                         const long long ns = (long long)__dmul_rn(clip_length, (double)sr);
-                        prop = (ns != 0) ? text_to_audio(text_length, sr, ns) : __longlong_as_double(0x7ff0000000000000LL);
+                        if (ns != 0) prop = text_to_audio(text_length, sr, ns);
                     }
                     if (!is_last) {  // :111-113
                         next_ns = (c.row_type[R + 1] == 1);
@@ -274,6 +274,7 @@ __global__ void sweep_advance_kernel(const ipfa_sweep_corpus c, const ipfa_sweep
     s.row[f] += 1;
     s.n_windows[f] += 1;
     s.cells[f] += (int64_t)w.in_len[f] * w.n_cols[f];
+    s.frames[f] += w.in_len[f];
 }
 
 }  // namespace
@@ -302,7 +303,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
         !c.file_frames || !c.file_samples || !c.row_first || !c.row_type || !c.row_start || !c.row_end ||
         !c.row_utt_end || !c.utt_first || !c.utt_col || !c.utt_chars || !c.file_tok0 || !c.tokens ||
         !s.row || !s.utt || !s.anchor || !s.prop || !s.next_ns || !s.follow_start || !s.exc || !s.status ||
-        !s.need || !s.recalc_row || !s.n_windows || !s.cells || params->sample_rate <= 0 ||
+        !s.need || !s.recalc_row || !s.n_windows || !s.cells || !s.frames || params->sample_rate <= 0 ||
         params->frame_shift <= 0 || !(params->samples_to_frames_ratio > 0.0) || !(params->index_duration > 0.0) || params->score_len <= 0)
         return IPFA_ERR_INVALID_ARG;
     if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode

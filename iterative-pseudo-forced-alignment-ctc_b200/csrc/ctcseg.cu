@@ -314,8 +314,11 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     constexpr int SPW = 32 / KC;        // frames per word
     constexpr int NW = KC;              // word-rows per 32-frame block
     constexpr int NCW = 31 / KC + 2;    // thread-columns reachable inside one block
-    constexpr int NWORDS = NCW * NW;
-    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: raw[NWORDS] + gt[Cmax]
+    // staged one block ahead, before the walk of the current block is known: the start column
+    // can drop by up to 32 more columns (one switch per frame) -> 32 / KC + 1 more thread-columns
+    constexpr int NCW2 = NCW + 32 / KC + 1;
+    constexpr int NWORDS2 = NCW2 * NW;
+    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: raw[NWORDS2] + gt[Cmax]
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= prm.N * prm.Kmax) return;
@@ -355,93 +358,110 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     __syncwarp();
 
     // ---- walk the 1-bit backpointers from (t_term, c_end) to (0, 0) ----------
-    // Per 32-frame block: stage every word the walk can reach in shared memory (coalesced),
-    // then one LDS per frame, no branch on the serial chain.  Column 0 stores bit 0 (stay).
+    // Per 32-frame block the words the walk can reach sit in shared memory.  The walk does not
+    // step frame by frame: inside a word the bits of one column are the frames at which that
+    // column was ENTERED, so "the next switch at or below frame t" is one mask + find-leading-one;
+    // the serial chain is one LDS per column change (about C steps per window instead of T).
+    // The words of block b-1 are requested before block b is walked (a superset wide enough
+    // for wherever the walk ends up), so no global-memory latency sits on the chain either.
+    // Column 0 / thread-column -1 is staged as zeros: its bits read 0 (stay).
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
-    uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) + (size_t)(threadIdx.x >> 5) * (NWORDS + prm.Cmax);
-    int32_t *gt_s = reinterpret_cast<int32_t *>(raw + NWORDS);
+    constexpr int LOG2KC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
+    constexpr uint32_t COLBITS = (KC == 1) ? 0xffffffffu : (KC == 2) ? 0x55555555u : (KC == 4) ? 0x11111111u
+                                                                                               : 0x01010101u;
+    uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) + (size_t)(threadIdx.x >> 5) * (NWORDS2 + prm.Cmax);
+    int32_t *gt_s = reinterpret_cast<int32_t *>(raw + NWORDS2);
     for (int cc = lane; cc <= c_end; cc += 32) {
         int g = gt[cc];
         if (g < 0 || g >= prm.V) g = prm.blank;
         gt_s[cc] = g;
     }
-    // outputs of the previous (higher) block are stored one iteration late, so their emission
-    // gathers overlap the next block's staging loads
+    constexpr int NQ = (NWORDS2 + 31) / 32;
+    uint32_t v[NQ];
+    auto request = [&](int blk, int i_base) {  // words of block blk, thread-columns i_base - [0, NCW2)
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            const int q = lane + 32 * u;
+            const int row = q / NCW2, crel = q - row * NCW2;
+            const int col = i_base - crel;
+            const int wrow = blk * NW + row;
+            v[u] = 0;
+            if (q < NWORDS2 && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
+        }
+    };
+    // per-frame outputs of a block are stored one block late: their emission gathers are issued
+    // before the next block's walk and consumed after it
     int pend_t = -1, pend_c = 0, pend_sw = 0;
     float pend_eb = 0.0f, pend_ec = 0.0f;
-    auto flush_pending = [&]() {
+    int lc = c_end - 1;  // lattice column (table column - 1); -1 is table column 0
+    int i_base = lc >> LOG2KC;  // arithmetic shift: -1 -> thread-column -1
+    request(t_term >> 5, i_base);
+    for (int blk = t_term >> 5; blk >= 0; --blk) {
+        const int t_hi = min(t_term, blk * 32 + 31);
+        const int t_lo = blk * 32;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            const int q = lane + 32 * u;
+            if (q < NWORDS2) raw[q] = v[u];
+        }
+        __syncwarp();
+        const int i_cur = i_base;
+        i_base = lc >> LOG2KC;
+        if (blk > 0) request(blk - 1, i_base);  // in flight during this block's walk
+        if (pend_t >= 0) {
+            const float *row = lp + (int64_t)pend_t * prm.stride_t;
+            pend_eb = row[prm.blank];
+            pend_ec = row[gt_s[pend_c]];
+        }
+        // switch frames of this block as a 32-bit mask (bit = frame - t_lo)
+        uint32_t S = 0;
+        const int c_hi = lc + 1;  // table column at frame t_hi
+        int f_hi = (t_hi - t_lo) & (SPW - 1);
+#pragma unroll 1
+        for (int row = (t_hi - t_lo) / SPW; row >= 0; --row) {
+            // frame 0 of the table is never visited: the reference's loop ends at (0, 0)
+            const uint32_t keep = (blk == 0 && row == 0) ? ~((1u << KC) - 1u) : 0xffffffffu;
+            while (true) {
+                const int i = lc >> LOG2KC, k = lc & (KC - 1);
+                const uint32_t word = raw[row * NCW2 + (i_cur - i)];
+                const int top = f_hi * KC + k;  // bit of (frame f_hi, column k)
+                const uint32_t m = word & (COLBITS << k) & ((2u << top) - 1u) & keep;
+                if (m == 0) break;                       // stays down to the first frame of the word
+                const int f = (31 - __clz(m)) >> LOG2KC;  // the column was entered at this frame
+                S |= 1u << (row * SPW + f);
+                --lc;
+                f_hi = f - 1;
+                if (f_hi < 0) break;
+            }
+            f_hi = SPW - 1;
+        }
+        // the previous block's outputs (their gathers had this block's walk to arrive)
         if (pend_t >= 0) {
             const float p = (pend_c == 0) ? pend_eb : (pend_sw ? pend_ec : fmaxf(pend_eb, pend_ec));
             cprob[pend_t] = p;
             if (pend_sw && pend_c > 0) timing[pend_c] = pend_t;
             if (state) state[pend_t] = pend_sw ? pend_c : -1;
         }
-    };
-    // The walk runs on the lattice column lc = c - 1 (lc == -1 is table column 0).  Words of
-    // thread-column -1 are staged as zeros, so at lc == -1 the bit reads 0 (stay) and no
-    // clamp or select sits on the serial chain: SHR -> ADD -> LDS -> SHF -> AND -> SUB.
-    constexpr int LOG2KC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
-    int lc = c_end - 1;
-    for (int blk = t_term >> 5; blk >= 0; --blk) {
-        const int t_hi = min(t_term, blk * 32 + 31);
-        const int t_lo = blk * 32;
-        const int i_hi = lc >> LOG2KC;  // arithmetic shift: -1 -> thread-column -1
-        __syncwarp();
-        {   // all loads in flight before the first store: one exposed memory latency per block
-            constexpr int NQ = (NWORDS + 31) / 32;
-            uint32_t v[NQ];
-#pragma unroll
-            for (int u = 0; u < NQ; ++u) {
-                const int q = lane + 32 * u;
-                const int row = q / NCW, crel = q - row * NCW;
-                const int col = i_hi - crel;
-                const int wrow = blk * NW + row;
-                v[u] = 0;
-                if (q < NWORDS && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
-            }
-            // the emission gather of the previous block's frames rides along with the staging
-            // loads: __syncwarp waits for outstanding loads, so none may be in flight at the
-            // loop-top barrier
-            if (pend_t >= 0) {
-                const float *row = lp + (int64_t)pend_t * prm.stride_t;
-                pend_eb = row[prm.blank];
-                pend_ec = row[gt_s[pend_c]];
-            }
-#pragma unroll
-            for (int u = 0; u < NQ; ++u) {
-                const int q = lane + 32 * u;
-                if (q < NWORDS) raw[q] = v[u];
-            }
-        }
-        __syncwarp();
-        flush_pending();
-        int my_c = -1, my_sw = 0;
-        const int t_stop = max(t_lo, 1);  // (0, c): the loop `while t != 0 or c != 0` ends at (0, 0)
-        for (int t = t_hi; t >= t_stop; --t) {
-            const int i = lc >> LOG2KC, k = lc & (KC - 1);
-            const int row = (t / SPW) - blk * NW;
-            const uint32_t word = raw[row * NCW + (i_hi - i)];
-            const int sw = (word >> ((t % SPW) * KC + k)) & 1;
-            const bool mine = lane == (t & 31);
-            my_c = mine ? lc + 1 : my_c;
-            my_sw = mine ? sw : my_sw;
-            lc -= sw;
-        }
+        // lane = frame: column at frame t = c_hi - (switches at later frames of the block)
         const int t = t_lo + lane;
         pend_t = -1;
-        if (t <= t_hi && t >= 1 && my_c >= 0) {
+        if (t <= t_hi && t >= 1) {
             pend_t = t;
-            pend_c = my_c;
-            pend_sw = my_sw;
+            pend_c = c_hi - __popc((S >> lane) >> 1);
+            pend_sw = (S >> lane) & 1u;
         }
     }
     if (pend_t >= 0) {
         const float *row = lp + (int64_t)pend_t * prm.stride_t;
         pend_eb = row[prm.blank];
         pend_ec = row[gt_s[pend_c]];
+        const float p = (pend_c == 0) ? pend_eb : (pend_sw ? pend_ec : fmaxf(pend_eb, pend_ec));
+        cprob[pend_t] = p;
+        if (pend_sw && pend_c > 0) timing[pend_c] = pend_t;
+        if (state) state[pend_t] = pend_sw ? pend_c : -1;
     }
-    flush_pending();
     __syncwarp();
     __threadfence_block();
 
@@ -623,7 +643,7 @@ int ctcseg_run(const float *lp, const int64_t *win_off, int64_t stride_n, int64_
     const int blocks = (warps + 3) / 4;
     {
         const int kc = s.PER;
-        const size_t bt_smem = (size_t)4 * ((31 / kc + 2) * kc + Cmax) * sizeof(uint32_t);
+        const size_t bt_smem = (size_t)4 * ((31 / kc + 2 + 32 / kc + 1) * kc + Cmax) * sizeof(uint32_t);
         cudaError_t ea = cudaSuccess;
 #define IPFA_BT(K_)                                                                                     \
     if (kc == K_) {                                                                                     \

@@ -34,7 +34,7 @@ class _Corpus(ctypes.Structure):
 
 class _State(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("row", "utt", "anchor", "prop", "next_ns", "follow_start", "exc", "status",
-                                   "need", "recalc_row", "n_windows", "cells")]
+                                   "need", "recalc_row", "n_windows", "cells", "frames")]
 
 
 class _Params(ctypes.Structure):
@@ -177,7 +177,15 @@ class AnchorSweep:
         p.frame_shift = int(frame_shift if frame_shift is not None else round(samples_to_frames_ratio))
         p.score_len, p.seg_flags = scoring_length, seg_flags
         self.params = p
-        nan = float("nan")
+        self.reset()
+        self.steps = 0
+        self.capacity = list(capacity) if capacity else self._initial_capacity()
+        self._ws = None
+        self._ws_cap = None
+
+    def reset(self):
+        """Initial loop state of every file (:36-43) and empty outputs."""
+        dev, n, nan = self.corpus.device, len(self.corpus.files), float("nan")
         self.state = dict(
             row=torch.zeros(n, dtype=torch.int32, device=dev), utt=torch.zeros(n, dtype=torch.int32, device=dev),
             anchor=torch.full((n,), nan, dtype=torch.float64, device=dev),
@@ -189,13 +197,11 @@ class AnchorSweep:
             need=torch.zeros((n, 3), dtype=torch.int32, device=dev),
             recalc_row=torch.full((n,), -1, dtype=torch.int32, device=dev),
             n_windows=torch.zeros(n, dtype=torch.int32, device=dev),
-            cells=torch.zeros(n, dtype=torch.int64, device=dev))
-        self.out_seg = torch.zeros((corpus.n_slots, 4), dtype=torch.float64, device=dev)
-        self.out_info = torch.full((corpus.n_slots, 2), -1, dtype=torch.int32, device=dev)
+            cells=torch.zeros(n, dtype=torch.int64, device=dev),
+            frames=torch.zeros(n, dtype=torch.int64, device=dev))
+        self.out_seg = torch.zeros((self.corpus.n_slots, 4), dtype=torch.float64, device=dev)
+        self.out_info = torch.full((self.corpus.n_slots, 2), -1, dtype=torch.int32, device=dev)
         self.steps = 0
-        self.capacity = list(capacity) if capacity else self._initial_capacity()
-        self._ws = None
-        self._ws_cap = None
 
     def _initial_capacity(self):
         """(Tmax, Cmax, Kmax) that holds every single row's own window."""
@@ -299,5 +305,6 @@ class AnchorSweep:
     def stats(self):
         return {"steps": self.steps, "windows": int(self.state["n_windows"].sum().item()),
                 "cells": int(self.state["cells"].sum().item()),
+                "frames": int(self.state["frames"].sum().item()),
                 "status": {STATUS_NAMES[k]: int(v) for k, v in
                            zip(*np.unique(self.state["status"].cpu().numpy(), return_counts=True))}}

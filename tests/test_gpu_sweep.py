@@ -146,3 +146,31 @@ def test_sweep_is_independent_of_batching_and_capacity(exact_audio, tmp_path):
         status = solo.run(steps_per_poll=1)
         assert solo.file_rows()[0] == rows_both[i]
         assert status[0] == both.state["status"].cpu().numpy()[i]
+
+
+def test_sweep_equals_cpu_oracle_on_a_synthetic_corpus():
+    """A small configs[4]-style corpus (files of different lengths, non-speech rows, utterances
+    whose audio says something else): rows, final status and work counters of every file equal
+    the CPU restatement oracle/sweep.py, which aligns once per shrinking-transcript iteration."""
+    import sweep_corpus
+    from oracle import sweep as osweep
+    tok = stub.CharTokenizer()
+    specs = [sweep_corpus.make_spec(f"f{i}", m, 100 + i, corrupt_frac=c, non_speech_every=ns)
+             for i, (m, c, ns) in enumerate([(1.0, 0.1, 0), (4.0, 0.2, 3), (2.5, 0.0, 0), (6.0, 0.12, 5),
+                                             (0.6, 0.3, 0), (3.0, 0.5, 2)])]
+    lps = [sweep_corpus.emissions(s, "cuda", seed=7 + i) for i, s in enumerate(specs)]
+    files = [sweep.SweepFile(s.file_id, s.audio_path, lp, s.n_samples, s.rows) for s, lp in zip(specs, lps)]
+    sw = sweep.AnchorSweep(sweep.SweepCorpus(files, tok), index_duration=0.02, samples_to_frames_ratio=320.0)
+    status = sw.run(steps_per_poll=8)
+    got = sw.file_rows()
+    windows = sw.state["n_windows"].cpu().numpy()
+    cells = sw.state["cells"].cpu().numpy()
+    n_rows = 0
+    for f, (s, lp) in enumerate(zip(specs, lps)):
+        ref, ref_status, stats = osweep.sweep_file(s.file_id, s.audio_path, lp.cpu().numpy(), s.n_samples,
+                                                   s.rows, tok)
+        assert sweep.STATUS_NAMES[status[f]] == ref_status, s.file_id
+        assert got[f] == ref, s.file_id
+        assert windows[f] == stats["windows"] and cells[f] == stats["cells"], s.file_id
+        n_rows += len(ref)
+    assert n_rows > 100
