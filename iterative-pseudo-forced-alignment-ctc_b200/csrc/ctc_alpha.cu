@@ -19,6 +19,8 @@
 #include "emission_pipe.cuh"
 #include "lattice_shapes.cuh"
 
+#include <type_traits>
+
 namespace ipfa {
 
 struct AlphaParams {
@@ -30,14 +32,29 @@ struct AlphaParams {
     const int32_t *tgt_len;
     const int32_t *order;  // optional window permutation (heaviest first), may be null
     int N, V, blank;
+    int halves;            // groups per window: 2 = meet-in-the-middle walk, 1 = forward only
     int pitch, tc;         // pipe geometry
     int u_cap;             // capacity of the per-group column list (gather mode)
     int l_cap;             // Lmax the launch was sized for
     size_t group_smem;     // bytes of shared memory per group
     float *nll_out;
+    float *join_vec;       // [N][2 halves][2][l_cap + 1] state vectors at the cut (workspace)
+    int *join_count;       // [N] arrivals at the cut, zeroed before the launch (workspace)
 };
 
-template <int P, int WARPS, bool DENSE>
+// PITCH > 0: compile-time panel pitch (dense rows of <= 32 symbols), so the unrolled frames
+// address the panel with immediate offsets from one pointer per column.
+//
+// Two groups per window.  The recursion is T-serial, so a window is cut at its middle frame
+// m = (T-1)/2 and walked from both ends at once (twice the resident warp-chains, half the
+// chain length): group 0 runs alpha over frames 0..m; group 1 runs the SAME recursion over
+// frames T-1..m+1 with the target reversed, which is beta with the emission of its own frame
+// included (the blank-interleaved lattice and its skip rule are symmetric under reversal).
+// Each group leaves its state vector in the workspace; the one that finishes second joins
+// them:  p = sum_s alpha_m(s) * sum_{s' in succ(s)} b_{m+1}(s').
+constexpr int kBidirMinFrames = 16;  // shorter windows are walked by group 0 alone
+
+template <int P, int WARPS, bool DENSE, int PITCH>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctc_alpha_kernel(const AlphaParams prm) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
@@ -46,27 +63,36 @@ ctc_alpha_kernel(const AlphaParams prm) {
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    int w = blockIdx.x * GROUPS + group;
-    if (w >= prm.N) return;  // WARPS==1: whole warp leaves; WARPS>1: whole CTA leaves
-    if (prm.order) w = prm.order[w];
+    const int g2 = blockIdx.x * GROUPS + group;  // (window, half)
+    if (g2 >= prm.halves * prm.N) return;  // WARPS==1: whole warp leaves; WARPS>1: whole CTA leaves
+    const int w = (prm.halves == 2) ? g2 >> 1 : g2;
+    const int half = (prm.halves == 2) ? g2 & 1 : 0;
 
+    const int pitch = PITCH ? PITCH : prm.pitch;
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
-    float *xline = ring + (size_t)kStages * prm.tc * prm.pitch;  // [2][NT + 1] neighbour exchange (WARPS > 1)
-    float *fin = xline + 2 * (NT + 1);                            // [2]
-    int *cols = reinterpret_cast<int *>(fin + 2);                 // [u_cap] (gather mode)
+    float *xline = ring + (size_t)kStages * prm.tc * pitch;  // [2][NT + 1] neighbour exchange (WARPS > 1)
+    float *fin = xline + 2 * (NT + 1);                        // [2 + WARPS]
+    int *cols = reinterpret_cast<int *>(fin + 2 + WARPS);     // [u_cap] (gather mode)
 
-    const int T = prm.in_len[w];
+    const int T_all = prm.in_len[w];
     const int L = max(0, min(prm.tgt_len[w], prm.l_cap));
     const int32_t *tg = prm.targets + (int64_t)w * prm.tgt_stride;
     const int blank = prm.blank;
 
-    if (T <= 0) {
-        if (tid == 0) prm.nll_out[w] = (L == 0) ? 0.0f : __int_as_float(0x7f800000);
+    if (T_all <= 0) {
+        if (tid == 0 && half == 0) prm.nll_out[w] = (L == 0) ? 0.0f : __int_as_float(0x7f800000);
         return;
     }
+    const bool bidir = prm.halves == 2 && T_all >= kBidirMinFrames;
+    if (!bidir && half == 1) return;
+    const int m = bidir ? (T_all - 1) >> 1 : T_all - 1;  // last frame of the forward half
+    const bool rev = half == 1;
+    const int t_lo = rev ? m + 1 : 0;
+    const int T = rev ? T_all - 1 - m : m + 1;           // frames this group walks
 
-    // per-thread lattice constants
+    // per-thread lattice constants; the reverse half sees the target back to front
+    auto target = [&](int j) { return rev ? tg[L - 1 - j] : tg[j]; };
     int col[P];      // panel column of label_p
     bool skip[P];    // s-2 transition allowed into label_p
     bool bad = false;
@@ -76,9 +102,9 @@ ctc_alpha_kernel(const AlphaParams prm) {
         // States past the end of the target (j >= L) are left to run on garbage: they only
         // feed states further right, never a real one, and every value stays finite.
         const bool lab_ok = j < L;
-        int lab = lab_ok ? tg[j] : blank;
+        int lab = lab_ok ? target(j) : blank;
         if (lab < 0 || lab >= prm.V) { bad = true; lab = blank; }
-        const int prev = (j >= 1 && lab_ok) ? tg[j - 1] : -1;
+        const int prev = (j >= 1 && lab_ok) ? target(j - 1) : -1;
         skip[p] = lab_ok && j >= 1 && prev != lab;
         col[p] = DENSE ? lab : (lab_ok ? j + 1 : 0);
     }
@@ -86,7 +112,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
     int U = L + 1;  // panel columns
     if constexpr (!DENSE) {
         for (int j = tid; j <= L; j += NT) {
-            int c = (j == 0) ? blank : tg[j - 1];
+            int c = (j == 0) ? blank : target(j - 1);
             if (c < 0 || c >= prm.V) c = blank;
             cols[j] = c;
         }
@@ -105,21 +131,24 @@ ctc_alpha_kernel(const AlphaParams prm) {
     group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
-    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, U, prm.V, prm.pitch,
-              prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
+    pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, U, prm.V, pitch,
+              prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid, t_lo, rev);
     pipe.prologue(tid);
 
     float ab[P], al[P];  // blank / label alphas (log2 domain)
 #pragma unroll
     for (int p = 0; p < P; ++p) { ab[p] = kNegBig; al[p] = kNegBig; }
 
-    // One frame of the recursion.  `rd`/`wr`: this frame's read / write lines of the
-    // cross-warp exchange (WARPS > 1); inside a warp the neighbour comes by shuffle.
-    auto frame = [&](const float *row, const float *rd, float *wr) {
-        const float eb = row[colb];
+    // One frame of the recursion, `off` floats past the column cursors.  `rd`/`wr`: this frame's
+    // read / write lines of the cross-warp exchange (WARPS > 1); inside a warp the neighbour
+    // comes by shuffle.
+    const float *pb = nullptr;   // cursor on the blank column
+    const float *pl[P];          // cursors on the label columns
+    auto frame = [&](const int off, const float *rd, float *wr) {
+        const float eb = pb[off];
         float el[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) el[p] = row[col[p]];
+        for (int p = 0; p < P; ++p) el[p] = pl[p][off];
         float prev;
         if constexpr (WARPS > 1) {
             prev = rd[tid];
@@ -142,16 +171,42 @@ ctc_alpha_kernel(const AlphaParams prm) {
             __syncthreads();
         }
     };
-
     float *line0 = xline, *line1 = xline + NT + 1;
+    // The j-th frame a chunk processes reads line[(j-1)&1] and writes line[j&1] (tc is even, so
+    // j has the parity of the frame's position in the walk).  DIR = +1: rows 0, 1, ...;
+    // DIR = -1 (reverse half): rows rows-1, rows-2, ...; the 4 unrolled frames sit at immediate
+    // offsets from the cursors either way.
+    auto run_rows = [&](auto dir, int j, const int rows) {
+        constexpr int DIR = decltype(dir)::value;
+        const int step = DIR * pitch;
+        auto bump = [&](const int frames) {
+            pb += frames * step;
+#pragma unroll
+            for (int p = 0; p < P; ++p) pl[p] += frames * step;
+        };
+        if ((j & 1) && j < rows) { frame(0, line0, line1); bump(1); ++j; }
+        for (; j + 3 < rows; j += 4) {
+            frame(0, line1, line0);
+            frame(step, line0, line1);
+            frame(2 * step, line1, line0);
+            frame(3 * step, line0, line1);
+            bump(4);
+        }
+        for (; j + 1 < rows; j += 2) {
+            frame(0, line1, line0);
+            frame(step, line0, line1);
+            bump(2);
+        }
+        if (j < rows) frame(0, line1, line0);
+    };
+
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
         float *panel = const_cast<float *>(pipe.acquire(chunk, tid));
-        const int t0 = chunk * pipe.tc;
-        const int rows = min(pipe.tc, T - t0);
+        const int rows = pipe.chunk_rows(chunk);
         // in-place: natural log -> log2, clamp log(0) to the finite stand-in
         {
             float4 *p4 = reinterpret_cast<float4 *>(panel);
-            const int n4 = (rows * prm.pitch) >> 2;
+            const int n4 = (rows * pitch) >> 2;
             for (int q = tid; q < n4; q += NT) {
                 float4 v = p4[q];
                 v.x = fmaxf(v.x * kLog2e, kNegBig); v.y = fmaxf(v.y * kLog2e, kNegBig);
@@ -160,42 +215,97 @@ ctc_alpha_kernel(const AlphaParams prm) {
             }
             group_sync<WARPS>();
         }
-        int r = 0;
-        if (chunk == 0) {  // frame 0: only states 0 and 1 are alive
+        const int first_row = rev ? rows - 1 : 0;  // the chunk's first frame in walking order
+        int j = 0;
+        if (chunk == 0) {  // first frame of the walk: only states 0 and 1 are alive
             if (tid == 0) {
-                ab[0] = panel[colb];
-                if (L > 0) al[0] = panel[col[0]];
+                ab[0] = panel[first_row * pitch + colb];
+                if (L > 0) al[0] = panel[first_row * pitch + col[0]];
             }
             if constexpr (WARPS > 1) {
                 line0[tid + 1] = al[P - 1];
                 __syncthreads();
             }
-            r = 1;
+            j = 1;
         }
-        // frame t reads line[(t-1)&1] and writes line[t&1]; tc is even, so r has t's parity
-        const float *row = panel + r * prm.pitch;
-        if ((r & 1) && r < rows) { frame(row, line0, line1); row += prm.pitch; ++r; }
-        for (; r + 1 < rows; r += 2) {
-            frame(row, line1, line0);
-            frame(row + prm.pitch, line0, line1);
-            row += 2 * prm.pitch;
-        }
-        if (r < rows) frame(row, line1, line0);
+        const int row = rev ? rows - 1 - j : j;
+        pb = panel + row * pitch + colb;
+#pragma unroll
+        for (int p = 0; p < P; ++p) pl[p] = panel + row * pitch + col[p];
+        if (rev) run_rows(std::integral_constant<int, -1>{}, j, rows);
+        else run_rows(std::integral_constant<int, 1>{}, j, rows);
     }
 
-    // final states 2L (blank of pair L) and 2L-1 (label of pair L-1)
+    if (!bidir) {
+        // final states 2L (blank of pair L) and 2L-1 (label of pair L-1)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int j = tid * P + p;
+            if (j == L) fin[0] = ab[p];
+            if (j == L - 1) fin[1] = al[p];
+        }
+        if (L == 0 && tid == 0) fin[1] = kNegBig;
+        group_sync<WARPS>();
+        if (tid == 0) {
+            const float v = lse2_2(fin[0], fin[1]);
+            float nll = -v * kLn2;
+            if (v < kNegThreshold || bad) nll = __int_as_float(0x7f800000);
+            prm.nll_out[w] = nll;
+        }
+        return;
+    }
+
+    // ---- join the two halves ------------------------------------------------
+    // vec[w][half][0][j] = blank of pair j, vec[w][half][1][j] = label of pair j, j = 0..l_cap,
+    // each in its own half's pair numbering.
+    const int64_t vstride = prm.l_cap + 1;
+    float *vec_w = prm.join_vec + (int64_t)w * 4 * vstride;
+    float *mine = vec_w + (int64_t)half * 2 * vstride;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int j = tid * P + p;
-        if (j == L) fin[0] = ab[p];
-        if (j == L - 1) fin[1] = al[p];
+        if (j <= L) {
+            mine[j] = ab[p];
+            mine[vstride + j] = (j < L) ? al[p] : kNegBig;
+        }
     }
-    if (L == 0 && tid == 0) fin[1] = kNegBig;
+    __threadfence();
     group_sync<WARPS>();
+    if (tid == 0) fin[0] = __int_as_float(atomicAdd(prm.join_count + w, 1));
+    group_sync<WARPS>();
+    if (__float_as_int(fin[0]) == 0) return;  // the other half is still walking; it will join
+    __threadfence();
+    // In forward numbering: A = alpha_m, B = b_{m+1}.  Reverse pair i holds the blank of forward
+    // pair L - i and the label of forward pair L - 1 - i.
+    const float *fwd = vec_w, *bwd = vec_w + 2 * vstride;
+    auto A_b = [&](int j) { return __ldcg(fwd + j); };
+    auto A_l = [&](int j) { return __ldcg(fwd + vstride + j); };
+    auto B_b = [&](int j) { return __ldcg(bwd + (L - j)); };
+    auto B_l = [&](int j) { return __ldcg(bwd + vstride + (L - 1 - j)); };
+    float acc = kNegBig;
+    for (int j = tid; j <= L; j += NT) {
+        // blank j -> {blank j, label j}
+        float succ = B_b(j);
+        if (j < L) succ = lse2_2(succ, B_l(j));
+        acc = lse2_2(acc, A_b(j) + succ);
+        if (j < L) {  // label j -> {label j, blank j+1, label j+1 if it differs}
+            float s2 = lse2_2(B_l(j), B_b(j + 1));
+            if (j + 1 < L && tg[j + 1] != tg[j]) s2 = lse2_2(s2, B_l(j + 1));
+            acc = lse2_2(acc, A_l(j) + s2);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc = lse2_2(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    if constexpr (WARPS > 1) {
+        if ((tid & 31) == 0) fin[2 + (tid >> 5)] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < WARPS; ++q) acc = lse2_2(acc, fin[2 + q]);
+        }
+    }
     if (tid == 0) {
-        const float v = lse2_2(fin[0], fin[1]);
-        float nll = -v * kLn2;
-        if (v < kNegThreshold || bad) nll = __int_as_float(0x7f800000);
+        float nll = -acc * kLn2;
+        if (acc < kNegThreshold || bad) nll = __int_as_float(0x7f800000);
         prm.nll_out[w] = nll;
     }
 }
@@ -206,10 +316,10 @@ ctc_alpha_kernel(const AlphaParams prm) {
 extern cudaError_t g_last_cuda_error;
 extern uint64_t g_launch_count;
 
-template <int P, int WARPS, bool DENSE>
-static int launch_alpha(AlphaParams prm, int Lmax, cudaStream_t stream) {
+template <int P, int WARPS, bool DENSE, int PITCH>
+static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
-    const int U = DENSE ? prm.V : (Lmax + 1);
+    const int U = PITCH ? PITCH : (DENSE ? prm.V : (Lmax + 1));
     // shared-memory budget per group for the emission ring
     const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
     PipeGeometry g = pipe_geometry(U, budget);
@@ -217,20 +327,28 @@ static int launch_alpha(AlphaParams prm, int Lmax, cudaStream_t stream) {
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
     prm.l_cap = Lmax;
-    size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2) * sizeof(float) + (size_t)prm.u_cap * sizeof(int) + 40;
+    size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2 + WARPS) * sizeof(float) + (size_t)prm.u_cap * sizeof(int) + 40;
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
-    auto kern = ctc_alpha_kernel<P, WARPS, DENSE>;
+    auto kern = ctc_alpha_kernel<P, WARPS, DENSE, PITCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
-    const int blocks = (prm.N + GROUPS - 1) / GROUPS;
+    const int blocks = (prm.halves * prm.N + GROUPS - 1) / GROUPS;
     kern<<<blocks, threads, smem, stream>>>(prm);
     ++g_launch_count;
     e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;
+}
+
+template <int P, int WARPS, bool DENSE>
+static int launch_alpha(const AlphaParams &prm, int Lmax, cudaStream_t stream) {
+    if constexpr (DENSE) {
+        if (prm.V <= 32) return launch_alpha_p<P, WARPS, true, 32>(prm, Lmax, stream);
+    }
+    return launch_alpha_p<P, WARPS, DENSE, 0>(prm, Lmax, stream);
 }
 
 template <bool DENSE>
@@ -248,8 +366,12 @@ bool use_dense_panel(int V, int Lmax) { return V <= 64 || V <= 2 * (Lmax + 1); }
 
 using namespace ipfa;
 
-extern "C" size_t ipfa_ctc_alpha_workspace_bytes(int N, int, int, int) {
-    return (size_t)(N > 0 ? N : 1) * sizeof(int32_t) + 256;
+static inline size_t alpha_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// arrival counters [N] + the two halves' state vectors at the cut [N][2][2][Lmax + 1]
+extern "C" size_t ipfa_ctc_alpha_workspace_bytes(int N, int, int Lmax, int) {
+    const size_t n = (size_t)(N > 0 ? N : 1), l1 = (size_t)(Lmax > 0 ? Lmax : 0) + 1;
+    return alpha_pad256(n * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) + 256;
 }
 
 extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
@@ -257,19 +379,33 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
                                      const int32_t *in_len, const int32_t *tgt_len, int N, int Tmax,
                                      int Lmax, int V, int blank, float *nll_out, void *workspace,
                                      size_t workspace_bytes, void *stream) {
-    (void)workspace; (void)workspace_bytes; (void)Tmax;
+    (void)Tmax;
     if (N == 0) return IPFA_OK;
     if (!lp || !in_len || !tgt_len || !nll_out || N < 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V ||
         (Lmax > 0 && !targets))
         return IPFA_ERR_INVALID_ARG;
+    if (!workspace) return IPFA_ERR_INVALID_ARG;
+    if (workspace_bytes < ipfa_ctc_alpha_workspace_bytes(N, Tmax, Lmax, V)) return IPFA_ERR_WORKSPACE;
+    // Dense panels: two groups per window (the halves of the meet-in-the-middle walk), and the
+    // MUFU pipe wants ~6 resident warp-chains per SM sub-partition more than it wants units per
+    // thread.  The gather panel (large vocabularies) is bound by its loads, not by the chain:
+    // one group per window.
+    const bool dense = use_dense_panel(V, Lmax);
+    const int halves = dense ? 2 : 1;
     LatticeShape s;
-    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_ALPHA_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return IPFA_ERR_UNSUPPORTED;
+    if (!pick_lattice_shape(Lmax + 1, halves * N, &s, "IPFA_ALPHA_SHAPE", 6)) return IPFA_ERR_UNSUPPORTED;
     AlphaParams prm{};
+    prm.halves = halves;
     prm.lp = lp; prm.stride_n = stride_n; prm.stride_t = stride_t;
     prm.targets = targets; prm.tgt_stride = tgt_stride;
     prm.in_len = in_len; prm.tgt_len = tgt_len; prm.order = nullptr;
     prm.N = N; prm.V = V; prm.blank = blank; prm.nll_out = nll_out;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (use_dense_panel(V, Lmax)) return dispatch_alpha<true>(prm, Lmax, s, st);
+    prm.join_count = static_cast<int *>(workspace);
+    prm.join_vec = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) +
+                                             alpha_pad256((size_t)N * sizeof(int32_t)));
+    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, (size_t)N * sizeof(int32_t), st);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    if (dense) return dispatch_alpha<true>(prm, Lmax, s, st);
     return dispatch_alpha<false>(prm, Lmax, s, st);
 }

@@ -260,29 +260,57 @@ ctcseg_fill_kernel(const SegFillParams prm) {
 // np.ndarray.mean on a contiguous float64 vector = pairwise sum (8 accumulators
 // for n <= 128, recursive halving above) / n.  char_probs is float64 holding
 // fp32 values; mirroring the order keeps the score bit-identical.
-__device__ double np_pairwise_sum(const float *a, int n) {
+__device__ __forceinline__ double np_sum_upto128(const float *__restrict__ a, int n) {
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = (double)a[j];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = (double)a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], (double)a[i + j]);
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
-        return res;
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], (double)a[i + j]);
     }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
+    return res;
+}
+__device__ __noinline__ double np_pairwise_sum_rec(const float *a, int n) {
+    if (n <= 128) return np_sum_upto128(a, n);
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return __dadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+    return __dadd_rn(np_pairwise_sum_rec(a, n2), np_pairwise_sum_rec(a + n2, n - n2));
+}
+// the scoring windows are score_len (30) frames: the common case stays inline, register-only
+__device__ __forceinline__ double np_pairwise_sum(const float *a, int n) {
+    return (n <= 128) ? np_sum_upto128(a, n) : np_pairwise_sum_rec(a, n);
+}
+
+// Bits 0, KC, 2KC, ... of x packed into the low 32 / KC bits.
+template <int KC>
+__device__ __forceinline__ uint32_t compress_stride(uint32_t x) {
+    if constexpr (KC == 1) {
+        return x;
+    } else if constexpr (KC == 2) {
+        x &= 0x55555555u;
+        x = (x | (x >> 1)) & 0x33333333u;
+        x = (x | (x >> 2)) & 0x0f0f0f0fu;
+        x = (x | (x >> 4)) & 0x00ff00ffu;
+        return (x | (x >> 8)) & 0x0000ffffu;
+    } else if constexpr (KC == 4) {
+        x &= 0x11111111u;
+        x = (x | (x >> 3)) & 0x03030303u;
+        x = (x | (x >> 6)) & 0x000f000fu;
+        return (x | (x >> 12)) & 0x000000ffu;
+    } else {
+        x &= 0x01010101u;
+        x = (x | (x >> 7)) & 0x00030003u;
+        return (x | (x >> 14)) & 0x0000000fu;
+    }
 }
 
 struct SegBackParams {
@@ -318,7 +346,7 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     // can drop by up to 32 more columns (one switch per frame) -> 32 / KC + 1 more thread-columns
     constexpr int NCW2 = NCW + 32 / KC + 1;
     constexpr int NWORDS2 = NCW2 * NW;
-    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: raw[NWORDS2] + gt[Cmax]
+    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: raw[NWORDS2] + col32[NCW2*KC] + gt[Cmax]
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= prm.N * prm.Kmax) return;
@@ -368,10 +396,10 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
     constexpr int LOG2KC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
-    constexpr uint32_t COLBITS = (KC == 1) ? 0xffffffffu : (KC == 2) ? 0x55555555u : (KC == 4) ? 0x11111111u
-                                                                                               : 0x01010101u;
-    uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) + (size_t)(threadIdx.x >> 5) * (NWORDS2 + prm.Cmax);
-    int32_t *gt_s = reinterpret_cast<int32_t *>(raw + NWORDS2);
+    uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) +
+                    (size_t)(threadIdx.x >> 5) * (NWORDS2 + NCW2 * KC + prm.Cmax);
+    uint32_t *col32 = raw + NWORDS2;
+    int32_t *gt_s = reinterpret_cast<int32_t *>(col32 + NCW2 * KC);
     for (int cc = lane; cc <= c_end; cc += 32) {
         int g = gt[cc];
         if (g < 0 || g >= prm.V) g = prm.blank;
@@ -415,27 +443,37 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
             pend_eb = row[prm.blank];
             pend_ec = row[gt_s[pend_c]];
         }
-        // switch frames of this block as a 32-bit mask (bit = frame - t_lo)
+        // per-column words of the whole block: col32[d] bit f = "column top - d was entered at frame
+        // t_lo + f" (the KC-strided bits of the NW word-rows compressed and concatenated)
+        const int top = i_cur * KC + (KC - 1);  // lattice column of col32[0]
+        for (int d = lane; d < NCW2 * KC; d += 32) {
+            const int crel = d >> LOG2KC, k = (KC - 1) - (d & (KC - 1));
+            uint32_t bits = 0;
+#pragma unroll
+            for (int row = 0; row < NW; ++row)
+                bits |= compress_stride<KC>(raw[row * NCW2 + crel] >> k) << (row * SPW);
+            col32[d] = bits;
+        }
+        __syncwarp();
+        // switch frames of this block as a 32-bit mask (bit = frame - t_lo): the serial chain is
+        // one LDS + mask + find-leading-one per column change
         uint32_t S = 0;
         const int c_hi = lc + 1;  // table column at frame t_hi
-        int f_hi = (t_hi - t_lo) & (SPW - 1);
-#pragma unroll 1
-        for (int row = (t_hi - t_lo) / SPW; row >= 0; --row) {
+        {
             // frame 0 of the table is never visited: the reference's loop ends at (0, 0)
-            const uint32_t keep = (blk == 0 && row == 0) ? ~((1u << KC) - 1u) : 0xffffffffu;
+            const uint32_t keep = (blk == 0) ? ~1u : 0xffffffffu;
+            int d = top - lc;
+            uint32_t below = ((2u << (t_hi - t_lo)) - 1u) & keep;  // frames <= the current one
             while (true) {
-                const int i = lc >> LOG2KC, k = lc & (KC - 1);
-                const uint32_t word = raw[row * NCW2 + (i_cur - i)];
-                const int top = f_hi * KC + k;  // bit of (frame f_hi, column k)
-                const uint32_t m = word & (COLBITS << k) & ((2u << top) - 1u) & keep;
-                if (m == 0) break;                       // stays down to the first frame of the word
-                const int f = (31 - __clz(m)) >> LOG2KC;  // the column was entered at this frame
-                S |= 1u << (row * SPW + f);
-                --lc;
-                f_hi = f - 1;
-                if (f_hi < 0) break;
+                const uint32_t m = col32[d] & below;
+                if (m == 0) break;                 // stays down to the first frame of the block
+                const int f = 31 - __clz(m);       // the column was entered at this frame
+                S |= 1u << f;
+                ++d;
+                below &= (1u << f) - 1u;
+                if (below == 0) break;
             }
-            f_hi = SPW - 1;
+            lc = top - d;
         }
         // the previous block's outputs (their gathers had this block's walk to arrive)
         if (pend_t >= 0) {
@@ -643,7 +681,7 @@ int ctcseg_run(const float *lp, const int64_t *win_off, int64_t stride_n, int64_
     const int blocks = (warps + 3) / 4;
     {
         const int kc = s.PER;
-        const size_t bt_smem = (size_t)4 * ((31 / kc + 2 + 32 / kc + 1) * kc + Cmax) * sizeof(uint32_t);
+        const size_t bt_smem = (size_t)4 * (2 * (31 / kc + 2 + 32 / kc + 1) * kc + Cmax) * sizeof(uint32_t);
         cudaError_t ea = cudaSuccess;
 #define IPFA_BT(K_)                                                                                     \
     if (kc == K_) {                                                                                     \

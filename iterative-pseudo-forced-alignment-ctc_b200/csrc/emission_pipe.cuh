@@ -70,15 +70,18 @@ struct EmissionPipe {
     const float *base;    // &lp[w, 0, 0]
     int64_t stride_t;
     int T, U, V, pitch, tc, nchunks;
+    int t_lo;             // first frame of the range this pipe walks
+    bool rev;             // chunks (and the caller's rows) run from the last frame down
     bool vec16, bulk;
     uint64_t *bars;       // [kStages] mbarriers (bulk mode)
 
     // All threads of the group call init(); it ends with a group barrier.
     __device__ __forceinline__ void init(float *ring_, const int *cols_, const float *base_,
                                          int64_t stride_t_, int T_, int U_, int V_, int pitch_, int tc_,
-                                         uint64_t *bars_, int tid) {
+                                         uint64_t *bars_, int tid, int t_lo_ = 0, bool rev_ = false) {
+        // T_ frames starting at t_lo_; rev_: logical chunk 0 holds the LAST tc frames of the range
         ring = ring_; cols = cols_; base = base_; stride_t = stride_t_;
-        T = T_; U = U_; V = V_; pitch = pitch_; tc = tc_; bars = bars_;
+        T = T_; U = U_; V = V_; pitch = pitch_; tc = tc_; bars = bars_; t_lo = t_lo_; rev = rev_;
         nchunks = (T + tc - 1) / tc;
         vec16 = DENSE && (V % 4 == 0) && (stride_t % 4 == 0) &&
                 ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
@@ -93,6 +96,12 @@ struct EmissionPipe {
         group_sync<WARPS>();
     }
 
+    __device__ __forceinline__ int chunk_rows(int chunk) const { return min(tc, T - chunk * tc); }
+    // first (lowest) frame of a chunk; smem row r of the chunk holds frame chunk_t0 + r
+    __device__ __forceinline__ int chunk_t0(int chunk) const {
+        return rev ? t_lo + T - chunk * tc - chunk_rows(chunk) : t_lo + chunk * tc;
+    }
+
     __device__ __forceinline__ float *stage_ptr(int chunk) const {
         return ring + (size_t)(chunk % kStages) * tc * pitch;
     }
@@ -101,8 +110,8 @@ struct EmissionPipe {
     __device__ __forceinline__ void issue(int chunk, int tid) {
         if (chunk < nchunks) {
             float *dst = stage_ptr(chunk);
-            const int t0 = chunk * tc;
-            const int rows = min(tc, T - t0);
+            const int t0 = chunk_t0(chunk);
+            const int rows = chunk_rows(chunk);
             if constexpr (DENSE) {
                 if (bulk) {
                     if (tid == 0) {

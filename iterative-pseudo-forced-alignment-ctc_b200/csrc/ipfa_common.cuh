@@ -29,7 +29,7 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // log2(2^a + 2^b)
 __device__ __forceinline__ float lse2_2(float a, float b) {
     const float m = fmaxf(a, b);
-    const float d = fminf(a, b) - m;
+    const float d = -fabsf(a - b);  // == min - max; the |.| and the sign fold into the MUFU operand
     return m + lg2_approx(1.0f + ex2_approx(d));
 }
 // log2(2^a + 2^b + 2^c): three MUFU ops (the max term is exp2(0) = 1)
