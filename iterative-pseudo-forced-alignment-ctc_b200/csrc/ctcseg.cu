@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
 // ---------------------------------------------------------------------------
 using SegShape = LatticeShape;
 static bool pick_seg_shape(int cols, int n_windows, int V, SegShape *s) {
-    return pick_lattice_shape(cols, n_windows, s, "IPFA_SEG_SHAPE", use_dense_panel(V, cols) ? 3 : 6);
+    return pick_lattice_shape(cols, n_windows, s, "IPFA_SEG_SHAPE", use_dense_panel(V, cols) ? 3 : 6, true);
 }
 static int64_t seg_words_per_window(int Tmax, SegShape s) {
     const int spw = 32 / s.PER;
@@ -608,6 +608,7 @@ static int dispatch_seg_fill(const SegFillParams &prm, SegShape s, cudaStream_t 
 #define IPFA_X(K_, W_) \
     if (s.PER == K_ && s.WARPS == W_) return launch_seg_fill<K_, W_, DENSE>(prm, stream);
     IPFA_FOR_EACH_SHAPE(IPFA_X)
+    IPFA_FOR_EACH_EXTRA_SHAPE(IPFA_X)
 #undef IPFA_X
     return IPFA_ERR_UNSUPPORTED;
 }

@@ -164,8 +164,10 @@ class AnchorSweep:
     def __init__(self, corpus, index_duration, samples_to_frames_ratio, frame_shift=None, sample_rate=16000,
                  threshold=-2.0, short_utterance_len=30, max_window_size=70.0, window_to_stop=500.0,
                  min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, scoring_length=30, seg_flags=2,
-                 capacity=None):
+                 capacity=None, groups=1):
         self.corpus = corpus
+        self.groups = int(groups)
+        self._streams = None
         dev = corpus.device
         n = len(corpus.files)
         p = _Params()
@@ -228,26 +230,69 @@ class AnchorSweep:
             setattr(s, k, t.data_ptr())
         return s
 
-    def _workspace(self):
+    # ------------------------------------------------------------------ groups
+    # Lock step makes every iteration as long as its longest window.  Files are therefore cut into
+    # `groups` contiguous ranges that iterate independently on their own streams (a group is the
+    # same corpus / state with the per-file pointers shifted), so one file's long window only
+    # holds back its own group and the groups' kernels overlap on the GPU.
+    def _group_ranges(self):
+        n = len(self.corpus.files)
+        g = max(1, min(self.groups, n))
+        edges = [round(i * n / g) for i in range(g + 1)]
+        return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+    _PER_FILE_CORPUS = ("file_frame0", "file_frames", "file_samples", "row_first", "utt_first", "file_tok0")
+
+    def _structs(self, lo, hi):
+        c = self.corpus
+        cs = c.struct()
+        cs.n_files = hi - lo
+        for k in self._PER_FILE_CORPUS:
+            t = c.arrays[k]
+            setattr(cs, k, t.data_ptr() + lo * t.element_size())
+        ss = _State()
+        for k, t in self.state.items():
+            setattr(ss, k, t.data_ptr() + lo * t.stride(0) * t.element_size())
+        return cs, ss
+
+    def _workspaces(self):
         cap = tuple(self.capacity)
         if self._ws_cap != cap:
-            nbytes = lib().ipfa_sweep_workspace_bytes(len(self.corpus.files), cap[0], cap[1], cap[2], self.corpus.V)
             self._ws = None
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.corpus.device)
+            self._ws = []
+            for lo, hi in self._group_ranges():
+                nbytes = lib().ipfa_sweep_workspace_bytes(hi - lo, cap[0], cap[1], cap[2], self.corpus.V)
+                self._ws.append(torch.empty(nbytes, dtype=torch.uint8, device=self.corpus.device))
             self._ws_cap = cap
         return self._ws
 
     def step(self, n_steps=1):
-        """``n_steps`` lock-step iterations, asynchronous on the current stream."""
+        """``n_steps`` iterations of every group; asynchronous, joined back into the current stream."""
         c = self.corpus
-        ws = self._workspace()
-        cs, ss = c.struct(), self._state_struct()
+        ranges = self._group_ranges()
+        wss = self._workspaces()
+        cur = torch.cuda.current_stream(c.device)
+        if self._streams is None or len(self._streams) != len(ranges):
+            self._streams = [cur] if len(ranges) == 1 else [torch.cuda.Stream(c.device) for _ in ranges]
         with torch.cuda.device(c.device):
-            rc = lib().ipfa_sweep_step_device(
-                ctypes.byref(cs), ctypes.byref(self.params), ctypes.byref(ss), self.out_seg.data_ptr(),
-                self.out_info.data_ptr(), self.steps, n_steps, self.capacity[0], self.capacity[1],
-                self.capacity[2], ws.data_ptr(), ws.numel(), torch.cuda.current_stream(c.device).cuda_stream)
-        check(rc, "ipfa_sweep_step_device")
+            start = None
+            if len(ranges) > 1:
+                start = torch.cuda.Event()
+                start.record(cur)
+            for (lo, hi), ws, st in zip(ranges, wss, self._streams):
+                if start is not None:
+                    st.wait_event(start)
+                cs, ss = self._structs(lo, hi)
+                rc = lib().ipfa_sweep_step_device(
+                    ctypes.byref(cs), ctypes.byref(self.params), ctypes.byref(ss), self.out_seg.data_ptr(),
+                    self.out_info.data_ptr(), self.steps, n_steps, self.capacity[0], self.capacity[1],
+                    self.capacity[2], ws.data_ptr(), ws.numel(), st.cuda_stream)
+                check(rc, "ipfa_sweep_step_device")
+            if len(ranges) > 1:
+                for st in self._streams:
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    cur.wait_event(done)
         self.steps += n_steps
 
     def run(self, steps_per_poll=8, max_steps=100000, recalc_fn=None):
@@ -308,3 +353,36 @@ class AnchorSweep:
                 "frames": int(self.state["frames"].sum().item()),
                 "status": {STATUS_NAMES[k]: int(v) for k, v in
                            zip(*np.unique(self.state["status"].cpu().numpy(), return_counts=True))}}
+
+
+def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, threshold=-2.0, short_utterance_len=30,
+                         max_words_sequence=24, max_window_size=70.0, window_to_stop=500.0,
+                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10):
+    """Anchor loop of several files with file-level emissions resident on the GPU.
+
+    ``jobs``: list of ``(audio_path, file_df, vad_file_df)`` like the arguments of
+    ``get_file_iterative_segmentation``.  Every file is encoded ONCE (``aligner.get_lpz`` on the
+    whole normalised audio) instead of once per window (:149-201).  Returns
+    ``(rows_per_file, status_per_file)``; files whose status is not DONE stopped where the
+    reference's host-side policy takes over (see ``ipfa_b200.h``) and carry the rows found so far."""
+    files = []
+    for audio_path, file_df, vad_file_df in jobs:
+        info = hg.audio_info(audio_path)
+        audio, sr = hg.audio_load(audio_path, channels_first=False)
+        lpz = aligner.get_lpz(asr_model.audio_normalizer(audio, sr))
+        if not torch.is_tensor(lpz):
+            lpz = torch.as_tensor(lpz)
+        fixed = hg.fix_time_reference(file_df, vad_file_df, info.num_frames / info.sample_rate, len(file_df.index))
+        file_id = audio_path.split('/')[-1].replace('.wav', '')
+        files.append(SweepFile(file_id, audio_path, lpz.cuda(), info.num_frames,
+                               rows_from_dataframe(fixed, max_words_sequence)))
+    corpus = SweepCorpus(files, asr_model.tokenizer, blank=aligner.config.blank)
+    fs = int(asr_model.hparams.sample_rate)
+    sweep = AnchorSweep(corpus, index_duration=samples_to_frames_ratio / fs,
+                        samples_to_frames_ratio=samples_to_frames_ratio, sample_rate=fs, threshold=threshold,
+                        short_utterance_len=short_utterance_len, max_window_size=max_window_size,
+                        window_to_stop=window_to_stop, min_text_to_audio_prop=min_text_to_audio_prop,
+                        max_text_to_audio_prop_exec=max_text_to_audio_prop_exec,
+                        scoring_length=aligner.config.score_min_mean_over_L, seg_flags=aligner.config.flags)
+    status = sweep.run()
+    return sweep.file_rows(), status

@@ -12,7 +12,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import ipfa_b200  # noqa: E402  (fails loudly when libipfa_b200.so is missing)
-from ipfa_b200 import anchor, hostglue, sharding, words  # noqa: E402,F401
+from ipfa_b200 import anchor, hostglue, sharding, sweep, words  # noqa: E402,F401
 from ipfa_b200.ctc_segmentation import CTCSegmentation  # noqa: E402,F401
 
 

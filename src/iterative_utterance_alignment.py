@@ -37,6 +37,29 @@ def main(args):
     mine = sharding.lpt_shards(costs, world)[rank]
     os.makedirs(args.dst, exist_ok=True)
 
+    todo = []
+    for i in mine:
+        audio_path = audio_paths[i]
+        tsv_result_file = os.path.join(args.dst, audio_path.split('/')[-1].replace('.wav', '.tsv'))
+        if not (os.path.isfile(tsv_result_file) and os.path.getsize(tsv_result_file) > 0):
+            todo.append(i)
+    resident = {}
+    if args.resident_emissions and todo:
+        # every file encoded once, the anchor loops of all files in lock step on the device;
+        # files that reach the reference's time re-spreading branch (:119-146) are redone below
+        from _common import sweep as sweep_mod
+        jobs = [(audio_paths[i], df[df['Sample_Path'] == audio_paths[i]].reset_index(drop=True),
+                 vad_df[vad_df['Sample_Path'] == audio_paths[i]].reset_index(drop=True)) for i in todo]
+        rows_per_file, status = sweep_mod.align_files_resident(
+            asr_model, aligner, jobs, samples_to_frames_ratio, threshold=args.threshold,
+            short_utterance_len=args.short_utterance_len, max_words_sequence=args.max_words_sequence,
+            max_window_size=args.max_window_size, window_to_stop=args.window_to_stop,
+            min_text_to_audio_prop=args.min_text_to_audio_prop,
+            max_text_to_audio_prop_exec=args.max_text_to_audio_prop_exec)
+        for i, rows, st in zip(todo, rows_per_file, status):
+            if st in (sweep_mod.DONE, sweep_mod.STOP_WINDOW, sweep_mod.STOP_EXCEPTIONS):
+                resident[i] = rows
+
     for i in mine:
         audio_path = audio_paths[i]
         tsv_result_file = os.path.join(args.dst, audio_path.split('/')[-1].replace('.wav', '.tsv'))
@@ -45,7 +68,7 @@ def main(args):
             continue
         file_df = df[df['Sample_Path'] == audio_path].reset_index(drop=True)
         vad_file_df = vad_df[vad_df['Sample_Path'] == audio_path].reset_index(drop=True)
-        rows = anchor.get_file_iterative_segmentation(
+        rows = resident[i] if i in resident else anchor.get_file_iterative_segmentation(
             asr_model, aligner, audio_path, file_df, vad_file_df, samples_to_frames_ratio,
             logs_path=args.logs_path, threshold=args.threshold, short_utterance_len=args.short_utterance_len,
             max_words_sequence=args.max_words_sequence, min_words_sequence=args.min_words_sequence,
@@ -73,4 +96,7 @@ if __name__ == '__main__':
     parser.add_argument('--window_to_stop', type=float, default=500.0)
     parser.add_argument('--min_text_to_audio_prop', type=float, default=0.8)
     parser.add_argument('--max_text_to_audio_prop_exec', type=int, default=10)
+    parser.add_argument('--resident_emissions', action='store_true',
+                        help='encode every file once and run the anchor loops of all files on the GPU '
+                             '(windows are frame slices of the file-level emissions)')
     main(parser.parse_args())

@@ -138,7 +138,7 @@ def test_sweep_is_independent_of_batching_and_capacity(exact_audio, tmp_path):
     files = _sweep_files(specs)
     tok = stub.CharTokenizer()
     kw = dict(index_duration=0.02, samples_to_frames_ratio=320.0)
-    both = sweep.AnchorSweep(sweep.SweepCorpus(files, tok), **kw)
+    both = sweep.AnchorSweep(sweep.SweepCorpus(files, tok), groups=2, **kw)
     both.run()
     rows_both = both.file_rows()
     for i in range(2):
@@ -160,7 +160,8 @@ def test_sweep_equals_cpu_oracle_on_a_synthetic_corpus():
                                              (0.6, 0.3, 0), (3.0, 0.5, 2)])]
     lps = [sweep_corpus.emissions(s, "cuda", seed=7 + i) for i, s in enumerate(specs)]
     files = [sweep.SweepFile(s.file_id, s.audio_path, lp, s.n_samples, s.rows) for s, lp in zip(specs, lps)]
-    sw = sweep.AnchorSweep(sweep.SweepCorpus(files, tok), index_duration=0.02, samples_to_frames_ratio=320.0)
+    sw = sweep.AnchorSweep(sweep.SweepCorpus(files, tok), index_duration=0.02, samples_to_frames_ratio=320.0,
+                           groups=3)
     status = sw.run(steps_per_poll=8)
     got = sw.file_rows()
     windows = sw.state["n_windows"].cpu().numpy()
@@ -174,3 +175,36 @@ def test_sweep_equals_cpu_oracle_on_a_synthetic_corpus():
         assert windows[f] == stats["windows"] and cells[f] == stats["cells"], s.file_id
         n_rows += len(ref)
     assert n_rows > 100
+
+
+def test_entry_point_with_resident_emissions(tmp_path):
+    """The drop-in CLI in --resident_emissions mode: every file encoded once, all anchor loops on
+    the device, same per-file TSV layout as the reference (:410, :469-473)."""
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(0)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows, vads = [], []
+    for name, secs in (("a", 40), ("b", 25)):
+        wav = str(tmp_path / f"{name}.wav")
+        hg.write_wav(wav, rng.normal(0, 0.1, secs * 16000))
+        utts = _utterances(rng, 5)
+        for i, u in enumerate(utts):
+            rows.append([f"{name}_{i}", wav, 1, secs / 5, 0.0, float(secs), u, "spk", "db"])
+        vads.append([wav, 0.0, float(secs), float(secs)])
+    tsv, vad = str(tmp_path / "in.tsv"), str(tmp_path / "vad.tsv")
+    pd.DataFrame(rows, columns=['Sample_ID', 'Sample_Path', 'Channel', 'Audio_Length', 'Start', 'End',
+                                'Transcription', 'Speaker_ID', 'Database']).to_csv(tsv, sep='\t', index=None)
+    pd.DataFrame(vads, columns=['Sample_Path', 'Start', 'End', 'Segment_Length']).to_csv(vad, sep='\t', index=None)
+    dst = str(tmp_path / "out")
+    cmd = [sys.executable, os.path.join(root, "src", "iterative_utterance_alignment.py"), "--tsv", tsv,
+           "--vad_segments_tsv", vad, "--dst", dst, "--logs_path", str(tmp_path), "--asr_hub", "stub",
+           "--max_words_sequence", "8", "--resident_emissions"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    for name in ("a", "b"):
+        out = pd.read_csv(os.path.join(dst, f"{name}.tsv"), sep='\t')
+        assert list(out.columns) == anchor.RESULT_COLUMNS
+        assert len(out.index) >= 1  # the last row of a file is always kept (:263)
+        assert (out['End'] >= out['Start']).all()
