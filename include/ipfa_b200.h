@@ -49,6 +49,8 @@ extern "C" {
 #define IPFA_WIN_INFEASIBLE 1    /* forced_align: T < L + repeats (torchaudio raises) */
 #define IPFA_WIN_BAD_LABEL 2     /* a target id is < 0, >= V or equals blank (Viterbi) */
 #define IPFA_WIN_TEXT_LONGER 4   /* ctcseg: N > T */
+#define IPFA_WIN_WINDOW_TOO_SMALL 8 /* windowed ctcseg: the backtrace left the window (reference: IndexError,
+                                      retry with twice the window) */
 
 int ipfa_version(void);
 const char *ipfa_status_string(int status);
@@ -136,7 +138,8 @@ int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
  *   status_out    [N] int32 IPFA_WIN_* bits (IPFA_WIN_TEXT_LONGER <-> AssertionError)
  *   With IPFA_SEG_ALL_PREFIXES clear only the full text is aligned: slot K_w - 1 is
  *   written, the other prefix slots are left untouched.  Slot k-1 fills seg[., k-1, 0..k-1].
- *   Tmax > 8000 frames (the reference's windowed table mode) returns IPFA_ERR_UNSUPPORTED.
+ *   Tmax > 8000 frames (the reference's windowed table mode): use ipfa_ctcseg_windowed_device;
+ *   this entry point returns IPFA_ERR_UNSUPPORTED.
  * ------------------------------------------------------------------------- */
 #define IPFA_SEG_BLANK_COST_ZERO 1
 #define IPFA_SEG_PREAMBLE_COST_ZERO 2
@@ -205,6 +208,28 @@ int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_off, int64_t 
                                double *seg_out, int32_t *term_t_out, int32_t *timing_out,
                                float *char_prob_out, int32_t *state_out, int32_t *status_out,
                                void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Kernel (2b), windowed table mode -- audio longer than config.min_window_size frames
+ * (8000).  ctc-segmentation keeps `window` rows per column and slides the window down the
+ * audio column by column (offset from the previous column's arg-max), so the fill is
+ * column-serial; the per-column offsets depend on the number of columns, so with
+ * IPFA_SEG_ALL_PREFIXES every prefix gets its own fill.  Same arguments and outputs as
+ * ipfa_ctcseg_device / ipfa_ctcseg_windows_device (win_off may be NULL -> w * stride_n) plus
+ *   window       table rows (config.min_window_size, doubled by the caller after
+ *                IPFA_WIN_WINDOW_TOO_SMALL up to config.max_window_size)
+ *   term_t_out   terminal ROW inside the last column's window
+ * For T <= window the result equals ipfa_ctcseg_device's.
+ * ------------------------------------------------------------------------- */
+size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window);
+int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_off, int64_t stride_n, int64_t stride_t,
+                                const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
+                                const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
+                                int N, int Tmax, int Cmax, int Kmax, int V, int blank,
+                                double index_duration, int score_len, int flags, int window,
+                                double *seg_out, int32_t *term_t_out, int32_t *timing_out,
+                                float *char_prob_out, int32_t *state_out, int32_t *status_out,
+                                void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Anchor sweep: the iterative anchor loop of many files, resident on the device

@@ -290,6 +290,62 @@ __device__ __forceinline__ double np_pairwise_sum(const float *a, int n) {
     return (n <= 128) ? np_sum_upto128(a, n) : np_pairwise_sum_rec(a, n);
 }
 
+// determine_utterance_segments for utterances 0..n_utt-1 of one
+// alignment, one warp: start/end from the column timings, score = min over the windowed means
+// of char_probs (numpy summation order, fp64).
+__device__ __forceinline__ void score_segments(const int32_t *__restrict__ ub, const int32_t *timing,
+                                               const float *cprob, int n_utt, int T, int Cmax, double dur,
+                                               int n, bool round_nearest, int lane, double *seg) {
+    auto tm = [&](int cc) -> double {
+        if (cc < 0 || cc >= Cmax) return 0.0;
+        const int f = timing[cc];
+        return f < 0 ? 0.0 : __dmul_rn((double)f, dur);
+    };
+    for (int u = 0; u < n_utt; ++u) {
+        const int b = ub[u], e = ub[u + 1];
+        const double mid_b = __ddiv_rn(__dadd_rn(tm(b), tm(b - 1)), 2.0);
+        const double start = fmax(__dadd_rn(tm(b + 1), -0.5), mid_b);
+        const double mid_e = __ddiv_rn(__dadd_rn(tm(e), tm(e - 1)), 2.0);
+        const double end = fmin(__dadd_rn(tm(e - 1), 0.5), mid_e);
+        const double qs = __ddiv_rn(start, dur), qe = __ddiv_rn(end, dur);
+        const long long s_t = (long long)(round_nearest ? rint(qs) : floor(qs));
+        const long long e_t = (long long)(round_nearest ? rint(qe) : floor(qe));
+        double score;
+        if (e_t <= s_t) {
+            score = -10000000000.0;
+        } else if (e_t - s_t <= n) {
+            const int lo = (int)max(0LL, min(s_t, (long long)T));
+            const int hi = (int)max(0LL, min(e_t, (long long)T));
+            const int cnt = hi - lo;
+            score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
+                              : __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            double best = 0.0;
+            bool has_nan = false;
+            for (long long t = s_t + lane; t < e_t - n; t += 32) {
+                const int lo = (int)max(0LL, min(t, (long long)T));
+                const int hi = (int)max(0LL, min(t + n, (long long)T));
+                const int cnt = hi - lo;
+                if (cnt <= 0) { has_nan = true; continue; }
+                const double m = __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt);
+                best = fmin(best, m);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, best, off);
+                best = fmin(best, o);
+            }
+            (void)has_nan;
+            score = best;
+        }
+        if (lane == 0) {
+            seg[u * 3] = start;
+            seg[u * 3 + 1] = end;
+            seg[u * 3 + 2] = score;
+        }
+    }
+}
+
 // Bits 0, KC, 2KC, ... of x packed into the low 32 / KC bits.
 template <int KC>
 __device__ __forceinline__ uint32_t compress_stride(uint32_t x) {
@@ -504,57 +560,264 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     __threadfence_block();
 
     // ---- determine_utterance_segments ---------------------------------------
-    const double dur = prm.index_duration;
-    const int n = prm.score_len;
-    const bool round_nearest = prm.flags & IPFA_SEG_ROUND_NEAREST;
-    auto tm = [&](int cc) -> double {
-        if (cc < 0 || cc >= prm.Cmax) return 0.0;
-        const int f = timing[cc];
-        return f < 0 ? 0.0 : __dmul_rn((double)f, dur);
-    };
-    for (int u = 0; u <= kslot; ++u) {
-        const int b = ub[u], e = ub[u + 1];
-        const double mid_b = __ddiv_rn(__dadd_rn(tm(b), tm(b - 1)), 2.0);
-        const double start = fmax(__dadd_rn(tm(b + 1), -0.5), mid_b);
-        const double mid_e = __ddiv_rn(__dadd_rn(tm(e), tm(e - 1)), 2.0);
-        const double end = fmin(__dadd_rn(tm(e - 1), 0.5), mid_e);
-        const double qs = __ddiv_rn(start, dur), qe = __ddiv_rn(end, dur);
-        const long long s_t = (long long)(round_nearest ? rint(qs) : floor(qs));
-        const long long e_t = (long long)(round_nearest ? rint(qe) : floor(qe));
-        double score;
-        if (e_t <= s_t) {
-            score = -10000000000.0;
-        } else if (e_t - s_t <= n) {
-            const int lo = (int)max(0LL, min(s_t, (long long)T));
-            const int hi = (int)max(0LL, min(e_t, (long long)T));
-            const int cnt = hi - lo;
-            score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
-                              : __longlong_as_double(0x7ff8000000000000LL);
-        } else {
-            double best = 0.0;
-            bool has_nan = false;
-            for (long long t = s_t + lane; t < e_t - n; t += 32) {
-                const int lo = (int)max(0LL, min(t, (long long)T));
-                const int hi = (int)max(0LL, min(t + n, (long long)T));
-                const int cnt = hi - lo;
-                if (cnt <= 0) { has_nan = true; continue; }
-                const double m = __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt);
-                best = fmin(best, m);
+    score_segments(ub, timing, cprob, kslot + 1, T, prm.Cmax, prm.index_duration, prm.score_len,
+                   (prm.flags & IPFA_SEG_ROUND_NEAREST) != 0, lane, seg);
+}
+
+// ===========================================================================
+// Windowed table mode: audio longer than
+// `min_window_size` frames (8000 = 160 s).  ctc-segmentation then keeps only W rows per
+// column and slides that window down the audio column by column:
+//     offset_c = min(max(0, argmax_{c-1} - W/2), min(ceil((T-W)/N), (T-W) - sum of offsets))
+// where argmax_{c-1} is the first arg-max over ALL W rows of the previous column -- so a
+// column cannot start before the previous one is complete, and inside a column
+//     x_t = max(switch_t, x_{t-1} + e_t)
+// is a chain of W fp32-rounded adds.  The fill is therefore column-serial with a serial
+// scan per column (phase B below); everything around the chain -- emission gathers, switch
+// candidates, the tolerance test of the reference's backtrace (evaluated at fill time and
+// stored as one bit per cell, like the full-table kernel), first-argmax -- is data parallel
+// over the rows of a tile.  One CTA per (window, prefix): the per-column offsets depend on
+// the number of columns, so prefixes do NOT share a fill in this mode.  This is the rare
+// path; parity with the reference's arithmetic, not speed, is the point.
+struct SegWinParams {
+    const float *lp;
+    const int64_t *win_off;
+    int64_t stride_n, stride_t;
+    const int32_t *in_len;
+    const int32_t *gt;
+    int64_t gt_stride;
+    const int32_t *n_cols;
+    const int32_t *utt_begin;  // [N][Kmax+1]
+    const int32_t *n_utts;
+    int N, Tmax, Cmax, Kmax, V, blank, flags, window, score_len;
+    double index_duration;
+    float *cols2;        // [problems][2][window] previous / current table column
+    uint32_t *bits;      // [problems][Cmax][words] 1 bit per (column, row): reverse transition = switch
+    int64_t words;       // 32-bit words per column = ceil(window / 32)
+    int32_t *offsets;    // [problems][Cmax] window offset of every column
+    int32_t *term;       // [problems] first argmax row of the last column
+    double *seg_out;     // [N][Kmax][Kmax][3]
+    int32_t *term_t_out; // [N][Kmax]
+    int32_t *timing;     // [N][Kmax][Cmax]
+    float *char_prob;    // [N][Kmax][Tmax]
+    int32_t *state_out;  // nullable
+    int32_t *status_out; // [N]
+};
+
+constexpr int kWinTile = 2048;
+constexpr int kWinThreads = 256;
+
+__global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const SegWinParams prm) {
+    const int prob = blockIdx.x;
+    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int K = max(0, min(prm.n_utts[w], prm.Kmax));
+    const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
+    const int NC = min(ub[kslot + 1] + 1, min(prm.n_cols[w], prm.Cmax));  // columns of this prefix
+    if (T <= 0 || NC <= 1 || NC > T) return;
+    const int W = min(prm.window, T);
+    const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
+    const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
+    float *colA = prm.cols2 + (int64_t)prob * 2 * prm.window;
+    float *colB = colA + prm.window;
+    uint32_t *bits = prm.bits + (int64_t)prob * prm.Cmax * prm.words;
+    int32_t *offs = prm.offsets + (int64_t)prob * prm.Cmax;
+    const bool blank_cost_zero = prm.flags & IPFA_SEG_BLANK_COST_ZERO;
+    const bool preamble_cost_zero = prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO;
+    const int tid = threadIdx.x;
+
+    __shared__ float s_sw[kWinTile], s_e[kWinTile], s_eg[kWinTile], s_x[kWinTile + 1];
+    __shared__ int s_off, s_offsum, s_arg;
+    __shared__ float s_max, s_carry;
+
+    const float mean_offset = (float)(T - W) / (float)NC;
+    const int higher_offset = (int)ceilf(mean_offset);
+    if (tid == 0) { s_off = 0; s_offsum = 0; s_arg = -1; s_max = 0.0f; }
+    __syncthreads();
+
+    float *prev = colA, *cur = colB;
+    for (int c = 0; c < NC; ++c) {
+        if (tid == 0) {
+            int offset = s_off;
+            if (c > 0) {
+                const int lim = (T - W) - s_offsum;
+                const int hi = min(higher_offset, lim);
+                const int lo = max(s_arg - W / 2, 0);
+                offset = min(lo, hi);
+                s_off = offset;
+                s_offsum += offset;
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double o = __shfl_xor_sync(0xffffffffu, best, off);
-                best = fmin(best, o);
-            }
-            (void)has_nan;
-            score = best;
+            offs[c] = s_offsum;
+            s_arg = -1;
+            s_max = 0.0f;
         }
-        if (lane == 0) {
-            seg[u * 3] = start;
-            seg[u * 3 + 1] = end;
-            seg[u * 3 + 2] = score;
+        __syncthreads();
+        const int offset = s_off, offset_sum = s_offsum;
+        int g = gt[c];
+        if (c > 0 && (g < 0 || g >= prm.V)) g = prm.blank;
+        uint32_t *bits_c = bits + (int64_t)c * prm.words;
+        for (int t0 = 0; t0 < W; t0 += kWinTile) {
+            const int rows = min(kWinTile, W - t0);
+            // phase A: switch candidates and stay emissions of the tile
+            for (int r = tid; r < rows; r += kWinThreads) {
+                const int t = t0 + r;
+                const float *row = lp + (int64_t)(t + offset_sum) * prm.stride_t;
+                const float eb = row[prm.blank];
+                float eg = kProbMax, sw = kProbMax, e;
+                if (c > 0) {
+                    eg = row[g];
+                    const int tp = t - 1 + offset;
+                    if (!(tp >= W || tp < 0 || t - 1 < 0)) sw = prev[tp] + eg;
+                    e = blank_cost_zero ? 0.0f : fmaxf(eb, eg);
+                } else {
+                    e = eb;  // column 0: running blank sum when the preamble is not free
+                }
+                s_sw[r] = sw; s_e[r] = e; s_eg[r] = eg;
+            }
+            __syncthreads();
+            // phase B: the serial chain x_t = max(switch_t, x_{t-1} + e_t), first arg-max
+            if (tid == 0) {
+                float x = (t0 == 0) ? 0.0f : s_carry;
+                float best = s_max;
+                int arg = s_arg;
+                int r = 0;
+                if (t0 == 0) {
+                    if (c == 0) {
+                        x = 0.0f;        // table[0, 0] = 0, not part of the arg-max loop (it starts at t = 1)
+                    } else {
+                        x = kProbMax;    // t - 1 < 0: switch and stay are both prob_max
+                        arg = 0; best = x;
+                    }
+                    s_x[1] = x;
+                    r = 1;
+                }
+                for (; r < rows; ++r) {
+                    float stay;
+                    if (c == 0) stay = preamble_cost_zero ? 0.0f : x + s_e[r];
+                    else stay = x + s_e[r];
+                    x = fmaxf(s_sw[r], stay);
+                    s_x[r + 1] = x;
+                    if (arg == -1 || best < x) { best = x; arg = t0 + r; }
+                }
+                s_x[0] = (t0 == 0) ? 0.0f : s_carry;  // x_{t0-1}
+                s_carry = x;
+                s_max = best;
+                s_arg = arg;
+            }
+            __syncthreads();
+            // phase C: the column goes to the workspace; the tolerance test of the reference's
+            // backtrace, |stay_prob - est_stay| > |switch_prob - est_switch| -> switch, as one bit
+            for (int r = tid; r < ((rows + 31) & ~31); r += kWinThreads) {
+                const int t = t0 + r;
+                bool sw_bit = false;
+                if (r < rows) {
+                    const float x = s_x[r + 1];
+                    cur[t] = x;
+                    const int tp = t - 1 + offset;
+                    if (c > 0 && t > 0 && tp >= 0 && tp < W) {
+                        const float eg = s_eg[r];
+                        const float stay_prob = fmaxf(lp[(int64_t)(t + offset_sum) * prm.stride_t + prm.blank], eg);
+                        const float est_switch = x - prev[tp];
+                        const float est_stay = x - s_x[r];
+                        sw_bit = fabsf(stay_prob - est_stay) > fabsf(eg - est_switch);
+                    }
+                }
+                const uint32_t word = __ballot_sync(0xffffffffu, sw_bit);
+                if ((tid & 31) == 0 && r < rows) bits_c[t >> 5] = word;
+            }
+            __syncthreads();
+        }
+        float *tmp = prev; prev = cur; cur = tmp;
+    }
+    if (tid == 0) prm.term[prob] = s_arg;
+}
+
+// One warp per (window, prefix): follow the bits from (argmax of the last column, last column)
+// to (0, 0) in window coordinates, then score the utterances.
+__global__ void __launch_bounds__(128) ctcseg_windowed_backtrace_kernel(const SegWinParams prm) {
+    const int lane = threadIdx.x & 31;
+    const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (prob >= prm.N * prm.Kmax) return;
+    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int K = max(0, min(prm.n_utts[w], prm.Kmax));
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int NCw = max(0, min(prm.n_cols[w], prm.Cmax));
+    const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+    if (kslot == 0 && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
+    const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
+    const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
+    const int64_t slot = (int64_t)w * prm.Kmax + kslot;
+    int32_t *timing = prm.timing + slot * prm.Cmax;
+    float *cprob = prm.char_prob + slot * prm.Tmax;
+    int32_t *state = prm.state_out ? prm.state_out + slot * prm.Tmax : nullptr;
+    double *seg = prm.seg_out + slot * prm.Kmax * 3;
+    const int NC = min(ub[kslot + 1] + 1, NCw);
+    for (int t = lane; t < prm.Tmax; t += 32) {
+        cprob[t] = 0.0f;
+        if (state) state[t] = -2;
+    }
+    for (int c = lane; c < prm.Cmax; c += 32) timing[c] = -1;
+    const bool feasible = T > 0 && NC > 1 && NC <= T;
+    const int t_term = feasible ? prm.term[prob] : -1;
+    if (lane == 0) prm.term_t_out[slot] = t_term;  // window row; absolute frame = row + offset of the column
+    if (!feasible || t_term < 0) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+        return;
+    }
+    __syncwarp();
+    const int W = min(prm.window, T);
+    const uint32_t *bits = prm.bits + (int64_t)prob * prm.Cmax * prm.words;
+    const int32_t *offs = prm.offsets + (int64_t)prob * prm.Cmax;
+    bool too_small = false;
+    if (lane == 0) {
+        int t = t_term, c = NC - 1;
+        while (t != 0 || c != 0) {
+            const int oc = offs[c];
+            const int offset = (c > 0) ? oc - offs[c - 1] : 0;
+            // the reference reads table[t - 1 + offset, c - 1] here: beyond the window -> IndexError
+            // (it doubles the window and starts over); row 0 of a later column is unreachable
+            if ((c > 0 && t - 1 + offset >= W) || (t == 0 && c > 0)) { too_small = true; break; }
+            const float *row = lp + (int64_t)(t + oc) * prm.stride_t;
+            const float eb = row[prm.blank];
+            if (c == 0) {
+                cprob[oc + t] = eb;
+                if (state) state[oc + t] = -1;
+                --t;
+                continue;
+            }
+            int g = gt[c];
+            if (g < 0 || g >= prm.V) g = prm.blank;
+            const float eg = row[g];
+            const bool sw = (bits[(int64_t)c * prm.words + (t >> 5)] >> (t & 31)) & 1u;
+            if (sw) {
+                timing[c] = oc + t;
+                cprob[oc + t] = eg;
+                if (state) state[oc + t] = c;
+                --c;
+                t -= 1 - offset;
+            } else {
+                cprob[oc + t] = fmaxf(eb, eg);
+                if (state) state[oc + t] = -1;
+                --t;
+            }
         }
     }
+    too_small = __shfl_sync(0xffffffffu, too_small, 0);
+    __syncwarp();
+    __threadfence_block();
+    if (too_small) {
+        if (lane == 0) atomicOr(prm.status_out + w, IPFA_WIN_WINDOW_TOO_SMALL);
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+        return;
+    }
+    score_segments(ub, timing, cprob, kslot + 1, T, prm.Cmax, prm.index_duration, prm.score_len,
+                   (prm.flags & IPFA_SEG_ROUND_NEAREST) != 0, lane, seg);
 }
 
 // ---------------------------------------------------------------------------
@@ -727,4 +990,66 @@ extern "C" int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_of
     return ipfa::ctcseg_run(lp, win_off, 0, stride_t, in_len, gt, gt_stride, n_cols, utt_begin, n_utts, N, Tmax,
                             Cmax, Kmax, V, blank, index_duration, score_len, flags, seg_out, term_t_out,
                             timing_out, char_prob_out, state_out, status_out, workspace, workspace_bytes, stream);
+}
+
+// ---------------------------------------------------------------------------
+// windowed table mode
+static size_t win_words(int window) { return (size_t)((window + 31) / 32); }
+
+extern "C" size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window) {
+    if (N <= 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || window <= 0) return 256;
+    const size_t P = (size_t)N * Kmax;
+    const size_t W = (size_t)(window < Tmax ? window : Tmax);
+    size_t b = pad256(P * 2 * W * 4);                   // previous / current column
+    b += pad256(P * (size_t)Cmax * win_words((int)W) * 4);  // 1-bit transitions
+    b += pad256(P * (size_t)Cmax * 4);                  // offsets
+    b += pad256(P * 4);                                 // terminal rows
+    b += pad256(P * (size_t)Cmax * 4);                  // timing scratch
+    b += pad256(P * (size_t)Tmax * 4);                  // char_prob scratch
+    return b + 256;
+}
+
+extern "C" int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_off, int64_t stride_n,
+                                           int64_t stride_t, const int32_t *in_len, const int32_t *gt,
+                                           int64_t gt_stride, const int32_t *n_cols, const int32_t *utt_begin,
+                                           const int32_t *n_utts, int N, int Tmax, int Cmax, int Kmax, int V,
+                                           int blank, double index_duration, int score_len, int flags,
+                                           int window, double *seg_out, int32_t *term_t_out,
+                                           int32_t *timing_out, float *char_prob_out, int32_t *state_out,
+                                           int32_t *status_out, void *workspace, size_t workspace_bytes,
+                                           void *stream) {
+    if (N == 0) return IPFA_OK;
+    if (!lp || !in_len || !gt || !n_cols || !utt_begin || !n_utts || !seg_out || !term_t_out ||
+        !status_out || !workspace || N < 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || V <= 0 || blank < 0 ||
+        blank >= V || score_len <= 0 || !(index_duration > 0.0) || window <= 0)
+        return IPFA_ERR_INVALID_ARG;
+    if (workspace_bytes < ipfa_ctcseg_windowed_workspace_bytes(N, Tmax, Cmax, Kmax, window))
+        return IPFA_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t P = (size_t)N * Kmax;
+    const int W = window < Tmax ? window : Tmax;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    SegWinParams p{};
+    p.lp = lp; p.win_off = win_off; p.stride_n = stride_n; p.stride_t = stride_t; p.in_len = in_len;
+    p.gt = gt; p.gt_stride = gt_stride; p.n_cols = n_cols; p.utt_begin = utt_begin; p.n_utts = n_utts;
+    p.N = N; p.Tmax = Tmax; p.Cmax = Cmax; p.Kmax = Kmax; p.V = V; p.blank = blank; p.flags = flags;
+    p.window = W; p.score_len = score_len; p.index_duration = index_duration;
+    p.words = (int64_t)win_words(W);
+    p.cols2 = reinterpret_cast<float *>(ws);            ws += pad256(P * 2 * (size_t)W * 4);
+    p.bits = reinterpret_cast<uint32_t *>(ws);          ws += pad256(P * (size_t)Cmax * win_words(W) * 4);
+    p.offsets = reinterpret_cast<int32_t *>(ws);        ws += pad256(P * (size_t)Cmax * 4);
+    p.term = reinterpret_cast<int32_t *>(ws);           ws += pad256(P * 4);
+    int32_t *timing_scratch = reinterpret_cast<int32_t *>(ws); ws += pad256(P * (size_t)Cmax * 4);
+    float *cprob_scratch = reinterpret_cast<float *>(ws);
+    p.seg_out = seg_out; p.term_t_out = term_t_out;
+    p.timing = timing_out ? timing_out : timing_scratch;
+    p.char_prob = char_prob_out ? char_prob_out : cprob_scratch;
+    p.state_out = state_out; p.status_out = status_out;
+    ctcseg_windowed_fill_kernel<<<(unsigned)P, kWinThreads, 0, st>>>(p);
+    ++g_launch_count;
+    ctcseg_windowed_backtrace_kernel<<<(unsigned)((P + 3) / 4), 128, 0, st>>>(p);
+    ++g_launch_count;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
 }

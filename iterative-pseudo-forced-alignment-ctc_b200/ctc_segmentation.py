@@ -319,13 +319,23 @@ class CTCSegmentation:
     @staticmethod
     def _run(tasks, all_prefixes, details):
         cfg, lp, in_len, gt, n_cols, ub, n_utts = CTCSegmentation._pack(tasks)
-        if lp.shape[1] > cfg.min_window_size:
-            raise NotImplementedError("windowed table mode (T > min_window_size) is not built yet")
         flags = cfg.flags | (ops.SEG_ALL_PREFIXES if all_prefixes else 0)
-        res = ops.ctcseg_align(lp, in_len, gt, n_cols, ub, n_utts, cfg.index_duration_in_seconds,
-                               blank=cfg.blank, score_len=cfg.score_min_mean_over_L, flags=flags,
-                               details=details)
-        return cfg, res, n_utts
+        kw = dict(blank=cfg.blank, score_len=cfg.score_min_mean_over_L, flags=flags, details=details)
+        if lp.shape[1] <= cfg.min_window_size:
+            res = ops.ctcseg_align(lp, in_len, gt, n_cols, ub, n_utts, cfg.index_duration_in_seconds, **kw)
+            return cfg, res, n_utts
+        # ctc-segmentation's windowed table mode: audio longer than min_window_size frames.  When the
+        # backtrace leaves the window the reference catches IndexError, doubles the window and starts
+        # over until max_window_size ("Check data for large repetitions or noise").
+        window = int(cfg.min_window_size)
+        while True:
+            res = ops.ctcseg_align(lp, in_len, gt, n_cols, ub, n_utts, cfg.index_duration_in_seconds,
+                                   window=window, **kw)
+            if not bool((res.status & ops.WIN_WINDOW_TOO_SMALL).any()):
+                return cfg, res, n_utts
+            window *= 2
+            if window >= cfg.max_window_size:
+                raise IndexError("Maximum window size reached. Check data for large repetitions or noise.")
 
     @staticmethod
     def _result(task, cfg, res, i, k):

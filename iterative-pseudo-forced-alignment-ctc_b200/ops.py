@@ -26,6 +26,7 @@ SEG_BLANK_COST_ZERO = 1
 SEG_PREAMBLE_COST_ZERO = 2
 SEG_ROUND_NEAREST = 4
 SEG_ALL_PREFIXES = 8
+WIN_WINDOW_TOO_SMALL = 8
 
 
 def launch_count():
@@ -214,7 +215,10 @@ class SegAlignment:
 
 
 def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blank=0, score_len=30,
-                 flags=SEG_PREAMBLE_COST_ZERO, details=True, batch_first=True):
+                 flags=SEG_PREAMBLE_COST_ZERO, details=True, batch_first=True, window=None):
+    """``window``: table rows of ctc-segmentation's windowed mode (``config.min_window_size``).
+    ``None`` = full-table kernels (T <= 8000 frames).  In windowed mode ``status`` carries bit 8
+    (``WIN_WINDOW_TOO_SMALL``) where the reference would raise IndexError and double the window."""
     _need_cuda(lp, "lp")
     lp, n, t, v, sn, st = _lp_strides(lp, batch_first)
     dev = lp.device
@@ -237,6 +241,17 @@ def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blan
     else:
         timing = char_prob = state = None
     L = lib()
+    if window is not None:
+        with torch.cuda.device(dev):
+            ws_bytes = L.ipfa_ctcseg_windowed_workspace_bytes(n, t, cmax, kmax, int(window))
+            ws = _workspace(ws_bytes, dev)
+            rc = L.ipfa_ctcseg_windowed_device(
+                _ptr(lp), None, sn, st, _ptr(in_len), _ptr(gt), gt.stride(0), _ptr(n_cols), _ptr(utt_begin),
+                _ptr(n_utts), n, t, cmax, kmax, v, blank, float(index_duration), int(score_len), int(flags),
+                int(window), _ptr(seg), _ptr(term_t), _ptr(timing), _ptr(char_prob), _ptr(state),
+                _ptr(status), _ptr(ws), ws.numel(), _stream(dev))
+        check(rc, "ipfa_ctcseg_windowed_device")
+        return SegAlignment(seg, term_t, timing, char_prob, state, status)
     with torch.cuda.device(dev):
         ws_bytes = L.ipfa_ctcseg_workspace_bytes(n, t, cmax, kmax, v)
         ws = _workspace(ws_bytes, dev)

@@ -223,3 +223,100 @@ def test_anchor_select_matches_oracle_state_machine(ipfa):
             # rows kept are those of the accepted prefix
             k = dec[w, 0]
             assert [r[5] for r in rows] == [100.0 + float(f"{seg[w, k - 1, u, 1]:.2f}") for u in range(k)]
+
+
+# --------------------------------------------------------------------------- windowed table mode
+def _aligned_case(seed, n, t, v, k_utts, lo, hi):
+    """Peaked windows whose text spans the whole audio (so the table window has to slide)."""
+    return seg_case(seed, n, t, v, k_utts, lo, hi, peaked=True, ragged=False)
+
+
+def test_windowed_mode_equals_full_table_when_the_audio_fits(ipfa):
+    import torch
+    from oracle import ctcseg as oseg
+    cfg = oseg.CtcSegmentationParameters(index_duration=0.02)
+    lp, in_len, utts = seg_case(51, 4, 300, 32, 4, 3, 9)
+    gt, ubs, n_cols, n_utts = _pack(cfg, utts)
+    dev = torch.from_numpy(lp).cuda()
+    full = ipfa.ctcseg_align(dev, in_len, gt, n_cols, ubs, n_utts, cfg.index_duration, flags=cfg.flags | 8)
+    win = ipfa.ctcseg_align(dev, in_len, gt, n_cols, ubs, n_utts, cfg.index_duration, flags=cfg.flags | 8,
+                            window=512)
+    assert int(win.status.sum()) == 0
+    for i in range(4):
+        for k in range(1, int(n_utts[i]) + 1):
+            for name in ("timing", "char_prob", "state"):
+                assert torch.equal(getattr(full, name)[i, k - 1], getattr(win, name)[i, k - 1]), (name, i, k)
+            assert torch.equal(full.seg[i, k - 1, :k], win.seg[i, k - 1, :k]), (i, k)
+            assert int(full.term_t[i, k - 1]) == int(win.term_t[i, k - 1])
+
+
+@pytest.mark.parametrize("t,window,k_utts,lo,hi", [(700, 256, 3, 10, 20), (1000, 300, 5, 8, 16),
+                                                   (2300, 2100, 4, 20, 40)])
+def test_windowed_mode_vs_oracle(ipfa, t, window, k_utts, lo, hi):
+    """T > window: per-column sliding offsets, one fill per prefix; the oracle doubles its window on
+    IndexError exactly where the CUDA path reports WIN_WINDOW_TOO_SMALL."""
+    import torch
+    from oracle import ctcseg as oseg
+    n = 3
+    lp, in_len, utts = _aligned_case(61, n, t, 32, k_utts, lo, hi)
+    gt, ubs, n_cols, n_utts = _pack(oseg.CtcSegmentationParameters(), utts)
+    dev = torch.from_numpy(lp).cuda()
+    to_np = lambda x: x.cpu().numpy()
+    checked = 0
+    for i in range(n):
+        for k in range(1, int(n_utts[i]) + 1):
+            # one (window, prefix) at a time so each one can double its own window like the reference
+            w = window
+            while True:
+                res = ipfa.ctcseg_align(dev[i:i + 1], in_len[i:i + 1], gt[i:i + 1, :ubs[i, k] + 1],
+                                        np.array([ubs[i, k] + 1], np.int32), ubs[i:i + 1, :k + 1],
+                                        np.array([k], np.int32), 0.02, flags=2, window=w)
+                if not int(res.status[0]) & 8:
+                    break
+                w *= 2
+                assert w < 100000
+            cfg = oseg.CtcSegmentationParameters(index_duration=0.02, min_window_size=window)
+            _compare_window(cfg, res, 0, k, lp[i, :in_len[i]], utts[i], to_np)
+            checked += 1
+            # the offsets really moved
+            table, offsets, _, _, _ = oseg.fill_table(cfg, lp[i, :in_len[i]],
+                                                      oseg.prepare_token_list(cfg, utts[i][:k])[0], w)
+            if w < in_len[i] and k == int(n_utts[i]):
+                assert offsets[-1] > 0  # the full text spans the audio: the window had to slide
+    assert checked >= n
+
+
+def test_long_audio_through_the_ctcsegmentation_mirror(cs):
+    """> 8000 frames through CTCSegmentation.get_segments (the reference's default min_window_size)."""
+    import torch
+    from oracle import ctcseg as oseg
+    import importlib
+    stub = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+    rng = np.random.default_rng(5)
+    tok = stub.CharTokenizer()
+    words = "uno dos tres cuatro cinco seis siete ocho nueve diez".split()
+    utts = [" ".join(rng.choice(words, size=6)) for _ in range(8)]
+    t_len = 9000
+    flat = []
+    for u in utts:
+        flat += [0] + tok.encode_as_ids(u)
+    flat += [0]
+    lp = rng.standard_normal((t_len, tok.vocab_size())).astype(np.float32)
+    pos = np.sort(rng.permutation(t_len)[:len(flat)])
+    for j, (a, b) in enumerate(zip(pos, list(pos[1:]) + [t_len])):
+        lp[a:b, flat[j]] += 5.0
+    lp = lp - np.log(np.exp(lp.astype(np.float64)).sum(-1, keepdims=True)).astype(np.float32)
+    asr = stub.StubEncoderASR(device="cuda")
+    aligner = cs.CTCSegmentation(asr, kaldi_style_text=False, time_stamps="fixed", scoring_length=30)
+    aligner.samples_to_frames_ratio = 320.0
+    task = aligner.prepare_segmentation_task(utts, torch.from_numpy(lp).cuda(), "long", t_len * 320)
+    got = cs.CTCSegmentation.get_segments(task)
+    cfg = oseg.CtcSegmentationParameters(index_duration=task.config.index_duration,
+                                         score_min_mean_over_L=30, char_list=task.config.char_list)
+    ref = oseg.get_segments(cfg, lp, task.ground_truth_mat, task.utt_begin_indices, task.text)
+    assert np.array_equal(got["timings"], ref["timings"])
+    assert np.array_equal(got["char_probs"], ref["char_probs"])
+    assert got["state_list"] == ref["state_list"]
+    for a, b in zip(got["segments"], ref["segments"]):
+        assert a[0] == b[0] and a[1] == b[1]
+        np.testing.assert_allclose(a[2], b[2], rtol=1e-12)
