@@ -46,6 +46,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the workload's dominant kernel from the committed `ncu --set full`
+    capture (profiles/traffic_r01.json, written by tools/summarize_ncu.py); None when absent."""
+    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(workload, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
@@ -686,7 +697,8 @@ def gpu_arm(args):
                             "sharding": "independent windows per rank, no collective on the data path"}, **wl.shape),
             "cells_per_s": world * cells / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(args.workload),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
                          "kernels_per_step": launches / max(args.steps, 1), "note": bound_note},
             "cpu_baseline": cpu_baseline_obj(legs, "same shapes, same generator"),

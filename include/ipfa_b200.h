@@ -219,14 +219,19 @@ int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_off, int64_t 
  *   window       table rows (config.min_window_size, doubled by the caller after
  *                IPFA_WIN_WINDOW_TOO_SMALL up to config.max_window_size)
  *   term_t_out   terminal ROW inside the last column's window
- * For T <= window the result equals ipfa_ctcseg_device's.
+ *   gt_cols      columns of the ground truth matrix: 1 for the tokenised text of the three entry
+ *                points; G > 1 for ctc-segmentation's `classic` text converter (prepare_text), where
+ *                gt is [N][Cmax][G], gt[c][s] = token spanning the last s+1 characters or -1, and
+ *                state_out holds column | (s << 24) at the frames where a token was entered.
+ *                window >= Tmax makes this the full-table algorithm for such tasks.
+ * For T <= window and gt_cols == 1 the result equals ipfa_ctcseg_device's.
  * ------------------------------------------------------------------------- */
-size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window);
+size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window, int gt_cols);
 int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_off, int64_t stride_n, int64_t stride_t,
                                 const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
                                 const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,
                                 int N, int Tmax, int Cmax, int Kmax, int V, int blank,
-                                double index_duration, int score_len, int flags, int window,
+                                double index_duration, int score_len, int flags, int window, int gt_cols,
                                 double *seg_out, int32_t *term_t_out, int32_t *timing_out,
                                 float *char_prob_out, int32_t *state_out, int32_t *status_out,
                                 void *workspace, size_t workspace_bytes, void *stream);

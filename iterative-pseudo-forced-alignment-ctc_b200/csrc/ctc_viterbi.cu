@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     constexpr int NT = 32 * WARPS;
-    constexpr int SPW = 8 / P;  // frames per backpointer word
     constexpr float NEG = -__builtin_huge_valf();
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -135,28 +134,44 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     float ab[P], al[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) { ab[p] = NEG; al[p] = NEG; }
-    uint32_t word = 0;
-    int shift = 0;  // bit position of the current frame inside `word`
+    // Backpointers as bit planes, one 32-bit word per state and 32-frame block: bit f of
+    //   mvb[p]  "the blank state of pair p was ENTERED from the label below (s-1) at frame f"
+    //   mvl[p]  "the label state of pair p was entered from its blank (s-1) at frame f"
+    //   by2[p]  "the label state of pair p was entered by the skip transition (s-2) at frame f"
+    // so the backtrace can hop from move to move with mask + find-leading-one instead of
+    // stepping frames, and a decision costs one predicated OR.  3P words per thread and block
+    // (1.5 bits per state and frame), stored plane by plane: every warp store is 128 contiguous bytes.
+    // (ptxas 12.9 segfaults on the widest instance, 8 pairs x 32 warps, unless its label plane also
+    // carries the skip moves; the backtrace ORs the two planes, so both encodings read the same.)
+    constexpr bool kMergedPlanes = (P == 8 && WARPS == 32);
+    uint32_t mvb[P], mvl[P], by2[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) { mvb[p] = 0; mvl[p] = 0; by2[p] = 0; }
+    uint32_t bit = 1;  // 1 << (t & 31)
     uint32_t *bp_ptr = prm.bp + (int64_t)w * prm.words_per_window + tid;
-
-    auto push_bits = [&](uint32_t bits) {
-        word |= bits << shift;
-        shift += 4 * P;
-        if (shift == 32) {
-            *bp_ptr = word;
-            bp_ptr += NT;
-            word = 0;
-            shift = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            bp_ptr[(3 * p + 0) * NT] = mvb[p];
+            bp_ptr[(3 * p + 1) * NT] = mvl[p];
+            bp_ptr[(3 * p + 2) * NT] = by2[p];
+            mvb[p] = 0; mvl[p] = 0; by2[p] = 0;
         }
+        bp_ptr += 3 * P * NT;
+    };
+    auto next_frame = [&]() {
+        bit <<= 1;
+        if (bit == 0) { flush(); bit = 1; }
     };
 
-    // One frame.  `sh` = bit position of this frame inside the backpointer word: a compile-time
-    // constant after unrolling, so every decision predicate becomes one SEL of a constant.
-    auto frame = [&](const float *row, const float *rd, float *wr, const int sh) -> uint32_t {
-        const float eb = row[colb];
+    // One frame, `off` floats past the column cursors.
+    const float *pb = nullptr;
+    const float *pl[P];
+    auto frame = [&](const int off, const float *rd, float *wr) {
+        const float eb = pb[off];
         float el[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) el[p] = row[col[p]];
+        for (int p = 0; p < P; ++p) el[p] = pl[p][off];
         float prev;
         if constexpr (WARPS > 1) {
             prev = rd[tid];
@@ -164,7 +179,6 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
             prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
             if (tid == 0) prev = NEG;
         }
-        uint32_t bits = 0;
 #pragma unroll
         for (int p = P - 1; p >= 0; --p) {
             const float lm1 = (p == 0) ? prev : al[p - 1];
@@ -181,14 +195,20 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
             const float nb = (takeb ? lm1 : ab[p]) + eb;
             al[p] = res + el[p];
             ab[p] = nb;
-            bits |= (takeb ? (1u << (sh + 4 * p)) : 0u) | (take1 ? (1u << (sh + 4 * p + 2)) : 0u) |
-                    (take2 ? (1u << (sh + 4 * p + 3)) : 0u);
+                    mvb[p] |= takeb ? bit : 0u;
+            mvl[p] |= (take1 || (kMergedPlanes && take2)) ? bit : 0u;
+            by2[p] |= take2 ? bit : 0u;
         }
         if constexpr (WARPS > 1) {
             wr[tid + 1] = al[P - 1];
             __syncthreads();
         }
-        return bits;
+        next_frame();
+    };
+    auto bump = [&](const int frames) {
+        pb += frames * pitch;
+#pragma unroll
+        for (int p = 0; p < P; ++p) pl[p] += frames * pitch;
     };
 
     float *line0 = xline, *line1 = xline + NT + 1;
@@ -204,35 +224,33 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
                 ab[0] = panel[colb];
                 if (L > 0) al[0] = panel[col[0]];
             }
-            push_bits(0);
+            next_frame();  // frame 0 has no incoming transition
             if constexpr (WARPS > 1) {
                 line0[tid + 1] = al[P - 1];
                 __syncthreads();
             }
             r = 1;
         }
-        const float *row = panel + r * pitch;
         // frame t reads line[(t-1)&1], writes line[t&1]; tc is even so r has t's parity
-        while (r < rows) {
-            if (SPW > 1 && shift == 0 && !(r & 1) && r + SPW <= rows) {
-                // a whole backpointer word: SPW frames with compile-time shifts and line parity
-                uint32_t acc = 0;
+        pb = panel + r * pitch + colb;
 #pragma unroll
-                for (int f = 0; f < SPW; ++f) {
-                    acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0, f * 4 * P);
-                }
-                *bp_ptr = acc;
-                bp_ptr += NT;
-                row += SPW * pitch;
-                r += SPW;
-            } else {
-                push_bits((r & 1) ? frame(row, line0, line1, 0) : frame(row, line1, line0, 0));
-                row += pitch;
-                ++r;
-            }
+        for (int p = 0; p < P; ++p) pl[p] = panel + r * pitch + col[p];
+        if ((r & 1) && r < rows) { frame(0, line0, line1); bump(1); ++r; }
+        for (; r + 3 < rows; r += 4) {
+            frame(0, line1, line0);
+            frame(pitch, line0, line1);
+            frame(2 * pitch, line1, line0);
+            frame(3 * pitch, line0, line1);
+            bump(4);
         }
+        for (; r + 1 < rows; r += 2) {
+            frame(0, line1, line0);
+            frame(pitch, line0, line1);
+            bump(2);
+        }
+        if (r < rows) frame(0, line1, line0);
     }
-    if (shift != 0) *bp_ptr = word;
+    if (bit != 1) flush();
 
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -272,19 +290,23 @@ struct BacktraceParams {
     float *tok_score;
 };
 
-// One warp per window.  Per 32-frame block the warp stages every backpointer word the walk can
-// reach (63 states -> NCW thread-columns x NW word-rows, <= 160 words) in shared memory with
-// coalesced loads, then walks the block with one LDS per frame and NO branch on the serial
-// chain.  The targets sit in shared memory; the per-frame score gather of block b is issued
-// before, and stored after, the staging loads of block b-1, so each block exposes one memory
-// latency.  Token spans are derived lane-parallel from neighbouring frames' states.
+// One warp per window.  The backpointers are bit planes (one word per state and 32-frame block,
+// bit f = "entered from a lower state at frame f"), so the walk hops from move to move:
+// "the next move at or below frame t" is word & below-mask + find-leading-one -- about 2L+1 steps
+// per window instead of T.  Per block the planes of the thread-columns the walk can reach are
+// staged in shared memory; the words of block b-1 are requested before block b is walked (a
+// superset wide enough for wherever the walk ends up), and the per-frame score gather of a block
+// is issued before the next block's walk and stored after it, so no memory latency sits on the
+// chain.  Lane = frame for the outputs: state at frame t = state at the block's top minus the
+// moves above t (two popcounts).  Token spans come lane-parallel from neighbouring frames' states.
 template <int P>
 __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const BacktraceParams prm) {
-    constexpr unsigned SPW = 8 / P;            // frames per word
-    constexpr int NW = 32 / SPW;               // word-rows per 32-frame block (= 4P)
     constexpr int SPT = 2 * P;                 // states per thread-column
-    constexpr int NCW = 62 / SPT + 2;          // thread-columns reachable inside one block
-    constexpr int NWORDS = NCW * NW;
+    constexpr int NPL = 3 * P;                 // planes per thread-column
+    constexpr int NTH = 64 / SPT + 2;          // thread-columns reachable inside one block (<= 64 states)
+    constexpr int NTH2 = NTH + 64 / SPT + 1;   // ... plus wherever the block below may start
+    constexpr int NWORDS = NTH2 * NPL;
+    constexpr int LOG2SPT = (P == 1) ? 1 : (P == 2) ? 2 : (P == 4) ? 3 : 4;
     extern __shared__ __align__(16) unsigned char bt_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -323,62 +345,73 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
 
     const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
     const int NT = prm.NT;
+    constexpr int NQ = (NWORDS + 31) / 32;
+    uint32_t v[NQ];
+    auto request = [&](int blk, int c_base) {  // planes of thread-columns c_base - [0, NTH2) of block blk
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            const int q = lane + 32 * u;
+            const int plane = q / NTH2, crel = q - plane * NTH2;
+            const int col = c_base - crel;
+            v[u] = 0;
+            if (q < NWORDS && col >= 0) v[u] = __ldg(bp_w + ((int64_t)blk * NPL + plane) * NT + col);
+        }
+    };
     int s_above = -1;  // state of frame t_hi + 1 (none above the last frame)
     // outputs of the previous (higher) block, stored one iteration late
     int pend_t = -1, pend_lab = 0;
     float pend_sc = 0.0f;
+    int c_base = s >> LOG2SPT;
+    request((T - 1) >> 5, c_base);
 
     for (int blk = (T - 1) >> 5; blk >= 0; --blk) {
-        const unsigned t_hi = min(T - 1, blk * 32 + 31);
-        const unsigned t_lo = blk * 32;
-        const int c_hi = s / SPT;  // thread-column of the state at t_hi
+        const int t_hi = min(T - 1, blk * 32 + 31);
+        const int t_lo = blk * 32;
         __syncwarp();
-        {   // every global load of this iteration is issued here, back to back: the staging words
-            // of block b and the score gather of block b+1 (whose states were found last
-            // iteration).  __syncwarp waits for outstanding loads, so none may be in flight at
-            // the loop-top barrier; this way the block exposes ONE memory latency.
-            constexpr int NQ = (NWORDS + 31) / 32;
-            uint32_t v[NQ];
 #pragma unroll
-            for (int u = 0; u < NQ; ++u) {
-                const int q = lane + 32 * u;
-                const int row = q / NCW, crel = q - row * NCW;
-                const int col = c_hi - crel;
-                const int wrow = blk * NW + row;
-                v[u] = 0;
-                if (q < NWORDS && col >= 0 && wrow * (int)SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
-            }
-            if (pend_t >= 0 && scores) pend_sc = lp[(int64_t)pend_t * prm.stride_t + pend_lab];
-#pragma unroll
-            for (int u = 0; u < NQ; ++u) {
-                const int q = lane + 32 * u;
-                if (q < NWORDS) raw[q] = v[u];
-            }
+        for (int u = 0; u < NQ; ++u) {
+            const int q = lane + 32 * u;
+            if (q < NWORDS) raw[q] = v[u];
         }
         __syncwarp();
+        const int c_cur = c_base;
+        c_base = s >> LOG2SPT;
+        if (blk > 0) request(blk - 1, c_base);  // in flight during this block's walk
+        if (pend_t >= 0 && scores) pend_sc = lp[(int64_t)pend_t * prm.stride_t + pend_lab];
+        // moves of this block as two 32-bit masks (bit = frame - t_lo)
+        uint32_t S_mv = 0, S_b2 = 0;
+        const int s_top = s;
+        {
+            // frame 0 has no incoming transition
+            uint32_t below = ((2u << (t_hi - t_lo)) - 1u) & ((blk == 0) ? ~1u : 0xffffffffu);
+            while (below) {
+                const int col = s >> LOG2SPT, k = s & (SPT - 1);
+                const uint32_t *wp = raw + (3 * (k >> 1) + (k & 1)) * NTH2 + (c_cur - col);
+                const uint32_t b2 = (k & 1) ? wp[NTH2] : 0u;  // label: the by-two plane follows
+                const uint32_t m = (wp[0] | b2) & below;
+                if (m == 0) break;                  // stays down to the first frame of the block
+                const int f = 31 - __clz(m);        // the state was entered at this frame
+                const uint32_t two = (b2 >> f) & 1u;
+                S_mv |= 1u << f;
+                S_b2 |= two << f;
+                s = max(s - 1 - (int)two, 0);
+                below &= (1u << f) - 1u;
+            }
+        }
         if (pend_t >= 0) {
             paths[pend_t] = pend_lab;
             if (scores) scores[pend_t] = pend_sc;
         }
-        int my_state = 0;
-        const unsigned t_stop = max(t_lo, 1u);
-        for (unsigned t = t_hi; t >= t_stop; --t) {
-            my_state = ((unsigned)lane == (t & 31u)) ? s : my_state;
-            const int col = s / SPT, k = s & (SPT - 1);
-            const unsigned row = (t / SPW) - blk * NW;
-            const uint32_t word = raw[row * NCW + (c_hi - col)];
-            s = max(s - (int)((word >> ((t % SPW) * 4 * P + 2 * k)) & 3), 0);
-        }
-        if (t_lo == 0 && lane == 0) my_state = s;  // frame 0 has no incoming transition
-        const int s_below = s;                      // state of frame t_lo - 1 (blk > 0)
-        const int t = (int)t_lo + lane;
+        const int s_below = s;  // state of frame t_lo - 1 (blk > 0)
+        const int t = t_lo + lane;
+        const int my_state = s_top - __popc((S_mv >> lane) >> 1) - __popc((S_b2 >> lane) >> 1);
         // neighbours' states for the token spans
         int st_up = __shfl_down_sync(0xffffffffu, my_state, 1);
         int st_dn = __shfl_up_sync(0xffffffffu, my_state, 1);
-        if (t == (int)t_hi) st_up = s_above;
+        if (t == t_hi) st_up = s_above;
         if (lane == 0) st_dn = (t_lo == 0) ? -1 : s_below;
         pend_t = -1;
-        if (t <= (int)t_hi) {
+        if (t <= t_hi) {
             const int lab = (my_state & 1) ? tg_s[my_state >> 1] : prm.blank;
             pend_t = t;
             pend_lab = lab;
@@ -409,8 +442,8 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
 
 // ---------------------------------------------------------------------------
 static int64_t viterbi_words_per_window(int Tmax, LatticeShape s) {
-    const int spw = 8 / s.PER;
-    return (int64_t)((Tmax + spw - 1) / spw) * 32 * s.WARPS;
+    // per 32-frame block and thread: 2 "moved" planes + 1 "by two" plane per state pair
+    return (int64_t)((Tmax + 31) / 32) * 3 * s.PER * 32 * s.WARPS;
 }
 
 template <int P, int WARPS, bool DENSE, int PITCH>
@@ -459,7 +492,7 @@ static int dispatch_fill(const ViterbiParams &prm, int Lmax, LatticeShape s, cud
 
 template <int P>
 static int launch_backtrace_p(const BacktraceParams &prm, cudaStream_t stream) {
-    constexpr int NWORDS = (62 / (2 * P) + 2) * (4 * P);
+    constexpr int NWORDS = (64 / (2 * P) + 2 + 64 / (2 * P) + 1) * (3 * P);
     const size_t smem = (size_t)4 * (NWORDS + prm.Lmax) * sizeof(uint32_t);
     auto kern = ctc_viterbi_backtrace_kernel<P>;
     if (smem > 48 * 1024) {

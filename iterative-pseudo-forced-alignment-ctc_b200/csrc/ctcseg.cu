@@ -821,6 +821,260 @@ __global__ void __launch_bounds__(128) ctcseg_windowed_backtrace_kernel(const Se
 }
 
 // ---------------------------------------------------------------------------
+// Multi-column ground truth: ctc-segmentation's `classic` text
+// converter gives every character position up to G candidate tokens, the s-th spanning the last
+// s+1 characters, so a cell has up to G switch transitions (from columns c-1-s).  Same
+// column-serial scheme as the windowed kernels above (it IS the general form of the algorithm:
+// window = T gives the full table); G+1 table columns are kept, and the reference's backtrace
+// test -- argmin_s |switch_prob_s - est_switch_s| against |stay_prob - est_stay| -- is stored as one
+// byte per cell: 0 stay, 1 + min_s switch, 255 "a read beyond the window" (IndexError there).
+constexpr int kMaxGtCols = 32;
+
+struct SegMultiParams {
+    SegWinParams w;      // gt is [N][Cmax][G] here (gt_stride elements per window)
+    int G;
+    float *ring;         // [problems][G + 1][window] last G + 1 table columns
+    uint8_t *codes;      // [problems][Cmax][window]
+};
+
+__global__ void __launch_bounds__(kWinThreads) ctcseg_multi_fill_kernel(const SegMultiParams mp) {
+    const SegWinParams &prm = mp.w;
+    const int G = mp.G;
+    const int prob = blockIdx.x;
+    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int K = max(0, min(prm.n_utts[w], prm.Kmax));
+    const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
+    const int NC = min(ub[kslot + 1] + 1, min(prm.n_cols[w], prm.Cmax));
+    if (T <= 0 || NC <= 1 || NC > T) return;
+    const int W = min(prm.window, T);
+    const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
+    const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
+    float *ring = mp.ring + (int64_t)prob * (G + 1) * prm.window;
+    uint8_t *codes = mp.codes + (int64_t)prob * prm.Cmax * prm.window;
+    int32_t *offs = prm.offsets + (int64_t)prob * prm.Cmax;
+    const bool blank_cost_zero = prm.flags & IPFA_SEG_BLANK_COST_ZERO;
+    const bool preamble_cost_zero = prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO;
+    const int tid = threadIdx.x;
+
+    __shared__ float s_sw[kWinTile], s_e[kWinTile], s_mx[kWinTile], s_x[kWinTile + 1];
+    __shared__ int s_off, s_offsum, s_arg, s_curoff[kMaxGtCols], s_g[kMaxGtCols];
+    __shared__ float s_max, s_carry;
+
+    const float mean_offset = (float)(T - W) / (float)NC;
+    const int higher_offset = (int)ceilf(mean_offset);
+    if (tid == 0) {
+        s_off = 0; s_offsum = 0; s_arg = -1; s_max = 0.0f;
+        for (int s = 0; s < G; ++s) s_curoff[s] = -1;  // np.zeros(G) - 1
+    }
+    __syncthreads();
+
+    for (int c = 0; c < NC; ++c) {
+        if (tid == 0) {
+            if (c > 0) {
+                const int lim = (T - W) - s_offsum;
+                const int hi = min(higher_offset, lim);
+                const int lo = max(s_arg - W / 2, 0);
+                const int offset = min(lo, hi);
+                for (int s = G - 2; s >= 0; --s) s_curoff[s + 1] = s_curoff[s] + offset;
+                s_curoff[0] = offset;
+                s_off = offset;
+                s_offsum += offset;
+            }
+            offs[c] = s_offsum;
+            s_arg = -1;
+            s_max = 0.0f;
+            for (int s = 0; s < G; ++s) {
+                int g = gt[(int64_t)c * G + s];
+                if (g >= prm.V) g = -1;
+                s_g[s] = g;
+            }
+        }
+        __syncthreads();
+        const int offset_sum = s_offsum;
+        float *cur = ring + (int64_t)(c % (G + 1)) * prm.window;
+        uint8_t *codes_c = codes + (int64_t)c * prm.window;
+        for (int t0 = 0; t0 < W; t0 += kWinTile) {
+            const int rows = min(kWinTile, W - t0);
+            for (int r = tid; r < rows; r += kWinThreads) {
+                const int t = t0 + r;
+                const float *row = lp + (int64_t)(t + offset_sum) * prm.stride_t;
+                const float eb = row[prm.blank];
+                float sw = kProbMax, mx = kProbMax;
+                for (int s = 0; s < G; ++s) {
+                    const int g = s_g[s];
+                    if (g < 0) continue;
+                    const float e = row[g];
+                    const int tp = t - 1 + s_curoff[s];
+                    float p = kProbMax;
+                    if (!(tp >= W || tp < 0 || t - 1 < 0 || c - (s + 1) < 0))
+                        p = ring[(int64_t)((c - 1 - s) % (G + 1)) * prm.window + tp] + e;
+                    sw = fmaxf(sw, p);
+                    mx = fmaxf(mx, e);
+                }
+                s_sw[r] = sw;
+                s_mx[r] = mx;
+                s_e[r] = (c == 0) ? eb : (blank_cost_zero ? 0.0f : fmaxf(eb, mx));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float x = (t0 == 0) ? 0.0f : s_carry;
+                float best = s_max;
+                int arg = s_arg;
+                int r = 0;
+                if (t0 == 0) {
+                    if (c == 0) {
+                        x = 0.0f;
+                    } else {
+                        x = kProbMax;
+                        arg = 0; best = x;
+                    }
+                    s_x[1] = x;
+                    r = 1;
+                }
+                for (; r < rows; ++r) {
+                    const float stay = (c == 0 && preamble_cost_zero) ? 0.0f : x + s_e[r];
+                    x = fmaxf(s_sw[r], stay);
+                    s_x[r + 1] = x;
+                    if (arg == -1 || best < x) { best = x; arg = t0 + r; }
+                }
+                s_x[0] = (t0 == 0) ? 0.0f : s_carry;
+                s_carry = x;
+                s_max = best;
+                s_arg = arg;
+            }
+            __syncthreads();
+            for (int r = tid; r < rows; r += kWinThreads) {
+                const int t = t0 + r;
+                const float x = s_x[r + 1];
+                cur[t] = x;
+                uint8_t code = 0;
+                if (c > 0 && t > 0) {
+                    const float *row = lp + (int64_t)(t + offset_sum) * prm.stride_t;
+                    float min_delta = __int_as_float(0x7f800000);
+                    int min_s = -1;
+                    float max_lpz = -10000000000.0f;  // config.max_prob
+                    bool oob = false;
+                    for (int s = 0; s < G; ++s) {
+                        const int g = s_g[s];
+                        if (g < 0 || c - (s + 1) < 0) continue;  // (a token reaching before column 0 cannot exist)
+                        const int tp = t - 1 + s_curoff[s];
+                        if (tp >= W) { oob = true; break; }
+                        const float switch_prob = row[g];
+                        const float est = x - ring[(int64_t)((c - 1 - s) % (G + 1)) * prm.window + tp];
+                        const float d = fabsf(switch_prob - est);
+                        if (d < min_delta) { min_delta = d; min_s = s; }
+                        max_lpz = fmaxf(max_lpz, switch_prob);
+                    }
+                    if (oob) {
+                        code = 255;
+                    } else {
+                        const float stay_prob = fmaxf(row[prm.blank], max_lpz);
+                        const float est_stay = x - s_x[r];
+                        if (fabsf(stay_prob - est_stay) > min_delta) code = (uint8_t)(1 + min_s);
+                    }
+                }
+                codes_c[t] = code;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) prm.term[prob] = s_arg;
+}
+
+__global__ void __launch_bounds__(128) ctcseg_multi_backtrace_kernel(const SegMultiParams mp) {
+    const SegWinParams &prm = mp.w;
+    const int G = mp.G;
+    const int lane = threadIdx.x & 31;
+    const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (prob >= prm.N * prm.Kmax) return;
+    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int K = max(0, min(prm.n_utts[w], prm.Kmax));
+    const int T = min(prm.in_len[w], prm.Tmax);
+    const int NCw = max(0, min(prm.n_cols[w], prm.Cmax));
+    const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+    if (kslot == 0 && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
+    const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
+    const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
+    const int64_t slot = (int64_t)w * prm.Kmax + kslot;
+    int32_t *timing = prm.timing + slot * prm.Cmax;
+    float *cprob = prm.char_prob + slot * prm.Tmax;
+    int32_t *state = prm.state_out ? prm.state_out + slot * prm.Tmax : nullptr;
+    double *seg = prm.seg_out + slot * prm.Kmax * 3;
+    const int NC = min(ub[kslot + 1] + 1, NCw);
+    for (int t = lane; t < prm.Tmax; t += 32) {
+        cprob[t] = 0.0f;
+        if (state) state[t] = -2;
+    }
+    for (int c = lane; c < prm.Cmax; c += 32) timing[c] = -1;
+    const bool feasible = T > 0 && NC > 1 && NC <= T;
+    const int t_term = feasible ? prm.term[prob] : -1;
+    if (lane == 0) prm.term_t_out[slot] = t_term;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (!feasible || t_term < 0) {
+        for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+        return;
+    }
+    __syncwarp();
+    const uint8_t *codes = mp.codes + (int64_t)prob * prm.Cmax * prm.window;
+    const int32_t *offs = prm.offsets + (int64_t)prob * prm.Cmax;
+    bool too_small = false;
+    if (lane == 0) {
+        int t = t_term, c = NC - 1;
+        while (t != 0 || c != 0) {
+            if (t == 0 || c < 0) { too_small = true; break; }  // row 0 of a later column is unreachable
+            const int oc = offs[c];
+            const float *row = lp + (int64_t)(t + oc) * prm.stride_t;
+            const float eb = row[prm.blank];
+            if (c == 0) {
+                cprob[oc + t] = eb;
+                if (state) state[oc + t] = -1;
+                --t;
+                continue;
+            }
+            const uint8_t code = codes[(int64_t)c * prm.window + t];
+            if (code == 255) { too_small = true; break; }
+            // max_lpz_prob and the `offset` the reference's loop leaves behind (that of the LAST
+            // candidate it looked at, not of the chosen one)
+            float max_lpz = -10000000000.0f;
+            int offset = 0;
+            for (int s = 0; s < G; ++s) {
+                int g = gt[(int64_t)c * G + s];
+                if (g < 0 || g >= prm.V || c - (s + 1) < 0) continue;
+                max_lpz = fmaxf(max_lpz, row[g]);
+                offset = oc - offs[c - 1 - s];
+            }
+            if (code > 0) {
+                const int min_s = code - 1;
+                for (int s = 0; s <= min_s; ++s) timing[c - s] = oc + t;
+                cprob[oc + t] = max_lpz;
+                if (state) state[oc + t] = c | (min_s << 24);
+                c -= 1 + min_s;
+                t -= 1 - offset;
+            } else {
+                cprob[oc + t] = fmaxf(eb, max_lpz);
+                if (state) state[oc + t] = -1;
+                --t;
+            }
+        }
+    }
+    too_small = __shfl_sync(0xffffffffu, too_small, 0);
+    __syncwarp();
+    __threadfence_block();
+    if (too_small) {
+        if (lane == 0) atomicOr(prm.status_out + w, IPFA_WIN_WINDOW_TOO_SMALL);
+        for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+        return;
+    }
+    score_segments(ub, timing, cprob, kslot + 1, T, prm.Cmax, prm.index_duration, prm.score_len,
+                   (prm.flags & IPFA_SEG_ROUND_NEAREST) != 0, lane, seg);
+}
+
+// ---------------------------------------------------------------------------
 using SegShape = LatticeShape;
 static bool pick_seg_shape(int cols, int n_windows, int V, SegShape *s) {
     return pick_lattice_shape(cols, n_windows, s, "IPFA_SEG_SHAPE", use_dense_panel(V, cols) ? 3 : 6, true);
@@ -996,12 +1250,14 @@ extern "C" int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_of
 // windowed table mode
 static size_t win_words(int window) { return (size_t)((window + 31) / 32); }
 
-extern "C" size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window) {
-    if (N <= 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || window <= 0) return 256;
+extern "C" size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window,
+                                                       int gt_cols) {
+    if (N <= 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || window <= 0 || gt_cols <= 0) return 256;
     const size_t P = (size_t)N * Kmax;
     const size_t W = (size_t)(window < Tmax ? window : Tmax);
-    size_t b = pad256(P * 2 * W * 4);                   // previous / current column
-    b += pad256(P * (size_t)Cmax * win_words((int)W) * 4);  // 1-bit transitions
+    size_t b = pad256(P * ((size_t)gt_cols + 1) * W * 4);  // the last gt_cols + 1 table columns
+    b += (gt_cols == 1) ? pad256(P * (size_t)Cmax * win_words((int)W) * 4)   // 1-bit transitions
+                        : pad256(P * (size_t)Cmax * W);                      // 1-byte transitions
     b += pad256(P * (size_t)Cmax * 4);                  // offsets
     b += pad256(P * 4);                                 // terminal rows
     b += pad256(P * (size_t)Cmax * 4);                  // timing scratch
@@ -1014,16 +1270,17 @@ extern "C" int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_o
                                            int64_t gt_stride, const int32_t *n_cols, const int32_t *utt_begin,
                                            const int32_t *n_utts, int N, int Tmax, int Cmax, int Kmax, int V,
                                            int blank, double index_duration, int score_len, int flags,
-                                           int window, double *seg_out, int32_t *term_t_out,
+                                           int window, int gt_cols, double *seg_out, int32_t *term_t_out,
                                            int32_t *timing_out, float *char_prob_out, int32_t *state_out,
                                            int32_t *status_out, void *workspace, size_t workspace_bytes,
                                            void *stream) {
     if (N == 0) return IPFA_OK;
     if (!lp || !in_len || !gt || !n_cols || !utt_begin || !n_utts || !seg_out || !term_t_out ||
         !status_out || !workspace || N < 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || V <= 0 || blank < 0 ||
-        blank >= V || score_len <= 0 || !(index_duration > 0.0) || window <= 0)
+        blank >= V || score_len <= 0 || !(index_duration > 0.0) || window <= 0 || gt_cols <= 0)
         return IPFA_ERR_INVALID_ARG;
-    if (workspace_bytes < ipfa_ctcseg_windowed_workspace_bytes(N, Tmax, Cmax, Kmax, window))
+    if (gt_cols > kMaxGtCols) return IPFA_ERR_UNSUPPORTED;
+    if (workspace_bytes < ipfa_ctcseg_windowed_workspace_bytes(N, Tmax, Cmax, Kmax, window, gt_cols))
         return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t P = (size_t)N * Kmax;
@@ -1035,8 +1292,9 @@ extern "C" int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_o
     p.N = N; p.Tmax = Tmax; p.Cmax = Cmax; p.Kmax = Kmax; p.V = V; p.blank = blank; p.flags = flags;
     p.window = W; p.score_len = score_len; p.index_duration = index_duration;
     p.words = (int64_t)win_words(W);
-    p.cols2 = reinterpret_cast<float *>(ws);            ws += pad256(P * 2 * (size_t)W * 4);
-    p.bits = reinterpret_cast<uint32_t *>(ws);          ws += pad256(P * (size_t)Cmax * win_words(W) * 4);
+    p.cols2 = reinterpret_cast<float *>(ws);            ws += pad256(P * ((size_t)gt_cols + 1) * (size_t)W * 4);
+    p.bits = reinterpret_cast<uint32_t *>(ws);
+    ws += (gt_cols == 1) ? pad256(P * (size_t)Cmax * win_words(W) * 4) : pad256(P * (size_t)Cmax * (size_t)W);
     p.offsets = reinterpret_cast<int32_t *>(ws);        ws += pad256(P * (size_t)Cmax * 4);
     p.term = reinterpret_cast<int32_t *>(ws);           ws += pad256(P * 4);
     int32_t *timing_scratch = reinterpret_cast<int32_t *>(ws); ws += pad256(P * (size_t)Cmax * 4);
@@ -1045,10 +1303,22 @@ extern "C" int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_o
     p.timing = timing_out ? timing_out : timing_scratch;
     p.char_prob = char_prob_out ? char_prob_out : cprob_scratch;
     p.state_out = state_out; p.status_out = status_out;
-    ctcseg_windowed_fill_kernel<<<(unsigned)P, kWinThreads, 0, st>>>(p);
-    ++g_launch_count;
-    ctcseg_windowed_backtrace_kernel<<<(unsigned)((P + 3) / 4), 128, 0, st>>>(p);
-    ++g_launch_count;
+    if (gt_cols == 1) {
+        ctcseg_windowed_fill_kernel<<<(unsigned)P, kWinThreads, 0, st>>>(p);
+        ++g_launch_count;
+        ctcseg_windowed_backtrace_kernel<<<(unsigned)((P + 3) / 4), 128, 0, st>>>(p);
+        ++g_launch_count;
+    } else {
+        SegMultiParams mp{};
+        mp.w = p;
+        mp.G = gt_cols;
+        mp.ring = p.cols2;
+        mp.codes = reinterpret_cast<uint8_t *>(p.bits);
+        ctcseg_multi_fill_kernel<<<(unsigned)P, kWinThreads, 0, st>>>(mp);
+        ++g_launch_count;
+        ctcseg_multi_backtrace_kernel<<<(unsigned)((P + 3) / 4), 128, 0, st>>>(mp);
+        ++g_launch_count;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;

@@ -87,6 +87,42 @@ def prepare_token_list(config, text):
     return ground_truth_mat, utt_begin_indices
 
 
+def prepare_text(config, text, char_list=None):
+    """The ``classic`` text converter (ctc_segmentation.prepare_text):
+    the ground truth is the character string ``#·utt0·utt1·...·``; row i of ``ground_truth_mat``
+    holds, in column s, the token that spells the last s+1 characters ending at i (or -1), so a
+    multi-character token is one transition that skips s columns."""
+    if char_list is not None:
+        config.char_list = char_list
+    blank = config.char_list[config.blank]
+    ground_truth = config.start_of_ground_truth
+    utt_begin_indices = []
+    for utt in text:
+        if not ground_truth.endswith(config.space):
+            ground_truth += config.space
+        utt_begin_indices.append(len(ground_truth) - 1)
+        for char in utt:
+            if char.isspace() and config.replace_spaces_with_blanks:
+                if not ground_truth.endswith(config.space):
+                    ground_truth += config.space
+            elif char in config.char_list and char not in config.excluded_characters:
+                ground_truth += char
+    if not ground_truth.endswith(config.space):
+        ground_truth += config.space
+    utt_begin_indices.append(len(ground_truth) - 1)
+    max_char_len = max(len(c) for c in config.char_list)
+    index = {c: i for i, c in reversed(list(enumerate(config.char_list)))}  # list.index: first match
+    ground_truth_mat = np.ones([len(ground_truth), max_char_len], np.int64) * -1
+    for i in range(len(ground_truth)):
+        for s in range(max_char_len):
+            if i - s < 0:
+                continue
+            span = ground_truth[i - s:i + 1].replace(config.space, blank)
+            if span in index:
+                ground_truth_mat[i, s] = index[span]
+    return ground_truth_mat, utt_begin_indices
+
+
 class CTCSegmentationTask:
     """Task object for CTC segmentation (speechbrain CTCSegmentationTask)."""
 
@@ -275,8 +311,10 @@ class CTCSegmentation:
             token_list = [utt[utt != unk] if utt.size else utt for utt in token_list]
             ground_truth_mat, utt_begin_indices = prepare_token_list(config, token_list)
         else:
-            raise NotImplementedError("text_converter='classic' (multi-column ground truth) is not on "
-                                      "the accelerated path; see DESIGN.md (SURVEY.md section 8(f) rank 4)")
+            assert self.text_converter == "classic"
+            text_pieces = ["".join(self._tokenizer.encode_as_pieces(utt)) for utt in text]
+            text_pieces = [utt.replace("<unk>", "") for utt in text_pieces]
+            ground_truth_mat, utt_begin_indices = prepare_text(config, text_pieces)
         return CTCSegmentationTask(config=config, name=name, text=text, ground_truth_mat=ground_truth_mat,
                                    utt_begin_indices=utt_begin_indices, utt_ids=utt_ids, timings=None,
                                    char_probs=None, state_list=None, segments=None, done=False, lpz=lpz)
@@ -289,17 +327,18 @@ class CTCSegmentation:
         t_max = max(int(t.lpz.shape[0]) for t in tasks)
         c_max = max(len(t.ground_truth_mat) for t in tasks)
         k_max = max(len(t.utt_begin_indices) - 1 for t in tasks)
-        gt = np.full((n, c_max), -1, np.int32)
+        g_cols = max(np.asarray(t.ground_truth_mat).reshape(len(t.ground_truth_mat), -1).shape[1] for t in tasks)
+        gt = np.full((n, c_max) if g_cols == 1 else (n, c_max, g_cols), -1, np.int32)
         ub = np.zeros((n, k_max + 1), np.int32)
         n_cols = np.zeros(n, np.int32)
         n_utts = np.zeros(n, np.int32)
         in_len = np.zeros(n, np.int32)
         for i, t in enumerate(tasks):
-            g = np.asarray(t.ground_truth_mat)
-            if g.ndim == 2 and g.shape[1] != 1:
-                raise NotImplementedError("multi-column ground truth (classic text converter)")
-            g = g.reshape(-1)
-            gt[i, :len(g)] = g
+            g = np.asarray(t.ground_truth_mat).reshape(len(t.ground_truth_mat), -1)
+            if g_cols == 1:
+                gt[i, :len(g)] = g[:, 0]
+            else:
+                gt[i, :len(g), :g.shape[1]] = g
             n_cols[i] = len(g)
             k = len(t.utt_begin_indices) - 1
             ub[i, :k + 1] = t.utt_begin_indices
@@ -322,6 +361,7 @@ class CTCSegmentation:
         flags = cfg.flags | (ops.SEG_ALL_PREFIXES if all_prefixes else 0)
         kw = dict(blank=cfg.blank, score_len=cfg.score_min_mean_over_L, flags=flags, details=details)
         if lp.shape[1] <= cfg.min_window_size:
+            # (a multi-column ground truth runs the general kernels with window = T)
             res = ops.ctcseg_align(lp, in_len, gt, n_cols, ub, n_utts, cfg.index_duration_in_seconds, **kw)
             return cfg, res, n_utts
         # ctc-segmentation's windowed table mode: audio longer than min_window_size frames.  When the
@@ -346,14 +386,14 @@ class CTCSegmentation:
         timings = np.where(timing < 0, 0.0, timing.astype(np.float64) * cfg.index_duration_in_seconds)
         char_probs = res.char_prob[i, k - 1, :t_len].cpu().numpy().astype(np.float64)
         state = res.state[i, k - 1, :t_len].cpu().numpy()
-        gt = np.asarray(task.ground_truth_mat).reshape(-1)
+        gt = np.asarray(task.ground_truth_mat).reshape(len(task.ground_truth_mat), -1)
         state_list = [""] * t_len
         for t in np.nonzero(state != -2)[0]:
             s = int(state[t])
             if s == -1:
                 state_list[t] = cfg.self_transition
             else:
-                tok = int(gt[s])
+                tok = int(gt[s & 0xffffff, s >> 24])  # column | (candidate index << 24)
                 state_list[t] = cfg.char_list[tok] if cfg.char_list is not None else tok
         seg = res.seg[i, k - 1, :k].cpu().numpy()
         segments = [(seg[u, 0], seg[u, 1], seg[u, 2]) for u in range(k)]

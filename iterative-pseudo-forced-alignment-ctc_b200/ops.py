@@ -229,6 +229,12 @@ def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blan
     if utt_begin.dim() == 1:
         utt_begin = utt_begin[None]
     cmax = gt.shape[1]
+    # [n, cmax, G]: multi-column ground truth of the `classic` text converter -> the general
+    # (column-serial) kernels; the full table is the window = T case
+    gt_cols = gt.shape[2] if gt.dim() == 3 else 1
+    if gt_cols > 1 and window is None:
+        window = t
+    gt = gt.contiguous()
     kmax = utt_begin.shape[1] - 1
     in_len, n_cols, n_utts = _i32(in_len, dev), _i32(n_cols, dev), _i32(n_utts, dev)
     seg = torch.full((n, kmax, kmax, 3), float("nan"), dtype=torch.float64, device=dev)
@@ -243,12 +249,12 @@ def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blan
     L = lib()
     if window is not None:
         with torch.cuda.device(dev):
-            ws_bytes = L.ipfa_ctcseg_windowed_workspace_bytes(n, t, cmax, kmax, int(window))
+            ws_bytes = L.ipfa_ctcseg_windowed_workspace_bytes(n, t, cmax, kmax, int(window), gt_cols)
             ws = _workspace(ws_bytes, dev)
             rc = L.ipfa_ctcseg_windowed_device(
                 _ptr(lp), None, sn, st, _ptr(in_len), _ptr(gt), gt.stride(0), _ptr(n_cols), _ptr(utt_begin),
                 _ptr(n_utts), n, t, cmax, kmax, v, blank, float(index_duration), int(score_len), int(flags),
-                int(window), _ptr(seg), _ptr(term_t), _ptr(timing), _ptr(char_prob), _ptr(state),
+                int(window), gt_cols, _ptr(seg), _ptr(term_t), _ptr(timing), _ptr(char_prob), _ptr(state),
                 _ptr(status), _ptr(ws), ws.numel(), _stream(dev))
         check(rc, "ipfa_ctcseg_windowed_device")
         return SegAlignment(seg, term_t, timing, char_prob, state, status)

@@ -91,9 +91,7 @@ def prepare_text(config, text, char_list=None):
             if char.isspace() and config.replace_spaces_with_blanks:
                 if not ground_truth.endswith(config.space):
                     ground_truth += config.space
-            elif char in config.excluded_characters:
-                continue
-            else:
+            elif char in config.char_list and char not in config.excluded_characters:
                 ground_truth += char
     if not ground_truth.endswith(config.space):
         ground_truth += config.space

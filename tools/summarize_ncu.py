@@ -55,3 +55,20 @@ if __name__ == "__main__":
             else:
                 summarize_report(a, out)
     print(open(f"profiles/{tag}.txt").read())
+
+
+def traffic_of(path, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the first kernel whose name contains
+    `kernel_substr` in an `ncu --set full` report."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for r in rows[2:]:
+        if kernel_substr in r[hdr.index("Kernel Name")]:
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(k)
+                tot += float(r[i]) * scale[units[i]]
+            return int(tot)
+    return None
