@@ -320,3 +320,100 @@ def test_long_audio_through_the_ctcsegmentation_mirror(cs):
     for a, b in zip(got["segments"], ref["segments"]):
         assert a[0] == b[0] and a[1] == b[1]
         np.testing.assert_allclose(a[2], b[2], rtol=1e-12)
+
+
+# --------------------------------------------------------------------------- classic text converter
+BPE_LIST = ["<blank>", "<unk>", "a", "b", "c", "d", "ab", "bc", "cd", "abc", "da", "·x"]
+
+
+def _classic_case(seed, t_len, n_utts, v=None):
+    """Character strings over {a,b,c,d} + a vocabulary with multi-character tokens: the ground
+    truth matrix has up to 3 candidate tokens per position."""
+    from oracle import ctcseg as oseg
+    rng = np.random.default_rng(seed)
+    cfg = oseg.CtcSegmentationParameters(index_duration=0.02, char_list=list(BPE_LIST))
+    utts = ["".join(rng.choice(list("abcd"), size=int(rng.integers(4, 12)))) for _ in range(n_utts)]
+    gt, ub = oseg.prepare_text(cfg, utts)
+    v = len(BPE_LIST)
+    lp = rng.standard_normal((t_len, v)).astype(np.float32)
+    # make some multi-character tokens attractive so that s > 0 transitions are really taken
+    pos = np.sort(rng.permutation(t_len)[:len(gt)])
+    for c, (a, b) in enumerate(zip(pos, list(pos[1:]) + [t_len])):
+        cand = [int(g) for g in gt[c] if g >= 0]
+        if cand:
+            lp[a:b, cand[-1]] += 3.0
+    lp = lp - np.log(np.exp(lp.astype(np.float64)).sum(-1, keepdims=True)).astype(np.float32)
+    return cfg, utts, gt, ub, lp
+
+
+@pytest.mark.parametrize("t_len,window", [(300, None), (500, 160)])
+def test_multi_column_ground_truth_vs_oracle(ipfa, t_len, window):
+    """ctc-segmentation's `classic` converter: up to G switch transitions per cell,
+    full table (window = T) and sliding window."""
+    import torch
+    from oracle import ctcseg as oseg
+    cfg, utts, gt, ub, lp = _classic_case(71, t_len, 4)
+    assert gt.shape[1] >= 3 and (gt[:, 1:3] >= 0).any() and (gt[:, 3:] < 0).all()
+    n_cols, k = len(gt), len(ub) - 1
+    w = window
+    while True:
+        res = ipfa.ctcseg_align(torch.from_numpy(lp).cuda()[None], [t_len], gt.astype(np.int32)[None],
+                                [n_cols], np.asarray(ub, np.int32)[None], [k], 0.02, flags=2, window=w)
+        if not int(res.status[0]) & 8:
+            break
+        w *= 2
+    if window is not None:
+        cfg.min_window_size = window
+    timings, char_probs, state_list = oseg.ctc_segmentation(cfg, lp, gt)
+    segs = oseg.determine_utterance_segments(cfg, ub, char_probs, timings, utts)
+    timing = res.timing[0, k - 1, :n_cols].cpu().numpy()
+    assert np.array_equal(np.where(timing < 0, 0.0, timing * 0.02), timings)
+    assert np.array_equal(res.char_prob[0, k - 1, :t_len].cpu().numpy().astype(np.float64), char_probs)
+    state = res.state[0, k - 1, :t_len].cpu().numpy()
+    got_states = ["" if s == -2 else (cfg.self_transition if s == -1 else
+                                      cfg.char_list[int(gt[s & 0xffffff, s >> 24])]) for s in state]
+    assert got_states == state_list
+    assert any(len(s) > 1 for s in state_list)   # a multi-character token was taken
+    seg = res.seg[0, k - 1, :k].cpu().numpy()
+    for u in range(k):
+        assert seg[u, 0] == segs[u][0] and seg[u, 1] == segs[u][1]
+        np.testing.assert_allclose(seg[u, 2], segs[u][2], rtol=1e-12)
+
+
+def test_classic_text_converter_through_the_mirror(cs):
+    import torch
+    from oracle import ctcseg as oseg
+    import types
+
+    class PieceTokenizer:
+        pieces = list(BPE_LIST)
+
+        def vocab_size(self):
+            return len(self.pieces)
+
+        def id_to_piece(self, i):
+            return self.pieces[i]
+
+        def unk_id(self):
+            return 1
+
+        def encode_as_pieces(self, text):
+            return list(text)
+
+        def encode_as_ids(self, text):
+            return [self.pieces.index(c) for c in text]
+
+    asr = types.SimpleNamespace(tokenizer=PieceTokenizer(), encode_batch=lambda *a: None, device="cuda",
+                                hparams=types.SimpleNamespace(sample_rate=16000, log_softmax=lambda x: x))
+    aligner = cs.CTCSegmentation(asr, kaldi_style_text=False, time_stamps="fixed", text_converter="classic")
+    aligner.samples_to_frames_ratio = 320.0
+    cfg, utts, gt, ub, lp = _classic_case(72, 350, 3)
+    task = aligner.prepare_segmentation_task(utts, torch.from_numpy(lp).cuda(), "classic", 350 * 320)
+    assert np.array_equal(task.ground_truth_mat, gt) and list(task.utt_begin_indices) == list(ub)
+    got = cs.CTCSegmentation.get_segments(task)
+    ref = oseg.get_segments(cfg, lp, gt, ub, utts)
+    assert np.array_equal(got["timings"], ref["timings"]) and got["state_list"] == ref["state_list"]
+    assert np.array_equal(got["char_probs"], ref["char_probs"])
+    for a, b in zip(got["segments"], ref["segments"]):
+        assert a[0] == b[0] and a[1] == b[1]
+        np.testing.assert_allclose(a[2], b[2], rtol=1e-12)

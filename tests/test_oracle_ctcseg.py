@@ -138,3 +138,21 @@ def test_windowed_table_equals_full_when_it_fits():
     a = oseg.ctc_segmentation(cfg_full, lpz, gt)
     b = oseg.ctc_segmentation(cfg_win, lpz, gt)
     assert np.allclose(a[0], b[0]) and np.allclose(a[1], b[1])
+
+
+def test_prepare_text_product_mirror_equals_oracle():
+    """The `classic` text converter: product mirror and oracle restatement build the same matrix."""
+    import importlib
+    from oracle import ctcseg as oseg
+    cs = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.ctc_segmentation")
+    chars = ["<blank>", "<unk>", "a", "b", "c", "ab", "bc", "abc", "ca"]
+    utts = ["abcab", "ca bc", "b.a,c", "zzz"]
+    for spaces in (False, True):
+        a = oseg.CtcSegmentationParameters(char_list=list(chars), replace_spaces_with_blanks=spaces)
+        b = cs.CtcSegmentationParameters(char_list=list(chars), replace_spaces_with_blanks=spaces)
+        ga, ua = oseg.prepare_text(a, utts)
+        gb, ub = cs.prepare_text(b, utts)
+        assert np.array_equal(ga, gb) and list(ua) == list(ub)
+        assert ga.shape[1] == len("<blank>") and (ga[0] == -1).all()  # max_char_len counts '<blank>' too
+        # a multi-character token sits in the column of its length - 1
+        assert (ga[:, 2] >= 0).sum() >= 1
