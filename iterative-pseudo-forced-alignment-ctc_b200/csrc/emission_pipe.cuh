@@ -13,6 +13,8 @@
 //   gather : the panel row holds only the window's own columns,
 //            panel[t][j] = lp[t, cols[j]] with cols[0] = blank; 4-byte cp.async.
 #pragma once
+#include <stdlib.h>
+
 #include "ipfa_common.cuh"
 
 namespace ipfa {
@@ -179,6 +181,10 @@ inline PipeGeometry pipe_geometry(int U_panel, size_t budget_bytes) {
     size_t per_frame = (size_t)kStages * g.pitch * sizeof(float);
     int tc = (int)(budget_bytes / per_frame);
     if (tc > 32) tc = 32;
+    if (const char *e = getenv("IPFA_PIPE_TC")) {  // tuning override: frames per chunk
+        const int v = atoi(e);
+        if (v >= 2 && v < tc) tc = v;
+    }
     tc &= ~1;  // even: frame parity == row parity inside a chunk (double-buffered exchange lines)
     if (tc < 2) tc = 2;
     g.tc = tc;
