@@ -208,3 +208,37 @@ def test_entry_point_with_resident_emissions(tmp_path):
         assert list(out.columns) == anchor.RESULT_COLUMNS
         assert len(out.index) >= 1  # the last row of a file is always kept (:263)
         assert (out['End'] >= out['Start']).all()
+
+
+@pytest.mark.parametrize("case", ["needs_recalc", "exceptions_limit", "window_to_stop", "low_text"])
+def test_sweep_terminal_states_equal_the_oracle(case):
+    """The branches around the alignment call (:119-125, :167-192, :390-402): hand-off to host policy,
+    consecutive text-longer-than-audio errors, the window_to_stop break, 'read more audio and text'."""
+    import copy
+    import sweep_corpus
+    from oracle import sweep as osweep
+    tok = stub.CharTokenizer()
+    spec = sweep_corpus.make_spec("t", 3.0, 77, corrupt_frac=0.0)
+    rows = copy.deepcopy(spec.rows)
+    kw = {}
+    if case == "needs_recalc":
+        kw = dict(max_window_size=12.0)          # the second or third clip reaches 12 s
+    elif case == "exceptions_limit":
+        for i, r in enumerate(rows):             # half-second clips for ~150 characters of text
+            r["Start"], r["End"] = 0.5 * i, 0.5 * (i + 1)
+        kw = dict(max_text_to_audio_prop_exec=3)
+    elif case == "window_to_stop":
+        kw = dict(max_window_size=1000.0, window_to_stop=15.0)
+    elif case == "low_text":
+        kw = dict(min_text_to_audio_prop=4.5)    # most clips have "too little text": merged with the next row
+    lp = sweep_corpus.emissions(spec, "cuda", seed=3)
+    f = sweep.SweepFile(spec.file_id, spec.audio_path, lp, spec.n_samples, rows)
+    sw = sweep.AnchorSweep(sweep.SweepCorpus([f], tok), index_duration=0.02, samples_to_frames_ratio=320.0, **kw)
+    status = sw.run(steps_per_poll=2)
+    ref_rows, ref_status, stats = osweep.sweep_file(spec.file_id, spec.audio_path, lp.cpu().numpy(), spec.n_samples,
+                                                    rows, tok, **kw)
+    assert sweep.STATUS_NAMES[status[0]] == ref_status
+    if case != "low_text":
+        assert ref_status == case
+    assert sw.file_rows()[0] == ref_rows
+    assert int(sw.state["n_windows"][0]) == stats["windows"]

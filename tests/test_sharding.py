@@ -46,3 +46,54 @@ def test_gather_rows_gloo_world2(tmp_path):
     assert sorted(r0["mine"] + r1["mine"]) == list(range(11)) and len(r0["mine"]) != len(r1["mine"]) or True
     assert [o["rank"] for o in r0["objs"]] == [0, 1]
     assert r0["objs"][1]["units"] == r1["mine"]
+
+
+def _sweep_worker(rank, world, port, out_dir):
+    """The N > 1 path of the anchor sweep (BASELINE configs[4]) on CPU: every rank derives the same
+    corpus description, aligns its own LPT shard of the FILES (here with the CPU restatement), and
+    the per-file rows are gathered -- no collective on the data path."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sweep_corpus
+    from oracle import sweep as osweep
+    stub = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    minutes = [0.6, 1.4, 0.4, 0.9, 0.5]
+    mine = sharding.my_shard(minutes)
+    out = {}
+    for i in mine:
+        spec = sweep_corpus.make_spec(f"f{i}", minutes[i], 300 + i, corrupt_frac=0.1)
+        lp = sweep_corpus.emissions(spec, "cpu", seed=i).numpy()
+        rows, status, _ = osweep.sweep_file(spec.file_id, spec.audio_path, lp, spec.n_samples, spec.rows,
+                                            stub.CharTokenizer())
+        out[i] = (status, rows)
+    gathered = sharding.gather_objects(out)
+    torch.save({"mine": mine, "gathered": gathered}, os.path.join(out_dir, f"s{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_anchor_sweep_file_shards_gloo_world2(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sweep_corpus
+    from oracle import sweep as osweep
+    stub = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_sweep_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "s0.pt", weights_only=False)
+    r1 = torch.load(tmp_path / "s1.pt", weights_only=False)
+    assert sorted(r0["mine"] + r1["mine"]) == list(range(5))
+    merged = {}
+    for part in r0["gathered"]:
+        merged.update(part)
+    assert r0["gathered"] == r1["gathered"] and sorted(merged) == list(range(5))
+    # the longest file sits alone with the lightest ones: shards are balanced by duration
+    loads = [sum([0.6, 1.4, 0.4, 0.9, 0.5][i] for i in r["mine"]) for r in (r0, r1)]
+    assert abs(loads[0] - loads[1]) <= 0.4
+    # a shard's result does not depend on which rank computed it
+    spec = sweep_corpus.make_spec("f1", 1.4, 301, corrupt_frac=0.1)
+    lp = sweep_corpus.emissions(spec, "cpu", seed=1).numpy()
+    rows, status, _ = osweep.sweep_file(spec.file_id, spec.audio_path, lp, spec.n_samples, spec.rows,
+                                        stub.CharTokenizer())
+    assert merged[1] == (status, rows) and len(rows) > 0
