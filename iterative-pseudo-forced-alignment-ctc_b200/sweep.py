@@ -325,6 +325,23 @@ class AnchorSweep:
                 break
         return self.state["status"].cpu().numpy()
 
+    # ------------------------------------------------------------------ host policy hand-off
+    def set_row_times(self, f, starts, ends):
+        """New Start / End (seconds) of file f's rows, e.g. after ``fix_text_to_time_proportion``."""
+        r0, r1 = int(self.corpus.host["row_first"][f]), int(self.corpus.host["row_first"][f + 1])
+        assert len(starts) == len(ends) == r1 - r0
+        dev = self.corpus.device
+        self.corpus.arrays["row_start"][r0:r1] = torch.as_tensor(np.asarray(starts, np.float64), device=dev)
+        self.corpus.arrays["row_end"][r0:r1] = torch.as_tensor(np.asarray(ends, np.float64), device=dev)
+        self.corpus.host["row_start"][r0:r1] = starts
+        self.corpus.host["row_end"][r0:r1] = ends
+
+    def resume_after_recalc(self, f):
+        """File f stopped with NEEDS_RECALC and the host has re-spread its rows (:127-146): continue
+        with the alignment of the same row."""
+        self.state["recalc_row"][f] = self.state["row"][f]
+        self.state["status"][f] = ACTIVE
+
     # ------------------------------------------------------------------ results
     def file_rows(self):
         """Per file: the rows the reference would have appended to ``file_alignments`` (:258-260)."""

@@ -40,8 +40,11 @@ def _find_a_valid_text_to_audio_proportion(audio_length, transcript, samples_to_
 def sweep_file(file_id, audio_path, lpz, n_samples, rows, tokenizer, index_duration=0.02,
                samples_to_frames_ratio=320.0, frame_shift=320, sample_rate=16000, threshold=-2.0,
                short_utterance_len=30, max_window_size=70.0, window_to_stop=500.0,
-               min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, scoring_length=30, blank=0):
-    """Returns ``(file_alignments, status, stats)``; ``rows`` as in the product's ``SweepFile.rows``."""
+               min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, scoring_length=30, blank=0,
+               recalc_fn=None):
+    """Returns ``(file_alignments, status, stats)``; ``rows`` as in the product's ``SweepFile.rows``.
+    ``recalc_fn(row_index, rows, clip_start) -> rows`` stands for ``fix_text_to_time_proportion``
+    (:127-146); without it the file stops with status ``needs_recalc`` at that point."""
     lpz = np.asarray(lpz, dtype=np.float32)
     cfg = oseg.CtcSegmentationParameters(index_duration=index_duration, score_min_mean_over_L=scoring_length,
                                          blank=blank)
@@ -85,8 +88,13 @@ def sweep_file(file_id, audio_path, lpz, n_samples, rows, tokenizer, index_durat
             status = "window_to_stop"
             break
         if recalculate_time_references:
-            status = "needs_recalc"
-            break
+            if recalc_fn is None:
+                status = "needs_recalc"
+                break
+            rows = recalc_fn(row_index, rows, clip_start)  # :127-146
+            row = rows[row_index]
+            clip_end = float(row["End"])
+            clip_length = clip_end - clip_start
 
         # :149-160 torchaudio.load(frame_offset, num_frames) clamps to the file
         offset = max(0, min(int(clip_start * sample_rate), n_samples))

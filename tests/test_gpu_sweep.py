@@ -242,3 +242,41 @@ def test_sweep_terminal_states_equal_the_oracle(case):
         assert ref_status == case
     assert sw.file_rows()[0] == ref_rows
     assert int(sw.state["n_windows"][0]) == stats["windows"]
+
+
+def test_sweep_resumes_after_host_recalc_and_trims_text_before_silence():
+    """:119-146 + :185-192: a speech segment that ends (next row is Non-Speech) with far more text than
+    audio first goes to the host's time re-spreading (here: the identity), then aligns only as many
+    utterances as fit (find_a_valid_text_to_audio_proportion)."""
+    import copy
+    import sweep_corpus
+    from oracle import sweep as osweep
+    tok = stub.CharTokenizer()
+    spec = sweep_corpus.make_spec("t", 2.0, 91, corrupt_frac=0.0)
+    rows = copy.deepcopy(spec.rows)
+    first = rows[0]
+    assert len(first["utterances"]) >= 2
+    n_chars = len(" ".join(first["utterances"]))
+    clip = n_chars * 0.019                                # text_to_audio_proportion = 0.24 / 0.019 = 12.6
+    assert clip > 5.0 and int(clip * 50) <= n_chars       # more characters than frames: text must be trimmed
+    first["Start"], first["End"] = 0.0, clip
+    silence = {"Type": "Non-Speech", "Start": clip, "End": clip + 1.0, "utterances": []}
+    rows = [first, silence] + rows[1:]
+    rows[2]["Start"] = clip + 1.0
+    lp = sweep_corpus.emissions(spec, "cuda", seed=4)
+    f = sweep.SweepFile(spec.file_id, spec.audio_path, lp, spec.n_samples, rows)
+    sw = sweep.AnchorSweep(sweep.SweepCorpus([f], tok), index_duration=0.02, samples_to_frames_ratio=320.0)
+    calls = []
+
+    def recalc(s, fi):
+        calls.append(int(s.state["row"][fi]))
+        s.resume_after_recalc(fi)
+        return True
+
+    status = sw.run(steps_per_poll=1, recalc_fn=recalc)
+    ref_rows, ref_status, stats = osweep.sweep_file(spec.file_id, spec.audio_path, lp.cpu().numpy(), spec.n_samples,
+                                                    rows, tok, recalc_fn=lambda i, r, c: r)
+    assert calls and calls[0] == 0
+    assert sweep.STATUS_NAMES[status[0]] == ref_status == "done"
+    assert sw.file_rows()[0] == ref_rows and len(ref_rows) > 3
+    assert int(sw.state["n_windows"][0]) == stats["windows"]
