@@ -331,8 +331,8 @@ class AnchorSweep:
         r0, r1 = int(self.corpus.host["row_first"][f]), int(self.corpus.host["row_first"][f + 1])
         assert len(starts) == len(ends) == r1 - r0
         dev = self.corpus.device
-        self.corpus.arrays["row_start"][r0:r1] = torch.as_tensor(np.asarray(starts, np.float64), device=dev)
-        self.corpus.arrays["row_end"][r0:r1] = torch.as_tensor(np.asarray(ends, np.float64), device=dev)
+        self.corpus.arrays["row_start"][r0:r1] = torch.as_tensor(np.array(starts, np.float64), device=dev)
+        self.corpus.arrays["row_end"][r0:r1] = torch.as_tensor(np.array(ends, np.float64), device=dev)
         self.corpus.host["row_start"][r0:r1] = starts
         self.corpus.host["row_end"][r0:r1] = ends
 
@@ -372,9 +372,49 @@ class AnchorSweep:
                            zip(*np.unique(self.state["status"].cpu().numpy(), return_counts=True))}}
 
 
+class _Quiet:
+    def debug(self, *a, **k):
+        pass
+
+
+def dataframe_recalc(frames, vads, real_lengths, logger=None):
+    """``recalc_fn`` for :meth:`AnchorSweep.run` that applies the reference's
+    ``fix_text_to_time_proportion`` (:127-146) on the host when a file stops with NEEDS_RECALC.
+
+    ``frames[f]``: the file's TSV rows after ``fix_time_reference`` (a DataFrame, updated in
+    place here like ``file_df`` in the reference); ``vads[f]``: its VAD table; ``real_lengths[f]``:
+    audio seconds.  The device keeps the row STRUCTURE it was given, so the file is resumed only
+    when the re-spreading leaves the number and types of rows unchanged (one VAD segment, the
+    common case); otherwise it stays NEEDS_RECALC for the per-file loop."""
+    logger = logger or _Quiet()
+
+    def recalc(sweep, f):
+        h = sweep.corpus.host
+        r0 = int(h["row_first"][f])
+        row = int(sweep.state["row"][f])
+        anchor = float(sweep.state["anchor"][f])
+        df = frames[f]
+        clip_start = anchor if anchor == anchor else float(df.iloc[row]['Start'])
+        speech = [i for i in range(row + 1) if df.iloc[i]['Type'] != 'Non-Speech']
+        ends = h["row_utt_end"][r0:r0 + row + 1]
+        list_of_splits = [int(ends[i] - (ends[i - 1] if i else 0)) for i in speech]  # :90
+        n_aligned_utts = int(sweep.state["utt"][f])                                  # len(file_alignments)
+        n_segments = int((df['Type'] != 'Non-Speech').sum())
+        new = hg.fix_text_to_time_proportion(df, vads[f], real_lengths[f] - clip_start,
+                                             hg.get_n_aligned_rows(list_of_splits, n_aligned_utts),
+                                             n_segments, clip_start, logger)
+        if len(new.index) != len(df.index) or list(new['Type']) != list(df['Type']):
+            return False
+        frames[f] = new
+        sweep.set_row_times(f, new['Start'].astype(float).to_numpy(), new['End'].astype(float).to_numpy())
+        sweep.resume_after_recalc(f)
+        return True
+    return recalc
+
+
 def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, threshold=-2.0, short_utterance_len=30,
                          max_words_sequence=24, max_window_size=70.0, window_to_stop=500.0,
-                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10):
+                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, groups=4):
     """Anchor loop of several files with file-level emissions resident on the GPU.
 
     ``jobs``: list of ``(audio_path, file_df, vad_file_df)`` like the arguments of
@@ -382,17 +422,21 @@ def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, thre
     whole normalised audio) instead of once per window (:149-201).  Returns
     ``(rows_per_file, status_per_file)``; files whose status is not DONE stopped where the
     reference's host-side policy takes over (see ``ipfa_b200.h``) and carry the rows found so far."""
-    files = []
+    files, frames, vads, lengths = [], [], [], []
     for audio_path, file_df, vad_file_df in jobs:
         info = hg.audio_info(audio_path)
         audio, sr = hg.audio_load(audio_path, channels_first=False)
         lpz = aligner.get_lpz(asr_model.audio_normalizer(audio, sr))
         if not torch.is_tensor(lpz):
             lpz = torch.as_tensor(lpz)
-        fixed = hg.fix_time_reference(file_df, vad_file_df, info.num_frames / info.sample_rate, len(file_df.index))
+        real_length = info.num_frames / info.sample_rate
+        fixed = hg.fix_time_reference(file_df, vad_file_df, real_length, len(file_df.index))
         file_id = audio_path.split('/')[-1].replace('.wav', '')
         files.append(SweepFile(file_id, audio_path, lpz.cuda(), info.num_frames,
                                rows_from_dataframe(fixed, max_words_sequence)))
+        frames.append(fixed)
+        vads.append(vad_file_df)
+        lengths.append(real_length)
     corpus = SweepCorpus(files, asr_model.tokenizer, blank=aligner.config.blank)
     fs = int(asr_model.hparams.sample_rate)
     sweep = AnchorSweep(corpus, index_duration=samples_to_frames_ratio / fs,
@@ -400,6 +444,7 @@ def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, thre
                         short_utterance_len=short_utterance_len, max_window_size=max_window_size,
                         window_to_stop=window_to_stop, min_text_to_audio_prop=min_text_to_audio_prop,
                         max_text_to_audio_prop_exec=max_text_to_audio_prop_exec,
-                        scoring_length=aligner.config.score_min_mean_over_L, seg_flags=aligner.config.flags)
-    status = sweep.run()
+                        scoring_length=aligner.config.score_min_mean_over_L, seg_flags=aligner.config.flags,
+                        groups=groups)
+    status = sweep.run(recalc_fn=dataframe_recalc(frames, vads, lengths))
     return sweep.file_rows(), status

@@ -280,3 +280,45 @@ def test_sweep_resumes_after_host_recalc_and_trims_text_before_silence():
     assert sweep.STATUS_NAMES[status[0]] == ref_status == "done"
     assert sw.file_rows()[0] == ref_rows and len(ref_rows) > 3
     assert int(sw.state["n_windows"][0]) == stats["windows"]
+
+
+def test_sweep_with_host_time_respreading_equals_the_per_file_loop(exact_audio, tmp_path):
+    """max_window_size small enough that the reference's `fix_text_to_time_proportion` (:119-146)
+    fires several times per file: the sweep hands the file to the host callback, takes the new
+    row times and resumes -- same rows as the per-file loop driven by the CPU oracle."""
+    specs = [_corpus_file("a", 14, 31), _corpus_file("b", 20, 32, corrupt=((300, 420),)),
+             _corpus_file("c", 9, 33)]
+    for s in specs:
+        exact_audio[s["wav"]] = s["total"]
+    kw = dict(KW, max_window_size=5.5)
+    ref = []
+    for s in specs:
+        aligner = cs.CTCSegmentation(s["asr"], kaldi_style_text=False, time_stamps="fixed", scoring_length=30)
+        aligner.samples_to_frames_ratio = 320.0
+        ref.append(anchor.get_file_iterative_segmentation(s["asr"], aligner, s["wav"], s["df"].copy(),
+                                                          s["vad"].copy(), 320.0, str(tmp_path),
+                                                          window_fn=oracle_window_fn, **kw))
+    frames, vads, lengths, files = [], [], [], []
+    for s in specs:
+        fixed = hg.fix_time_reference(s["df"], s["vad"], s["total"] / 16000, len(s["df"].index))
+        lpz = torch.log_softmax(s["asr"].logits[: s["total"] // 320].float(), dim=-1).cuda()
+        files.append(sweep.SweepFile(s["name"], s["wav"], lpz, s["total"],
+                                     sweep.rows_from_dataframe(fixed, kw["max_words_sequence"])))
+        frames.append(fixed)
+        vads.append(s["vad"])
+        lengths.append(s["total"] / 16000)
+    sw = sweep.AnchorSweep(sweep.SweepCorpus(files, stub.CharTokenizer()), index_duration=0.02,
+                           samples_to_frames_ratio=320.0, max_window_size=kw["max_window_size"])
+    n_calls = []
+    inner = sweep.dataframe_recalc(frames, vads, lengths)
+
+    def counted(s_, f_):
+        n_calls.append(f_)
+        return inner(s_, f_)
+
+    status = sw.run(steps_per_poll=2, recalc_fn=counted)
+    got = sw.file_rows()
+    assert len(n_calls) >= 2                       # the host policy really ran
+    for f, s in enumerate(specs):
+        assert status[f] == sweep.DONE, (s["name"], sweep.STATUS_NAMES[status[f]])
+        assert got[f] == ref[f], s["name"]
