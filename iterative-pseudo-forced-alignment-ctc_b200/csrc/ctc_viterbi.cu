@@ -141,9 +141,9 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
     // so the backtrace can hop from move to move with mask + find-leading-one instead of
     // stepping frames, and a decision costs one predicated OR.  3P words per thread and block
     // (1.5 bits per state and frame), stored plane by plane: every warp store is 128 contiguous bytes.
-    // (ptxas 12.9 segfaults on the widest instance, 8 pairs x 32 warps, unless its label plane also
+    // (ptxas 12.9 segfaults on some of the 8-pairs-per-thread instances unless their label plane also
     // carries the skip moves; the backtrace ORs the two planes, so both encodings read the same.)
-    constexpr bool kMergedPlanes = (P == 8 && WARPS == 32);
+    constexpr bool kMergedPlanes = (P == 8);
     uint32_t mvb[P], mvl[P], by2[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) { mvb[p] = 0; mvl[p] = 0; by2[p] = 0; }
@@ -159,15 +159,17 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
         }
         bp_ptr += 3 * P * NT;
     };
-    auto next_frame = [&]() {
-        bit <<= 1;
+    auto advance = [&](const int frames) {  // `frames` frames done; a group never straddles a block
+        bit <<= frames;
         if (bit == 0) { flush(); bit = 1; }
     };
 
-    // One frame, `off` floats past the column cursors.
+    // One frame, `off` floats past the column cursors, `sh` frames past the one `bit` stands for
+    // (a compile-time constant after inlining, so the unrolled group shares one block test).
     const float *pb = nullptr;
     const float *pl[P];
-    auto frame = [&](const int off, const float *rd, float *wr) {
+    auto frame = [&](const int off, const float *rd, float *wr, const int sh) {
+        const uint32_t fbit = bit << sh;
         const float eb = pb[off];
         float el[P];
 #pragma unroll
@@ -195,15 +197,14 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
             const float nb = (takeb ? lm1 : ab[p]) + eb;
             al[p] = res + el[p];
             ab[p] = nb;
-                    mvb[p] |= takeb ? bit : 0u;
-            mvl[p] |= (take1 || (kMergedPlanes && take2)) ? bit : 0u;
-            by2[p] |= take2 ? bit : 0u;
+                    mvb[p] |= takeb ? fbit : 0u;
+            mvl[p] |= (take1 || (kMergedPlanes && take2)) ? fbit : 0u;
+            by2[p] |= take2 ? fbit : 0u;
         }
         if constexpr (WARPS > 1) {
             wr[tid + 1] = al[P - 1];
             __syncthreads();
         }
-        next_frame();
     };
     auto bump = [&](const int frames) {
         pb += frames * pitch;
@@ -224,7 +225,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
                 ab[0] = panel[colb];
                 if (L > 0) al[0] = panel[col[0]];
             }
-            next_frame();  // frame 0 has no incoming transition
+            advance(1);  // frame 0 has no incoming transition
             if constexpr (WARPS > 1) {
                 line0[tid + 1] = al[P - 1];
                 __syncthreads();
@@ -235,20 +236,31 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
         pb = panel + r * pitch + colb;
 #pragma unroll
         for (int p = 0; p < P; ++p) pl[p] = panel + r * pitch + col[p];
-        if ((r & 1) && r < rows) { frame(0, line0, line1); bump(1); ++r; }
-        for (; r + 3 < rows; r += 4) {
-            frame(0, line1, line0);
-            frame(pitch, line0, line1);
-            frame(2 * pitch, line1, line0);
-            frame(3 * pitch, line0, line1);
-            bump(4);
+        // single frames up to a multiple of 4 (t0 is a multiple of tc, tc of 4 whenever tc > 2): from
+        // there groups of 4 frames sit inside one 32-frame block and share one advance()
+        // (the 8-pairs-per-thread instances keep single frames: ptxas 12.9 segfaults on their
+        // unrolled form)
+        const int align4 = (P == 8 || (pipe.tc & 3)) ? rows : min(rows, (r + 3) & ~3);
+        for (; r < align4; ++r) {
+            if (r & 1) frame(0, line0, line1, 0); else frame(0, line1, line0, 0);
+            advance(1);
+            bump(1);
         }
-        for (; r + 1 < rows; r += 2) {
-            frame(0, line1, line0);
-            frame(pitch, line0, line1);
-            bump(2);
+        if constexpr (P < 8) {
+            for (; r + 3 < rows; r += 4) {
+                frame(0, line1, line0, 0);
+                frame(pitch, line0, line1, 1);
+                frame(2 * pitch, line1, line0, 2);
+                frame(3 * pitch, line0, line1, 3);
+                advance(4);
+                bump(4);
+            }
         }
-        if (r < rows) frame(0, line1, line0);
+        for (; r < rows; ++r) {
+            if (r & 1) frame(0, line0, line1, 0); else frame(0, line1, line0, 0);
+            advance(1);
+            bump(1);
+        }
     }
     if (bit != 1) flush();
 
