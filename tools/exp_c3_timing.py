@@ -10,6 +10,11 @@ from ipfa_b200 import ops
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 dev = torch.device("cuda:0")
 inputs = wl.make(0, device=dev)
+if len(sys.argv) > 2:  # L2 fetch granularity experiment (bytes)
+    import ctypes
+    cu = ctypes.CDLL("libcuda.so.1")
+    print("cuCtxSetLimit(MAX_L2_FETCH_GRANULARITY,", sys.argv[2], ") ->",
+          cu.cuCtxSetLimit(0x05, ctypes.c_size_t(int(sys.argv[2]))))
 def step():
     return wl.step(ipfa, inputs)
 for _ in range(3): step()
