@@ -30,7 +30,8 @@ struct AlphaParams {
     int64_t tgt_stride;
     const int32_t *in_len;
     const int32_t *tgt_len;
-    const int32_t *order;  // optional window permutation (heaviest first), may be null
+    const int32_t *order;  // length bucket of this launch: windows order[0 .. *count) (null: all N)
+    const int32_t *count;
     int N, V, blank;
     int halves;            // groups per window: 2 = meet-in-the-middle walk, 1 = forward only
     int pitch, tc;         // pipe geometry
@@ -64,9 +65,11 @@ ctc_alpha_kernel(const AlphaParams prm) {
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
     const int g2 = blockIdx.x * GROUPS + group;  // (window, half)
-    if (g2 >= prm.halves * prm.N) return;  // WARPS==1: whole warp leaves; WARPS>1: whole CTA leaves
-    const int w = (prm.halves == 2) ? g2 >> 1 : g2;
+    // WARPS==1: whole warp leaves; WARPS>1: whole CTA leaves
+    if (g2 >= prm.halves * (prm.count ? *prm.count : prm.N)) return;
+    int w = (prm.halves == 2) ? g2 >> 1 : g2;
     const int half = (prm.halves == 2) ? g2 & 1 : 0;
+    if (prm.order) w = prm.order[w];
 
     const int pitch = PITCH ? PITCH : prm.pitch;
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
@@ -345,7 +348,9 @@ static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
 
 template <int P, int WARPS, bool DENSE>
 static int launch_alpha(const AlphaParams &prm, int Lmax, cudaStream_t stream) {
-    if constexpr (DENSE) {
+    // (ptxas 12.9 segfaults on the widest instance with the compile-time pitch; it keeps the
+    // runtime pitch -- 8192 state pairs over a 32-symbol vocabulary is not a real workload)
+    if constexpr (DENSE && !(P == 8 && WARPS == 32)) {
         if (prm.V <= 32) return launch_alpha_p<P, WARPS, true, 32>(prm, Lmax, stream);
     }
     return launch_alpha_p<P, WARPS, DENSE, 0>(prm, Lmax, stream);
@@ -371,7 +376,9 @@ static inline size_t alpha_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 // arrival counters [N] + the two halves' state vectors at the cut [N][2][2][Lmax + 1]
 extern "C" size_t ipfa_ctc_alpha_workspace_bytes(int N, int, int Lmax, int) {
     const size_t n = (size_t)(N > 0 ? N : 1), l1 = (size_t)(Lmax > 0 ? Lmax : 0) + 1;
-    return alpha_pad256(n * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) + 256;
+    // arrival counters, join vectors, length-bucket lists [2][N] + their counters
+    return alpha_pad256(n * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
+           alpha_pad256(n * 2 * sizeof(int32_t)) + 256 + 256;
 }
 
 extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
@@ -398,7 +405,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     prm.halves = halves;
     prm.lp = lp; prm.stride_n = stride_n; prm.stride_t = stride_t;
     prm.targets = targets; prm.tgt_stride = tgt_stride;
-    prm.in_len = in_len; prm.tgt_len = tgt_len; prm.order = nullptr;
+    prm.in_len = in_len; prm.tgt_len = tgt_len; prm.order = nullptr; prm.count = nullptr;
     prm.N = N; prm.V = V; prm.blank = blank; prm.nll_out = nll_out;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     prm.join_count = static_cast<int *>(workspace);
@@ -406,6 +413,32 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
                                              alpha_pad256((size_t)N * sizeof(int32_t)));
     cudaError_t e = cudaMemsetAsync(prm.join_count, 0, (size_t)N * sizeof(int32_t), st);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
-    if (dense) return dispatch_alpha<true>(prm, Lmax, s, st);
-    return dispatch_alpha<false>(prm, Lmax, s, st);
+    // two length buckets when the batch is large and a half-width instance exists (decided on the
+    // device, see length_bucket_kernel)
+    const int big_units = 32 * s.WARPS * s.PER, small_units = big_units / 2;
+    LatticeShape s_small;
+    const bool bucketed = N >= kBucketMinWindows && small_units >= 32 && !getenv("IPFA_NO_BUCKETS") &&
+                          pick_lattice_shape(small_units, halves * N, &s_small, "IPFA_ALPHA_SMALL_SHAPE", 6) &&
+                          32 * s_small.WARPS * s_small.PER == small_units;
+    if (!bucketed) {
+        if (dense) return dispatch_alpha<true>(prm, Lmax, s, st);
+        return dispatch_alpha<false>(prm, Lmax, s, st);
+    }
+    const size_t l1 = (size_t)Lmax + 1;
+    int32_t *order = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(prm.join_vec) +
+                                                 alpha_pad256((size_t)N * 4 * l1 * sizeof(float)));
+    int32_t *count = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(order) +
+                                                 alpha_pad256((size_t)N * 2 * sizeof(int32_t)));
+    e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, small_units, order, count);
+    ++g_launch_count;
+    for (int cls = 0; cls < 2; ++cls) {
+        prm.order = order + (int64_t)cls * N;
+        prm.count = count + cls;
+        const LatticeShape sh = cls == 0 ? s_small : s;
+        const int rc = dense ? dispatch_alpha<true>(prm, Lmax, sh, st) : dispatch_alpha<false>(prm, Lmax, sh, st);
+        if (rc) return rc;
+    }
+    return IPFA_OK;
 }

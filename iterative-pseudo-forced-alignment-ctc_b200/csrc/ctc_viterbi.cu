@@ -42,6 +42,9 @@ struct ViterbiParams {
     int32_t *final_state;    // [N]
     float *total_out;        // [N] nullable
     int32_t *status_out;     // [N]
+    // length buckets: this launch walks windows order[0 .. *count) (null: all N windows in order)
+    const int32_t *order;
+    const int32_t *count;
 };
 
 // PITCH > 0: compile-time panel pitch (dense rows of <= 32 symbols): the unrolled frames of a
@@ -56,8 +59,9 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    const int w = blockIdx.x * GROUPS + group;
-    if (w >= prm.N) return;
+    int w = blockIdx.x * GROUPS + group;
+    if (w >= (prm.count ? *prm.count : prm.N)) return;
+    if (prm.order) w = prm.order[w];
 
     const int pitch = PITCH ? PITCH : prm.pitch;
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
@@ -296,6 +300,8 @@ struct BacktraceParams {
     const uint32_t *bp;
     int64_t words_per_window;
     const int32_t *final_state;
+    const int32_t *order;    // length bucket of this launch (see ViterbiParams)
+    const int32_t *count;
     int32_t *paths_out;
     float *scores_out;
     int32_t *tok_start, *tok_end;
@@ -322,8 +328,9 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
     extern __shared__ __align__(16) unsigned char bt_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int w = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (w >= prm.N) return;
+    int w = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (w >= (prm.count ? *prm.count : prm.N)) return;
+    if (prm.order) w = prm.order[w];
     uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) + (size_t)wib * (NWORDS + prm.Lmax);
     int32_t *tg_s = reinterpret_cast<int32_t *>(raw + NWORDS);
     const int T = min(prm.in_len[w], prm.Tmax);
@@ -528,16 +535,20 @@ static int launch_backtrace(const BacktraceParams &prm, int P, cudaStream_t stre
     }
 }
 
+
 }  // namespace ipfa
 
 using namespace ipfa;
+
+static inline size_t vit_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 extern "C" size_t ipfa_ctc_viterbi_workspace_bytes(int N, int Tmax, int Lmax, int V) {
     (void)V;
     LatticeShape s;
     if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return 256;
     const size_t bp = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s) * sizeof(uint32_t);
-    return ((bp + 255) & ~(size_t)255) + (((size_t)N * 4 + 255) & ~(size_t)255) + 256;
+    // planes, final states, bucket lists [2][N] + counters
+    return vit_pad256(bp) + vit_pad256((size_t)N * 4) + vit_pad256((size_t)N * 8) + 256 + 256;
 }
 
 extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_t stride_t,
@@ -561,22 +572,51 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
     const size_t bp_bytes = ((size_t)N * (size_t)wpw * sizeof(uint32_t) + 255) & ~(size_t)255;
     int32_t *final_state = reinterpret_cast<int32_t *>(static_cast<unsigned char *>(workspace) + bp_bytes);
 
+    int32_t *order = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(final_state) +
+                                                 vit_pad256((size_t)N * 4));
+    int32_t *count = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(order) +
+                                                 vit_pad256((size_t)N * 8));
+
     ViterbiParams fp{};
     fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t;
     fp.targets = targets; fp.tgt_stride = tgt_stride; fp.in_len = in_len; fp.tgt_len = tgt_len;
     fp.N = N; fp.Tmax = Tmax; fp.V = V; fp.blank = blank;
     fp.bp = bp; fp.words_per_window = wpw; fp.final_state = final_state;
     fp.total_out = total_out; fp.status_out = status_out;
-    int rc = use_dense_panel(V, Lmax) ? dispatch_fill<true>(fp, Lmax, s, st)
-                                      : dispatch_fill<false>(fp, Lmax, s, st);
-    if (rc) return rc;
-
     BacktraceParams bt{};
     bt.lp = lp; bt.stride_n = stride_n; bt.stride_t = stride_t;
     bt.targets = targets; bt.tgt_stride = tgt_stride; bt.in_len = in_len; bt.tgt_len = tgt_len;
-    bt.N = N; bt.Tmax = Tmax; bt.Lmax = Lmax; bt.V = V; bt.blank = blank; bt.NT = 32 * s.WARPS;
+    bt.N = N; bt.Tmax = Tmax; bt.Lmax = Lmax; bt.V = V; bt.blank = blank;
     bt.bp = bp; bt.words_per_window = wpw; bt.final_state = final_state;
     bt.paths_out = paths_out; bt.scores_out = scores_out;
     bt.tok_start = tok_start; bt.tok_end = tok_end; bt.tok_score = tok_score;
-    return launch_backtrace(bt, s.PER, st);
+    const bool dense = use_dense_panel(V, Lmax);
+
+    // two length buckets when the batch is large and a half-width instance exists
+    const int big_units = 32 * s.WARPS * s.PER, small_units = big_units / 2;
+    LatticeShape s_small;
+    const bool bucketed = N >= kBucketMinWindows && small_units >= 32 && !getenv("IPFA_NO_BUCKETS") &&
+                          pick_lattice_shape(small_units, N, &s_small, "IPFA_VITERBI_SMALL_SHAPE", dense ? 3 : 6) &&
+                          32 * s_small.WARPS * s_small.PER == small_units;
+    if (!bucketed) {
+        int rc = dense ? dispatch_fill<true>(fp, Lmax, s, st) : dispatch_fill<false>(fp, Lmax, s, st);
+        if (rc) return rc;
+        bt.NT = 32 * s.WARPS;
+        return launch_backtrace(bt, s.PER, st);
+    }
+    cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, small_units, order, count);
+    ++g_launch_count;
+    for (int cls = 0; cls < 2; ++cls) {
+        const LatticeShape sh = cls == 0 ? s_small : s;
+        fp.order = order + (int64_t)cls * N; fp.count = count + cls;
+        bt.order = fp.order; bt.count = fp.count;
+        int rc = dense ? dispatch_fill<true>(fp, Lmax, sh, st) : dispatch_fill<false>(fp, Lmax, sh, st);
+        if (rc) return rc;
+        bt.NT = 32 * sh.WARPS;
+        rc = launch_backtrace(bt, sh.PER, st);
+        if (rc) return rc;
+    }
+    return IPFA_OK;
 }

@@ -89,4 +89,25 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Length buckets (large ragged batches): windows whose lattice fits half the launch width go to
+// a half-width instance -- half the lanes, half the instructions per frame.  Decided on the device
+// (no host synchronisation): one pass writes the two index lists, both instances are launched over
+// the full grid and the groups beyond their list's length leave at once.
+static __global__ void length_bucket_kernel(const int32_t *__restrict__ tgt_len, int N, int small_units,
+                                      int32_t *__restrict__ order, int32_t *__restrict__ count) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= N) return;
+    const int cls = (max(tgt_len[w], 0) + 1 <= small_units) ? 0 : 1;
+    // warp-aggregated append
+    const unsigned active = __activemask();
+    const unsigned same = __match_any_sync(active, cls);
+    const int leader = __ffs(same) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count + cls, __popc(same));
+    base = __shfl_sync(same, base, leader);
+    order[(int64_t)cls * N + base + __popc(same & ((1u << lane) - 1u))] = w;
+}
+
+constexpr int kBucketMinWindows = 4096;  // below this an extra launch costs more than it saves
+
 }  // namespace ipfa

@@ -203,3 +203,47 @@ def test_full_size_config2_properties(ipfa):
     np.testing.assert_allclose(nll_h, nll.cpu().numpy(), rtol=2e-6)
     res_h = ipfa.ctc_forced_align_host(lp_h, tgn, il_h, tl_h, tokens=False)
     assert np.array_equal(res_h.paths, paths) and np.array_equal(res_h.scores, res.scores.cpu().numpy())
+
+
+def test_viterbi_length_buckets(ipfa, monkeypatch):
+    """Large ragged batch (>= 4096 windows): windows whose lattice fits half the launch width run on
+    a half-width instance, decided on the device.  Same paths / scores / tokens as the oracle and as
+    the single-instance launch."""
+    import torch
+    from oracle import ctc as octc
+    n, t, l, v = 4500, 48, 40, 32
+    lp, tg, il, tl = ctc_case(31, n, t, l, v, ragged=True, repeats=True, peaked=True)
+    tl[:7] = [0, 1, 31, 32, 33, 40, 16]   # both sides of the bucket boundary (32 state pairs)
+    il[:7] = t
+    ref_paths, ref_scores, ref_status = octc.ctc_viterbi(lp, tg, il, tl)
+    dev = [_dev(x) for x in (lp, tg, il, tl)]
+    res = ipfa.ctc_forced_align(*dev)
+    _check_viterbi(res, ref_paths, ref_scores, ref_status, il)
+    monkeypatch.setenv("IPFA_NO_BUCKETS", "1")
+    one = ipfa.ctc_forced_align(*dev)
+    monkeypatch.delenv("IPFA_NO_BUCKETS")
+    for name in ("paths", "scores", "tok_start", "tok_end", "tok_score", "total", "status"):
+        assert torch.equal(getattr(res, name), getattr(one, name)), name
+    assert ((tl + 1 <= 32).sum() > 1000) and ((tl + 1 > 32).sum() > 300)
+
+
+def test_alpha_length_buckets(ipfa, monkeypatch):
+    """Kernel (1) on a large ragged batch: two length buckets decided on the device."""
+    import torch
+    from oracle import ctc as octc
+    n, t, l, v = 4300, 40, 40, 32
+    lp, tg, il, tl = ctc_case(32, n, t, l, v, ragged=True, repeats=True)
+    tl[:6] = [0, 1, 31, 32, 33, 40]
+    il[:6] = t
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    dev = [_dev(x) for x in (lp, tg, il, tl)]
+    nll = ipfa.ctc_alpha_nll(*dev)
+    _check_nll(nll.cpu().numpy(), ref)
+    monkeypatch.setenv("IPFA_NO_BUCKETS", "1")
+    one = ipfa.ctc_alpha_nll(*dev)
+    monkeypatch.delenv("IPFA_NO_BUCKETS")
+    _check_nll(one.cpu().numpy(), ref)
+    # the two launch shapes associate the log-sum-exp differently: equal to fp32 rounding
+    fin = torch.isfinite(one)
+    assert torch.equal(torch.isfinite(nll), fin)
+    assert torch.allclose(nll[fin], one[fin], rtol=1e-5, atol=1e-5)
