@@ -10,15 +10,16 @@
 // (:37 -- the anchor state is per file), so every lock-step iteration aligns ONE
 // window of EVERY active file:
 //
-//   sweep_build_kernel    :67-192  per file: skip non-speech rows, pick the clip
-//                                  [anchor or row start, row end), the text/audio
-//                                  proportion checks, text-longer-than-audio
-//                                  (AssertionError :390-402); writes the window's
-//                                  ground-truth column, utterance begins, text lengths
 //   ctcseg fill/backtrace :208-219 all utterance prefixes of every window (ctcseg.cu)
-//   anchor_select_kernel  :221-379 accept / shrink / revert (anchor_select.cu)
-//   sweep_advance_kernel  :231-260 accepted rows -> output slots; new anchor,
-//                                  pending utterances, next row
+//   sweep_tail_kernel     :221-379 accept / shrink / revert (anchor_select.cuh), then
+//                         :231-260 accepted rows -> output slots; new anchor, pending
+//                                  utterances, next row, then the file's NEXT window:
+//                         :67-192  skip non-speech rows, pick the clip [anchor or row
+//                                  start, row end), the text/audio proportion checks,
+//                                  text-longer-than-audio (AssertionError :390-402); writes
+//                                  the window's ground-truth column, utterance begins,
+//                                  text lengths (build_window; sweep_build_kernel runs it
+//                                  alone for the first iteration of a call)
 //
 // Nothing returns to the host between iterations; the host only polls the per-file
 // status words every few iterations.  Two situations hand a file back to host POLICY
@@ -33,7 +34,7 @@
 // utterances" = [utt, row_utt_end[row]).  Its ground-truth column is therefore a slice
 // of the file's token stream `blank, tokens(u0), blank, tokens(u1), ..., blank` behind a
 // leading -1 (prepare_token_list).
-#include "ipfa_common.cuh"
+#include "anchor_select.cuh"
 
 namespace ipfa {
 extern cudaError_t g_last_cuda_error;
@@ -96,11 +97,6 @@ size_t carve(SweepWindows *w, unsigned char *base, int F, int Tmax, int Cmax, in
     return off;
 }
 
-__device__ __forceinline__ double round_decimals(double x, double scale) {  // float(f"{x:.Nf}")
-    if (!(fabs(x) < 1.0e15)) return x;
-    return __ddiv_rn(rint(__dmul_rn(x, scale)), scale);
-}
-
 // get_text_to_audio_proportion (/root/reference/src/utils/alignment_utils.py:84-106):
 // text_length * 0.08 * 3 * sample_rate / audio_length, evaluated left to right in fp64
 __device__ __forceinline__ double text_to_audio(long long text_length, int sample_rate, long long audio_length) {
@@ -112,11 +108,14 @@ __device__ __forceinline__ double text_to_audio(long long text_length, int sampl
 
 constexpr int kBuildThreads = 128;
 
-__global__ void __launch_bounds__(kBuildThreads)
-sweep_build_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ipfa_sweep_state s,
-                   const SweepWindows w, int Tmax, int Cmax, int Kmax) {
-    const int f = blockIdx.x;
+// :67-192 + :390-402 for file f: find the file's next window (or its terminal state) and write the
+// window descriptor.  Called by all threads of a CTA; thread 0 walks the policy, all threads copy
+// the ground-truth column.
+__device__ __forceinline__ void build_window(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p,
+                                             const ipfa_sweep_state &s, const SweepWindows &w, int f, int Tmax,
+                                             int Cmax, int Kmax) {
     __shared__ int sh_active, sh_u0, sh_K, sh_ncols;
+    __syncthreads();
     if (threadIdx.x == 0) {
         int active = 0, u0 = 0, K = 0, n_cols = 0, T = 0, is_last = 0;
         long long f0 = 0;
@@ -241,40 +240,55 @@ sweep_build_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const i
     for (int k = threadIdx.x; k < Kmax; k += kBuildThreads) tl[k] = (k < K) ? c.utt_chars[slot0 + k] : 0;
 }
 
-// :231-260 + the bookkeeping after the candidate loop: one thread per file.
-__global__ void sweep_advance_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p,
-                                     const ipfa_sweep_state s, const SweepWindows w, int Kmax, int step,
-                                     double *__restrict__ out_seg, int32_t *__restrict__ out_info) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= c.n_files) return;
+__global__ void __launch_bounds__(kBuildThreads)
+sweep_build_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ipfa_sweep_state s,
+                   const SweepWindows w, int Tmax, int Cmax, int Kmax) {
+    build_window(c, p, s, w, blockIdx.x, Tmax, Cmax, Kmax);
+}
+
+// The tail of an iteration, one CTA per file: the accept / shrink / revert decision (:221-379,
+// anchor_select_one), the accepted rows and the loop state (:231-260, :388), then the file's NEXT
+// window (build_window) -- one launch instead of three between backtrace and the next fill.
+__global__ void __launch_bounds__(kBuildThreads)
+sweep_tail_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ipfa_sweep_state s,
+                  const SweepWindows w, int Tmax, int Cmax, int Kmax, int step, double *__restrict__ out_seg,
+                  int32_t *__restrict__ out_info) {
+    const int f = blockIdx.x;
     const int K = w.n_utts[f];
-    if (K <= 0) return;  // no window this iteration
-    const int k = w.decision[f * 4 + 0];
-    const int anchor_u = w.decision[f * 4 + 3];
-    const int u0 = s.utt[f];
-    const int64_t slot0 = c.utt_first[f] + u0;
-    const double clip_start = w.clip_start[f];
-    const double penalty = __dmul_rn(2.0, p.threshold);
-    const double *seg = w.seg + ((int64_t)f * Kmax + max(k - 1, 0)) * Kmax * 3;
-    for (int u = 0; u < k; ++u) {
-        double score = round_decimals(seg[u * 3 + 2], 1.0e4);
-        if (c.utt_chars[slot0 + u] < p.short_len) score = __dadd_rn(score, penalty);  // :241
-        double *o = out_seg + (slot0 + u) * 4;
-        o[0] = clip_start;
-        o[1] = round_decimals(seg[u * 3 + 0], 100.0);
-        o[2] = round_decimals(seg[u * 3 + 1], 100.0);
-        o[3] = score;
-        out_info[(slot0 + u) * 2] = step;
-        out_info[(slot0 + u) * 2 + 1] = s.row[f];
+    if (K > 0 && threadIdx.x == 0) {  // the file had a window this iteration
+        const double *seg_w = w.seg + (int64_t)f * Kmax * Kmax * 3;
+        const AnchorDecision d = anchor_select_one(seg_w, w.text_len + (int64_t)f * Kmax, min(K, Kmax), Kmax,
+                                                   w.is_last[f] != 0, p.threshold, p.short_len);
+        const int k = d.accepted;
+        const int u0 = s.utt[f];
+        const int64_t slot0 = c.utt_first[f] + u0;
+        const double clip_start = w.clip_start[f];
+        const double penalty = __dmul_rn(2.0, p.threshold);
+        const double *seg = seg_w + (int64_t)max(k - 1, 0) * Kmax * 3;
+        const int row = s.row[f];
+        for (int u = 0; u < k; ++u) {
+            double score = round_decimals(seg[u * 3 + 2], 1.0e4);
+            if (c.utt_chars[slot0 + u] < p.short_len) score = __dadd_rn(score, penalty);  // :241
+            double *o = out_seg + (slot0 + u) * 4;
+            o[0] = clip_start;
+            o[1] = round_decimals(seg[u * 3 + 0], 100.0);
+            o[2] = round_decimals(seg[u * 3 + 1], 100.0);
+            o[3] = score;
+            out_info[(slot0 + u) * 2] = step;
+            out_info[(slot0 + u) * 2 + 1] = row;
+        }
+        if (d.anchor_u == -1) s.anchor[f] = clip_start;                              // :277, :329
+        else if (d.anchor_u >= 0) s.anchor[f] = __dadd_rn(clip_start, d.anchor);     // :249
+        s.utt[f] = u0 + k;
+        s.exc[f] = 0;  // :388
+        s.row[f] = row + 1;
+        s.n_windows[f] += 1;
+        s.cells[f] += (int64_t)w.in_len[f] * w.n_cols[f];
+        s.frames[f] += w.in_len[f];
+        w.decision[f * 4 + 0] = d.accepted; w.decision[f * 4 + 1] = d.n_iter;
+        w.decision[f * 4 + 2] = d.outcome;  w.decision[f * 4 + 3] = d.anchor_u;
     }
-    if (anchor_u == -1) s.anchor[f] = clip_start;                                  // :277, :329
-    else if (anchor_u >= 0) s.anchor[f] = __dadd_rn(clip_start, w.anchor_rel[f]);  // :249
-    s.utt[f] = u0 + k;
-    s.exc[f] = 0;  // :388
-    s.row[f] += 1;
-    s.n_windows[f] += 1;
-    s.cells[f] += (int64_t)w.in_len[f] * w.n_cols[f];
-    s.frames[f] += w.in_len[f];
+    build_window(c, p, s, w, f, Tmax, Cmax, Kmax);
 }
 
 }  // namespace
@@ -312,19 +326,18 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
     carve(&w, static_cast<unsigned char *>(workspace), F, Tmax, Cmax, Kmax, c.V);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const ipfa_sweep_params p = *params;
+    // the window of every file for the first iteration (idempotent: the tail of the previous call
+    // already built it from the same state)
+    sweep_build_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax);
+    ++g_launch_count;
     for (int i = 0; i < n_steps; ++i) {
-        sweep_build_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax);
-        ++g_launch_count;
         int rc = ctcseg_run(c.lp, w.win_off, 0, c.stride_t, w.in_len, w.gt, Cmax, w.n_cols, w.utt_begin, w.n_utts,
                             F, Tmax, Cmax, Kmax, c.V, c.blank, p.index_duration, p.score_len,
                             p.seg_flags | IPFA_SEG_ALL_PREFIXES, w.seg, w.term_t, nullptr, nullptr, nullptr,
                             w.win_status, w.seg_ws, w.seg_ws_bytes, stream);
         if (rc) return rc;
-        rc = ipfa_anchor_select_device(w.seg, w.n_utts, w.text_len, w.is_last, F, Kmax, p.threshold,
-                                       p.short_len, w.decision, w.anchor_rel, stream);
-        if (rc) return rc;
-        sweep_advance_kernel<<<(F + 127) / 128, 128, 0, st>>>(c, p, s, w, Kmax, first_step + i, out_seg,
-                                                              out_info);
+        sweep_tail_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax, first_step + i, out_seg,
+                                                       out_info);
         ++g_launch_count;
     }
     cudaError_t e = cudaGetLastError();
