@@ -226,7 +226,8 @@ int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_off, int64_t 
  *                window >= Tmax makes this the full-table algorithm for such tasks.
  * For T <= window and gt_cols == 1 the result equals ipfa_ctcseg_device's.
  * ------------------------------------------------------------------------- */
-size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window, int gt_cols);
+size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window, int gt_cols,
+                                            int flags);
 int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_off, int64_t stride_n, int64_t stride_t,
                                 const int32_t *in_len, const int32_t *gt, int64_t gt_stride,
                                 const int32_t *n_cols, const int32_t *utt_begin, const int32_t *n_utts,

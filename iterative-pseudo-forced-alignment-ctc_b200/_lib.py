@@ -50,7 +50,7 @@ _SIGNATURES = {
                                          c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_i,
                                          c_void, c_void, c_void, c_void, c_void, c_void,
                                          c_void, c_sz, c_void]),
-    "ipfa_ctcseg_windowed_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i]),
+    "ipfa_ctcseg_windowed_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
     "ipfa_ctcseg_windowed_device": (c_i, [c_void, c_void, c_i64, c_i64, c_void, c_void, c_i64, c_void, c_void,
                                           c_void, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_i, c_i, c_i,
                                           c_void, c_void, c_void, c_void, c_void, c_void,

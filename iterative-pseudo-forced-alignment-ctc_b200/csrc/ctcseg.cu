@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
 
     if (kslot == 0 && lane == 0) prm.status_out[w] = (NC > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
-    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
 
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
@@ -609,10 +609,12 @@ constexpr int kWinThreads = 256;
 
 __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const SegWinParams prm) {
     const int prob = blockIdx.x;
-    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int PP = (prm.flags & IPFA_SEG_ALL_PREFIXES) ? prm.Kmax : 1;  // problems per window
+    const int w = prob / PP;
+    const int kslot = (PP > 1) ? prob - w * PP : max(0, min(prm.n_utts[w], prm.Kmax)) - 1;
     const int K = max(0, min(prm.n_utts[w], prm.Kmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
-    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int T = min(prm.in_len[w], prm.Tmax);
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int NC = min(ub[kslot + 1] + 1, min(prm.n_cols[w], prm.Cmax));  // columns of this prefix
@@ -739,14 +741,16 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
 __global__ void __launch_bounds__(128) ctcseg_windowed_backtrace_kernel(const SegWinParams prm) {
     const int lane = threadIdx.x & 31;
     const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (prob >= prm.N * prm.Kmax) return;
-    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int PP = (prm.flags & IPFA_SEG_ALL_PREFIXES) ? prm.Kmax : 1;  // problems per window
+    if (prob >= prm.N * PP) return;
+    const int w = prob / PP;
+    const int kslot = (PP > 1) ? prob - w * PP : max(0, min(prm.n_utts[w], prm.Kmax)) - 1;
     const int K = max(0, min(prm.n_utts[w], prm.Kmax));
     const int T = min(prm.in_len[w], prm.Tmax);
     const int NCw = max(0, min(prm.n_cols[w], prm.Cmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
-    if (kslot == 0 && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
-    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    if ((PP == 1 || kslot == 0) && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
     const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
@@ -841,10 +845,12 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_multi_fill_kernel(const Se
     const SegWinParams &prm = mp.w;
     const int G = mp.G;
     const int prob = blockIdx.x;
-    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int PP = (prm.flags & IPFA_SEG_ALL_PREFIXES) ? prm.Kmax : 1;  // problems per window
+    const int w = prob / PP;
+    const int kslot = (PP > 1) ? prob - w * PP : max(0, min(prm.n_utts[w], prm.Kmax)) - 1;
     const int K = max(0, min(prm.n_utts[w], prm.Kmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
-    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int T = min(prm.in_len[w], prm.Tmax);
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int NC = min(ub[kslot + 1] + 1, min(prm.n_cols[w], prm.Cmax));
@@ -989,14 +995,16 @@ __global__ void __launch_bounds__(128) ctcseg_multi_backtrace_kernel(const SegMu
     const int G = mp.G;
     const int lane = threadIdx.x & 31;
     const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (prob >= prm.N * prm.Kmax) return;
-    const int w = prob / prm.Kmax, kslot = prob - w * prm.Kmax;
+    const int PP = (prm.flags & IPFA_SEG_ALL_PREFIXES) ? prm.Kmax : 1;  // problems per window
+    if (prob >= prm.N * PP) return;
+    const int w = prob / PP;
+    const int kslot = (PP > 1) ? prob - w * PP : max(0, min(prm.n_utts[w], prm.Kmax)) - 1;
     const int K = max(0, min(prm.n_utts[w], prm.Kmax));
     const int T = min(prm.in_len[w], prm.Tmax);
     const int NCw = max(0, min(prm.n_cols[w], prm.Cmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
-    if (kslot == 0 && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
-    if (kslot >= K || (!all_prefixes && kslot != K - 1)) return;
+    if ((PP == 1 || kslot == 0) && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
     const float *lp = prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n);
@@ -1161,7 +1169,7 @@ int ctcseg_run(const float *lp, const int64_t *win_off, int64_t stride_n, int64_
         !status_out || !workspace || N < 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || V <= 0 || blank < 0 ||
         blank >= V || score_len <= 0 || !(index_duration > 0.0))
         return IPFA_ERR_INVALID_ARG;
-    if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode: not built yet
+    if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode: ipfa_ctcseg_windowed_device
     SegShape s;
     if (!pick_seg_shape(Cmax, N, V, &s)) return IPFA_ERR_UNSUPPORTED;
     if (workspace_bytes < ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V)) return IPFA_ERR_WORKSPACE;
@@ -1251,17 +1259,17 @@ extern "C" int ipfa_ctcseg_windows_device(const float *lp, const int64_t *win_of
 static size_t win_words(int window) { return (size_t)((window + 31) / 32); }
 
 extern "C" size_t ipfa_ctcseg_windowed_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int window,
-                                                       int gt_cols) {
+                                                       int gt_cols, int flags) {
     if (N <= 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || window <= 0 || gt_cols <= 0) return 256;
-    const size_t P = (size_t)N * Kmax;
+    const size_t P = (size_t)N * ((flags & IPFA_SEG_ALL_PREFIXES) ? Kmax : 1);  // one fill per aligned prefix
     const size_t W = (size_t)(window < Tmax ? window : Tmax);
     size_t b = pad256(P * ((size_t)gt_cols + 1) * W * 4);  // the last gt_cols + 1 table columns
     b += (gt_cols == 1) ? pad256(P * (size_t)Cmax * win_words((int)W) * 4)   // 1-bit transitions
                         : pad256(P * (size_t)Cmax * W);                      // 1-byte transitions
     b += pad256(P * (size_t)Cmax * 4);                  // offsets
     b += pad256(P * 4);                                 // terminal rows
-    b += pad256(P * (size_t)Cmax * 4);                  // timing scratch
-    b += pad256(P * (size_t)Tmax * 4);                  // char_prob scratch
+    b += pad256((size_t)N * Kmax * (size_t)Cmax * 4);   // timing scratch (indexed by output slot)
+    b += pad256((size_t)N * Kmax * (size_t)Tmax * 4);   // char_prob scratch
     return b + 256;
 }
 
@@ -1280,10 +1288,10 @@ extern "C" int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_o
         blank >= V || score_len <= 0 || !(index_duration > 0.0) || window <= 0 || gt_cols <= 0)
         return IPFA_ERR_INVALID_ARG;
     if (gt_cols > kMaxGtCols) return IPFA_ERR_UNSUPPORTED;
-    if (workspace_bytes < ipfa_ctcseg_windowed_workspace_bytes(N, Tmax, Cmax, Kmax, window, gt_cols))
+    if (workspace_bytes < ipfa_ctcseg_windowed_workspace_bytes(N, Tmax, Cmax, Kmax, window, gt_cols, flags))
         return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t P = (size_t)N * Kmax;
+    const size_t P = (size_t)N * ((flags & IPFA_SEG_ALL_PREFIXES) ? Kmax : 1);
     const int W = window < Tmax ? window : Tmax;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     SegWinParams p{};
@@ -1297,7 +1305,7 @@ extern "C" int ipfa_ctcseg_windowed_device(const float *lp, const int64_t *win_o
     ws += (gt_cols == 1) ? pad256(P * (size_t)Cmax * win_words(W) * 4) : pad256(P * (size_t)Cmax * (size_t)W);
     p.offsets = reinterpret_cast<int32_t *>(ws);        ws += pad256(P * (size_t)Cmax * 4);
     p.term = reinterpret_cast<int32_t *>(ws);           ws += pad256(P * 4);
-    int32_t *timing_scratch = reinterpret_cast<int32_t *>(ws); ws += pad256(P * (size_t)Cmax * 4);
+    int32_t *timing_scratch = reinterpret_cast<int32_t *>(ws); ws += pad256((size_t)N * Kmax * (size_t)Cmax * 4);
     float *cprob_scratch = reinterpret_cast<float *>(ws);
     p.seg_out = seg_out; p.term_t_out = term_t_out;
     p.timing = timing_out ? timing_out : timing_scratch;

@@ -249,7 +249,7 @@ def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blan
     L = lib()
     if window is not None:
         with torch.cuda.device(dev):
-            ws_bytes = L.ipfa_ctcseg_windowed_workspace_bytes(n, t, cmax, kmax, int(window), gt_cols)
+            ws_bytes = L.ipfa_ctcseg_windowed_workspace_bytes(n, t, cmax, kmax, int(window), gt_cols, int(flags))
             ws = _workspace(ws_bytes, dev)
             rc = L.ipfa_ctcseg_windowed_device(
                 _ptr(lp), None, sn, st, _ptr(in_len), _ptr(gt), gt.stride(0), _ptr(n_cols), _ptr(utt_begin),
