@@ -633,6 +633,8 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
     __shared__ float s_sw[kWinTile], s_e[kWinTile], s_eg[kWinTile], s_x[kWinTile + 1];
     __shared__ int s_off, s_offsum, s_arg;
     __shared__ float s_max, s_carry;
+    __shared__ float s_rv[kWinThreads / 32];
+    __shared__ int s_ri[kWinThreads / 32];
 
     const float mean_offset = (float)(T - W) / (float)NC;
     const int higher_offset = (int)ceilf(mean_offset);
@@ -662,7 +664,8 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
         uint32_t *bits_c = bits + (int64_t)c * prm.words;
         for (int t0 = 0; t0 < W; t0 += kWinTile) {
             const int rows = min(kWinTile, W - t0);
-            // phase A: switch candidates and stay emissions of the tile
+            // phase A: switch candidates and stay emissions of the tile (loads of 4 rows in flight)
+#pragma unroll 4
             for (int r = tid; r < rows; r += kWinThreads) {
                 const int t = t0 + r;
                 const float *row = lp + (int64_t)(t + offset_sum) * prm.stride_t;
@@ -679,44 +682,48 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
                 s_sw[r] = sw; s_e[r] = e; s_eg[r] = eg;
             }
             __syncthreads();
-            // phase B: the serial chain x_t = max(switch_t, x_{t-1} + e_t), first arg-max
+            // phase B: the serial chain x_t = max(switch_t, x_{t-1} + e_t).  Only FADD -> FMNMX sits on
+            // it: operands are fetched 8 rows at a time, the arg-max is left to phase C.
             if (tid == 0) {
                 float x = (t0 == 0) ? 0.0f : s_carry;
-                float best = s_max;
-                int arg = s_arg;
+                s_x[0] = x;  // x_{t0-1}
                 int r = 0;
                 if (t0 == 0) {
-                    if (c == 0) {
-                        x = 0.0f;        // table[0, 0] = 0, not part of the arg-max loop (it starts at t = 1)
-                    } else {
-                        x = kProbMax;    // t - 1 < 0: switch and stay are both prob_max
-                        arg = 0; best = x;
-                    }
+                    x = (c == 0) ? 0.0f : kProbMax;  // table[0,0] = 0; t - 1 < 0: both candidates are prob_max
                     s_x[1] = x;
                     r = 1;
                 }
-                for (; r < rows; ++r) {
-                    float stay;
-                    if (c == 0) stay = preamble_cost_zero ? 0.0f : x + s_e[r];
-                    else stay = x + s_e[r];
-                    x = fmaxf(s_sw[r], stay);
-                    s_x[r + 1] = x;
-                    if (arg == -1 || best < x) { best = x; arg = t0 + r; }
+                if (c == 0 && preamble_cost_zero) {
+                    for (; r < rows; ++r) { x = fmaxf(s_sw[r], 0.0f); s_x[r + 1] = x; }
+                } else {
+                    constexpr int UB = 8;
+                    for (; r + UB <= rows; r += UB) {
+                        float a[UB], e[UB];
+#pragma unroll
+                        for (int j = 0; j < UB; ++j) { a[j] = s_sw[r + j]; e[j] = s_e[r + j]; }
+#pragma unroll
+                        for (int j = 0; j < UB; ++j) { x = fmaxf(a[j], __fadd_rn(x, e[j])); a[j] = x; }
+#pragma unroll
+                        for (int j = 0; j < UB; ++j) s_x[r + 1 + j] = a[j];
+                    }
+                    for (; r < rows; ++r) { x = fmaxf(s_sw[r], __fadd_rn(x, s_e[r])); s_x[r + 1] = x; }
                 }
-                s_x[0] = (t0 == 0) ? 0.0f : s_carry;  // x_{t0-1}
                 s_carry = x;
-                s_max = best;
-                s_arg = arg;
             }
             __syncthreads();
             // phase C: the column goes to the workspace; the tolerance test of the reference's
-            // backtrace, |stay_prob - est_stay| > |switch_prob - est_switch| -> switch, as one bit
+            // backtrace, |stay_prob - est_stay| > |switch_prob - est_switch| -> switch, as one bit;
+            // first arg-max of the tile (strict '<' keeps the earliest row)
+            float bv = -__builtin_huge_valf();
+            int bi = 0x7fffffff;
+#pragma unroll 2
             for (int r = tid; r < ((rows + 31) & ~31); r += kWinThreads) {
                 const int t = t0 + r;
                 bool sw_bit = false;
                 if (r < rows) {
                     const float x = s_x[r + 1];
                     cur[t] = x;
+                    if (!(c == 0 && t == 0) && bv < x) { bv = x; bi = t; }  // column 0's loop starts at t = 1
                     const int tp = t - 1 + offset;
                     if (c > 0 && t > 0 && tp >= 0 && tp < W) {
                         const float eg = s_eg[r];
@@ -728,6 +735,19 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
                 }
                 const uint32_t word = __ballot_sync(0xffffffffu, sw_bit);
                 if ((tid & 31) == 0 && r < rows) bits_c[t >> 5] = word;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if ((tid & 31) == 0) { s_rv[tid >> 5] = bv; s_ri[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 1; q < kWinThreads / 32; ++q)
+                    if (s_rv[q] > bv || (s_rv[q] == bv && s_ri[q] < bi)) { bv = s_rv[q]; bi = s_ri[q]; }
+                if (bi != 0x7fffffff && (s_arg == -1 || s_max < bv)) { s_max = bv; s_arg = bi; }
             }
             __syncthreads();
         }
