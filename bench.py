@@ -683,10 +683,21 @@ def gpu_arm(args):
         # the step's kernels average ms_per_step of device time per step
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         legs = cpu_leg(wl, budget_s=12.0)
-        bound_note = {"alpha": "T-serial log-sum-exp recursion: MUFU/issue bound (4 MUFU per state pair and frame), "
-                               "not HBM bound -- DESIGN.md 5.1",
+        bound_note = {"alpha": "T-serial log-sum-exp recursion walked from both ends: MUFU bound (4 MUFU per state pair "
+                               "and frame), not HBM bound -- DESIGN.md 5.1",
                       "viterbi": "T-serial max-plus recursion + latency-bound backtrace: issue bound -- DESIGN.md 5.2",
                       "seg": "T-serial max-plus recursion with a CTA barrier per frame -- DESIGN.md 5.3"}[wl.kind]
+        extra_roof = {}
+        if wl.kind == "alpha" and wl.v <= 64:
+            # the bound that actually binds this kernel: 4 MUFU warp-instructions per
+            # 32 state pairs and frame, 8 cycles each per SM sub-partition (profiles/microbench_r01.txt)
+            il = sets[0][2].cpu().numpy().astype(np.int64)
+            tl = sets[0][3].cpu().numpy().astype(np.int64)
+            pair_warps = np.ceil((tl + 1) / 32.0)
+            mufu_cycles = float((il * pair_warps).sum()) * 4 * 8
+            clk = (sampler.result().get("sm_mhz") or 1965.0) * 1e6
+            floor_ms = mufu_cycles / (148 * 4) / clk * 1e3
+            extra_roof = {"mufu_floor_ms": floor_ms, "frac_of_mufu_floor": floor_ms / ms_per_step}
         line = {
             "metric": "aligned_audio_hours_per_s", "value": world * hours / (ms_per_step * 1e-3),
             "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -700,7 +711,7 @@ def gpu_arm(args):
                          "frac": achieved / peak, "traffic": measured_traffic(args.workload),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
-                         "kernels_per_step": launches / max(args.steps, 1), "note": bound_note},
+                         "kernels_per_step": launches / max(args.steps, 1), "note": bound_note, **extra_roof},
             "cpu_baseline": cpu_baseline_obj(legs, "same shapes, same generator"),
             "e2e": {"value": world * hours / (e2e_ms * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": wl.api},

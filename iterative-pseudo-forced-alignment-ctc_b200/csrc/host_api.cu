@@ -71,7 +71,9 @@ int upload_lp(float *dst, const float *src, int64_t stride_n, int N, int64_t per
 }
 
 // Windows per chunk of the host pipeline: H2D of chunk i+1 overlaps the kernels of chunk i.
-// ~16 MB of emissions per chunk keeps every copy at full PCIe rate and every launch wide.
+// ~16 MB of emissions per chunk: copies run at 53.8 of the 55.4 GB/s this box reaches with one 131 MB
+// copy (tools/exp_h2d.py) and only the last chunk's kernels are exposed; 32 MB chunks copy at 54.7 GB/s
+// but expose twice the kernel tail -- measured 2.63 ms against 2.61 ms per 131 MB step.
 int windows_per_chunk(int N, int64_t per_window_floats) {
     const int64_t bytes = per_window_floats * 4;
     int64_t c = bytes > 0 ? (16LL << 20) / bytes : N;
