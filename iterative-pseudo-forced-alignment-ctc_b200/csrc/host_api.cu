@@ -131,18 +131,27 @@ extern "C" int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t st
     int32_t *d_tl = g_arena.take<int32_t>(N);
     float *d_out = g_arena.take<float>(N);
     void *d_ws = g_arena.take<unsigned char>(ws);
-    if (Lmax > 0)
-        IPFA_CUDA(cudaMemcpy2DAsync(d_tg, (size_t)Lmax * 4, targets, (size_t)tgt_stride * 4, (size_t)Lmax * 4,
-                                    N, cudaMemcpyHostToDevice, st));
+    if (Lmax > 0) {
+        if (tgt_stride == Lmax)
+            IPFA_CUDA(cudaMemcpyAsync(d_tg, targets, (size_t)N * Lmax * 4, cudaMemcpyHostToDevice, st));
+        else
+            IPFA_CUDA(cudaMemcpy2DAsync(d_tg, (size_t)Lmax * 4, targets, (size_t)tgt_stride * 4, (size_t)Lmax * 4,
+                                        N, cudaMemcpyHostToDevice, st));
+    }
     IPFA_CUDA(cudaMemcpyAsync(d_il, in_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_tl, tgt_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     const int C = windows_per_chunk(N, per_window);
     cudaStream_t cs = g_arena.compute;
-    for (int w0 = 0, ci = 0; w0 < N; w0 += C, ++ci) {
+    // every copy is queued before the first kernel launch, so the copy engine never waits for the host
+    int n_chunks = 0;
+    for (int w0 = 0; w0 < N; w0 += C, ++n_chunks) {
         const int n = (N - w0 < C) ? (N - w0) : C;
         rc = upload_lp(d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
         if (rc) return rc;
-        IPFA_CUDA(cudaEventRecord(g_arena.ready[ci], st));
+        IPFA_CUDA(cudaEventRecord(g_arena.ready[n_chunks], st));
+    }
+    for (int w0 = 0, ci = 0; w0 < N; w0 += C, ++ci) {
+        const int n = (N - w0 < C) ? (N - w0) : C;
         IPFA_CUDA(cudaStreamWaitEvent(cs, g_arena.ready[ci], 0));
         rc = ipfa_ctc_alpha_device(d_lp + (int64_t)w0 * per_window, per_window, V, d_tg + (int64_t)w0 * Lmax, Lmax,
                                    d_il + w0, d_tl + w0, n, Tmax, Lmax, V, blank, d_out + w0, d_ws, ws, cs);
