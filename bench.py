@@ -415,6 +415,7 @@ def c5_arm(args):
     specs, minutes, mine = _c5_specs(args.hours, world, rank)
     files = [sw_mod.SweepFile(s.file_id, s.audio_path, sweep_corpus.emissions(s, dev, seed=i), s.n_samples, s.rows)
              for i, s in zip(mine, specs)]
+    files = sw_mod.sort_longest_first(files)
     corpus = sw_mod.SweepCorpus(files, stub.CharTokenizer())
     for f in files:
         f.lpz = None  # the corpus holds the only copy

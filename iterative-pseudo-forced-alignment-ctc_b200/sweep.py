@@ -127,6 +127,12 @@ def pack_files(files, tokenizer, blank=0):
     return {k: np.asarray(v, dtype=dtypes.get(k, np.int32)) for k, v in a.items()}, all_texts
 
 
+def sort_longest_first(files):
+    """Files ordered by emission frames, longest first: the anchor loop of a file is a serial chain,
+    so the longest files set the duration of the sweep and go into the smallest lock-step groups."""
+    return sorted(files, key=lambda f: -int(f.lpz.shape[0]))
+
+
 class SweepCorpus:
     """Files packed into the device arrays of ``ipfa_sweep_corpus``; emissions resident in HBM."""
 
@@ -236,9 +242,13 @@ class AnchorSweep:
     # same corpus / state with the per-file pointers shifted), so one file's long window only
     # holds back its own group and the groups' kernels overlap on the GPU.
     def _group_ranges(self):
+        """Contiguous file ranges of growing size (1 : 2 : 3 : ...).  With the files ordered longest
+        first (:func:`sort_longest_first`) the files that set the sweep's critical path share their
+        lock step with few others."""
         n = len(self.corpus.files)
         g = max(1, min(self.groups, n))
-        edges = [round(i * n / g) for i in range(g + 1)]
+        total = g * (g + 1) // 2
+        edges = [round(n * (i * (i + 1) // 2) / total) for i in range(g + 1)]
         return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
 
     _PER_FILE_CORPUS = ("file_frame0", "file_frames", "file_samples", "row_first", "utt_first", "file_tok0")
@@ -437,6 +447,9 @@ def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, thre
         frames.append(fixed)
         vads.append(vad_file_df)
         lengths.append(real_length)
+    order = sorted(range(len(files)), key=lambda i: -int(files[i].lpz.shape[0]))  # longest first
+    files = [files[i] for i in order]
+    frames, vads, lengths = ([x[i] for i in order] for x in (frames, vads, lengths))
     corpus = SweepCorpus(files, asr_model.tokenizer, blank=aligner.config.blank)
     fs = int(asr_model.hparams.sample_rate)
     sweep = AnchorSweep(corpus, index_duration=samples_to_frames_ratio / fs,
@@ -447,4 +460,6 @@ def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, thre
                         scoring_length=aligner.config.score_min_mean_over_L, seg_flags=aligner.config.flags,
                         groups=groups)
     status = sweep.run(recalc_fn=dataframe_recalc(frames, vads, lengths))
-    return sweep.file_rows(), status
+    rows = sweep.file_rows()
+    inverse = {src: pos for pos, src in enumerate(order)}  # back to the order of `jobs`
+    return [rows[inverse[i]] for i in range(len(order))], np.asarray([status[inverse[i]] for i in range(len(order))])
