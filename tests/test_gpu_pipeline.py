@@ -2,7 +2,6 @@
 (BASELINE configs[0]) and the word-level / search-on-speech row loops, CUDA path vs the
 same host glue driven by the CPU oracle (oracle/ctcseg + oracle/anchor)."""
 import importlib
-import os
 
 import numpy as np
 import pandas as pd

@@ -5,7 +5,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 import ipfa_b200 as ipfa
-from ipfa_b200 import ops
 
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 dev = torch.device("cuda:0")

@@ -3,7 +3,6 @@ Run on the GPU box:  python tools/tune_shapes.py [c2 c2v c3 c4]"""
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
