@@ -317,7 +317,9 @@ typedef struct ipfa_sweep_params {
 /* out_seg [slots][4] fp64: (clip_start, start, end, score) of every accepted utterance --
  * start/end rounded to 0.01 s and score to 1e-4 like the `str(task)` round trip (:219-230), the
  * short-utterance penalty already added (:241); absolute times are clip_start + start / end.
- * out_info [slots][2] int32: (iteration that accepted the utterance, file-relative TSV row that was
+ * out_info [slots][2] int32: (ordinal, within its file, of the window that accepted the utterance --
+ * nothing in the launch depends on the call count, so a captured CUDA graph of this call can be
+ * replayed; `first_step` is informational -- , file-relative TSV row that was
  * being aligned -- the row whose Channel / Speaker_ID / Database the result row carries, :258);
  * the caller initialises it to -1.
  * Runs n_steps iterations numbered first_step...; status words say when every file is finished. */

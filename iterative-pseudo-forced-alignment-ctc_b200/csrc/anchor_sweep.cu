@@ -251,7 +251,7 @@ sweep_build_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const i
 // window (build_window) -- one launch instead of three between backtrace and the next fill.
 __global__ void __launch_bounds__(kBuildThreads)
 sweep_tail_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ipfa_sweep_state s,
-                  const SweepWindows w, int Tmax, int Cmax, int Kmax, int step, double *__restrict__ out_seg,
+                  const SweepWindows w, int Tmax, int Cmax, int Kmax, double *__restrict__ out_seg,
                   int32_t *__restrict__ out_info) {
     const int f = blockIdx.x;
     const int K = w.n_utts[f];
@@ -274,7 +274,7 @@ sweep_tail_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ip
             o[1] = round_decimals(seg[u * 3 + 0], 100.0);
             o[2] = round_decimals(seg[u * 3 + 1], 100.0);
             o[3] = score;
-            out_info[(slot0 + u) * 2] = step;
+            out_info[(slot0 + u) * 2] = s.n_windows[f];  // ordinal of this window in its file
             out_info[(slot0 + u) * 2 + 1] = row;
         }
         if (d.anchor_u == -1) s.anchor[f] = clip_start;                              // :277, :329
@@ -306,6 +306,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
                                       const ipfa_sweep_state *state, double *out_seg, int32_t *out_info,
                                       int first_step, int n_steps, int Tmax, int Cmax, int Kmax,
                                       void *workspace, size_t workspace_bytes, void *stream) {
+    (void)first_step;
     if (!corpus || !params || !state || !out_seg || !out_info || !workspace || n_steps < 0 || Tmax <= 0 ||
         Cmax <= 1 || Kmax <= 0)
         return IPFA_ERR_INVALID_ARG;
@@ -336,8 +337,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
                             p.seg_flags | IPFA_SEG_ALL_PREFIXES, w.seg, w.term_t, nullptr, nullptr, nullptr,
                             w.win_status, w.seg_ws, w.seg_ws_bytes, stream);
         if (rc) return rc;
-        sweep_tail_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax, first_step + i, out_seg,
-                                                       out_info);
+        sweep_tail_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax, out_seg, out_info);
         ++g_launch_count;
     }
     cudaError_t e = cudaGetLastError();

@@ -165,17 +165,20 @@ class SweepCorpus:
 
 
 class AnchorSweep:
-    """Runs the anchor loop of every file of a :class:`SweepCorpus` on its device."""
+    """Runs the anchor loop of every file of a :class:`SweepCorpus` on its device.
+
+    ``groups``: independent lock-step groups of files, each on its own stream with its own launch
+    capacity; ``use_graphs``: the launches of ``steps_per_poll`` iterations of all groups are
+    captured once into a CUDA graph and replayed (the sweep is a chain of short dependent kernels,
+    so with many groups the host's launch rate would otherwise bound it)."""
 
     def __init__(self, corpus, index_duration, samples_to_frames_ratio, frame_shift=None, sample_rate=16000,
                  threshold=-2.0, short_utterance_len=30, max_window_size=70.0, window_to_stop=500.0,
                  min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, scoring_length=30, seg_flags=2,
-                 capacity=None, groups=1):
+                 capacity=None, groups=1, use_graphs=True):
         self.corpus = corpus
         self.groups = int(groups)
-        self._streams = None
-        dev = corpus.device
-        n = len(corpus.files)
+        self.use_graphs = bool(use_graphs)
         p = _Params()
         p.threshold, p.max_window_size, p.window_to_stop = threshold, max_window_size, window_to_stop
         p.min_text_to_audio_prop = min_text_to_audio_prop
@@ -185,38 +188,47 @@ class AnchorSweep:
         p.frame_shift = int(frame_shift if frame_shift is not None else round(samples_to_frames_ratio))
         p.score_len, p.seg_flags = scoring_length, seg_flags
         self.params = p
+        self.state = None
         self.reset()
-        self.steps = 0
-        self.capacity = list(capacity) if capacity else self._initial_capacity()
-        self._ws = None
-        self._ws_cap = None
+        self.ranges = self._group_ranges()
+        first = list(capacity) if capacity else None
+        self.capacities = [list(first) if first else self._initial_capacity(lo, hi) for lo, hi in self.ranges]
+        self._ws = [None] * len(self.ranges)
+        self._ws_cap = [None] * len(self.ranges)
+        dev = corpus.device
+        self._streams = [torch.cuda.Stream(dev) for _ in self.ranges] if len(self.ranges) > 1 else None
+        self._graph, self._graph_key, self._graph_launches = None, None, 0
+        self.kernel_launches = 0
+
+    @property
+    def capacity(self):
+        """Largest (Tmax, Cmax, Kmax) over the groups."""
+        return [max(c[i] for c in self.capacities) for i in range(3)]
 
     def reset(self):
-        """Initial loop state of every file (:36-43) and empty outputs."""
+        """Initial loop state of every file (:36-43) and empty outputs (in place: graphs keep pointers)."""
         dev, n, nan = self.corpus.device, len(self.corpus.files), float("nan")
-        self.state = dict(
-            row=torch.zeros(n, dtype=torch.int32, device=dev), utt=torch.zeros(n, dtype=torch.int32, device=dev),
-            anchor=torch.full((n,), nan, dtype=torch.float64, device=dev),
-            prop=torch.zeros(n, dtype=torch.float64, device=dev),
-            next_ns=torch.zeros(n, dtype=torch.int32, device=dev),
-            follow_start=torch.full((n,), nan, dtype=torch.float64, device=dev),
-            exc=torch.zeros(n, dtype=torch.int32, device=dev),
-            status=torch.zeros(n, dtype=torch.int32, device=dev),
-            need=torch.zeros((n, 3), dtype=torch.int32, device=dev),
-            recalc_row=torch.full((n,), -1, dtype=torch.int32, device=dev),
-            n_windows=torch.zeros(n, dtype=torch.int32, device=dev),
-            cells=torch.zeros(n, dtype=torch.int64, device=dev),
-            frames=torch.zeros(n, dtype=torch.int64, device=dev))
-        self.out_seg = torch.zeros((self.corpus.n_slots, 4), dtype=torch.float64, device=dev)
-        self.out_info = torch.full((self.corpus.n_slots, 2), -1, dtype=torch.int32, device=dev)
+        if self.state is None:
+            i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
+            f64 = lambda: torch.zeros(n, dtype=torch.float64, device=dev)
+            self.state = dict(row=i32(n), utt=i32(n), anchor=f64(), prop=f64(), next_ns=i32(n), follow_start=f64(),
+                              exc=i32(n), status=i32(n), need=i32(n, 3), recalc_row=i32(n), n_windows=i32(n),
+                              cells=torch.zeros(n, dtype=torch.int64, device=dev),
+                              frames=torch.zeros(n, dtype=torch.int64, device=dev))
+            self.out_seg = torch.zeros((self.corpus.n_slots, 4), dtype=torch.float64, device=dev)
+            self.out_info = torch.zeros((self.corpus.n_slots, 2), dtype=torch.int32, device=dev)
+        for k, t in self.state.items():
+            t.fill_(nan if k in ("anchor", "follow_start") else (-1 if k == "recalc_row" else 0))
+        self.out_seg.zero_()
+        self.out_info.fill_(-1)
         self.steps = 0
 
-    def _initial_capacity(self):
-        """(Tmax, Cmax, Kmax) that holds every single row's own window."""
+    def _initial_capacity(self, lo, hi):
+        """(Tmax, Cmax, Kmax) that holds every single row's own window of files [lo, hi)."""
         c, p = self.corpus, self.params
         h = c.host
         t_max, c_max, k_max = 64, 16, 2
-        for f in range(len(c.files)):
+        for f in range(lo, hi):
             u_prev = 0
             for r in range(h["row_first"][f], h["row_first"][f + 1]):
                 if h["row_type"][r] == 1:
@@ -230,17 +242,12 @@ class AnchorSweep:
         # head-room for pending utterances and anchors that lag behind the row start
         return [min(8000, int(t_max * 1.5) + 8), int(c_max * 2) + 8, int(k_max * 2) + 2]
 
-    def _state_struct(self):
-        s = _State()
-        for k, t in self.state.items():
-            setattr(s, k, t.data_ptr())
-        return s
-
     # ------------------------------------------------------------------ groups
-    # Lock step makes every iteration as long as its longest window.  Files are therefore cut into
-    # `groups` contiguous ranges that iterate independently on their own streams (a group is the
-    # same corpus / state with the per-file pointers shifted), so one file's long window only
-    # holds back its own group and the groups' kernels overlap on the GPU.
+    # Lock step makes every iteration as long as its longest window, and one launch is sized for
+    # the widest window in flight.  Files are therefore cut into `groups` contiguous ranges that
+    # iterate independently on their own streams with their own capacity (a group is the same
+    # corpus / state with the per-file pointers shifted), so one file's long window only holds back
+    # its own group and the groups' kernels overlap on the GPU.
     def _group_ranges(self):
         """Contiguous file ranges of growing size (1 : 2 : 3 : ...).  With the files ordered longest
         first (:func:`sort_longest_first`) the files that set the sweep's critical path share their
@@ -265,44 +272,64 @@ class AnchorSweep:
             setattr(ss, k, t.data_ptr() + lo * t.stride(0) * t.element_size())
         return cs, ss
 
-    def _workspaces(self):
-        cap = tuple(self.capacity)
-        if self._ws_cap != cap:
-            self._ws = None
-            self._ws = []
-            for lo, hi in self._group_ranges():
-                nbytes = lib().ipfa_sweep_workspace_bytes(hi - lo, cap[0], cap[1], cap[2], self.corpus.V)
-                self._ws.append(torch.empty(nbytes, dtype=torch.uint8, device=self.corpus.device))
-            self._ws_cap = cap
-        return self._ws
+    def _workspace(self, g):
+        cap = tuple(self.capacities[g])
+        if self._ws_cap[g] != cap:
+            lo, hi = self.ranges[g]
+            nbytes = lib().ipfa_sweep_workspace_bytes(hi - lo, cap[0], cap[1], cap[2], self.corpus.V)
+            self._ws[g] = None
+            self._ws[g] = torch.empty(nbytes, dtype=torch.uint8, device=self.corpus.device)
+            self._ws_cap[g] = cap
+        return self._ws[g]
+
+    def _issue(self, n_steps):
+        """Queue ``n_steps`` iterations of every group (fork from / join into the current stream)."""
+        c = self.corpus
+        cur = torch.cuda.current_stream(c.device)
+        multi = self._streams is not None
+        if multi:
+            start = torch.cuda.Event()
+            start.record(cur)
+        for g, (lo, hi) in enumerate(self.ranges):
+            st = self._streams[g] if multi else cur
+            if multi:
+                st.wait_event(start)
+            ws, cap = self._workspace(g), self.capacities[g]
+            cs, ss = self._structs(lo, hi)
+            rc = lib().ipfa_sweep_step_device(
+                ctypes.byref(cs), ctypes.byref(self.params), ctypes.byref(ss), self.out_seg.data_ptr(),
+                self.out_info.data_ptr(), self.steps, n_steps, cap[0], cap[1], cap[2], ws.data_ptr(), ws.numel(),
+                st.cuda_stream)
+            check(rc, "ipfa_sweep_step_device")
+        if multi:
+            for st in self._streams:
+                done = torch.cuda.Event()
+                done.record(st)
+                cur.wait_event(done)
 
     def step(self, n_steps=1):
-        """``n_steps`` iterations of every group; asynchronous, joined back into the current stream."""
+        """``n_steps`` iterations of every group; asynchronous on the current stream."""
         c = self.corpus
-        ranges = self._group_ranges()
-        wss = self._workspaces()
-        cur = torch.cuda.current_stream(c.device)
-        if self._streams is None or len(self._streams) != len(ranges):
-            self._streams = [cur] if len(ranges) == 1 else [torch.cuda.Stream(c.device) for _ in ranges]
+        for g in range(len(self.ranges)):
+            self._workspace(g)
         with torch.cuda.device(c.device):
-            start = None
-            if len(ranges) > 1:
-                start = torch.cuda.Event()
-                start.record(cur)
-            for (lo, hi), ws, st in zip(ranges, wss, self._streams):
-                if start is not None:
-                    st.wait_event(start)
-                cs, ss = self._structs(lo, hi)
-                rc = lib().ipfa_sweep_step_device(
-                    ctypes.byref(cs), ctypes.byref(self.params), ctypes.byref(ss), self.out_seg.data_ptr(),
-                    self.out_info.data_ptr(), self.steps, n_steps, self.capacity[0], self.capacity[1],
-                    self.capacity[2], ws.data_ptr(), ws.numel(), st.cuda_stream)
-                check(rc, "ipfa_sweep_step_device")
-            if len(ranges) > 1:
-                for st in self._streams:
-                    done = torch.cuda.Event()
-                    done.record(st)
-                    cur.wait_event(done)
+            if not self.use_graphs:
+                before = lib().ipfa_launch_count()
+                self._issue(n_steps)
+                self.kernel_launches += lib().ipfa_launch_count() - before
+            else:
+                key = (n_steps, tuple(tuple(cap) for cap in self.capacities), tuple(w.data_ptr() for w in self._ws))
+                if self._graph_key != key:
+                    self._graph = None
+                    torch.cuda.synchronize(c.device)
+                    graph = torch.cuda.CUDAGraph()
+                    before = lib().ipfa_launch_count()
+                    with torch.cuda.graph(graph):
+                        self._issue(n_steps)
+                    self._graph_launches = lib().ipfa_launch_count() - before
+                    self._graph, self._graph_key = graph, key
+                self._graph.replay()
+                self.kernel_launches += self._graph_launches
         self.steps += n_steps
 
     def run(self, steps_per_poll=8, max_steps=100000, recalc_fn=None):
@@ -313,14 +340,21 @@ class AnchorSweep:
             self.step(steps_per_poll)
             status = self.state["status"].cpu().numpy()
             if (status == CAPACITY).any():
-                need = self.state["need"].cpu().numpy()[status == CAPACITY].max(axis=0)
-                grew = False
-                for i in range(3):
-                    if need[i] > self.capacity[i]:
-                        self.capacity[i] = int(need[i] * 1.25) + 4
-                        grew = True
-                self.capacity[0] = min(self.capacity[0], 8000)
-                if need[0] > 8000 or not grew:
+                need = self.state["need"].cpu().numpy()
+                grew, too_long = False, False
+                for g, (lo, hi) in enumerate(self.ranges):
+                    mask = status[lo:hi] == CAPACITY
+                    if not mask.any():
+                        continue
+                    want = need[lo:hi][mask].max(axis=0)
+                    cap = self.capacities[g]
+                    for i in range(3):
+                        if want[i] > cap[i]:
+                            cap[i] = int(want[i] * 1.25) + 4
+                            grew = True
+                    cap[0] = min(cap[0], 8000)
+                    too_long |= bool(want[0] > 8000)
+                if too_long or not grew:
                     # windowed table mode (T > 8000 frames) is not on the device path
                     break
                 self.state["status"][self.state["status"] == CAPACITY] = ACTIVE
@@ -424,7 +458,7 @@ def dataframe_recalc(frames, vads, real_lengths, logger=None):
 
 def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, threshold=-2.0, short_utterance_len=30,
                          max_words_sequence=24, max_window_size=70.0, window_to_stop=500.0,
-                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, groups=4):
+                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, groups=None):
     """Anchor loop of several files with file-level emissions resident on the GPU.
 
     ``jobs``: list of ``(audio_path, file_df, vad_file_df)`` like the arguments of
@@ -451,6 +485,8 @@ def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, thre
     files = [files[i] for i in order]
     frames, vads, lengths = ([x[i] for i in order] for x in (frames, vads, lengths))
     corpus = SweepCorpus(files, asr_model.tokenizer, blank=aligner.config.blank)
+    if groups is None:  # measured on 201 files: 32 groups of ~6 files (bench.py --workload c5)
+        groups = min(32, max(1, len(files) // 6))
     fs = int(asr_model.hparams.sample_rate)
     sweep = AnchorSweep(corpus, index_duration=samples_to_frames_ratio / fs,
                         samples_to_frames_ratio=samples_to_frames_ratio, sample_rate=fs, threshold=threshold,
