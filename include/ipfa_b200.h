@@ -317,12 +317,14 @@ typedef struct ipfa_sweep_params {
 /* out_seg [slots][4] fp64: (clip_start, start, end, score) of every accepted utterance --
  * start/end rounded to 0.01 s and score to 1e-4 like the `str(task)` round trip (:219-230), the
  * short-utterance penalty already added (:241); absolute times are clip_start + start / end.
- * out_info [slots][2] int32: (ordinal, within its file, of the window that accepted the utterance --
- * nothing in the launch depends on the call count, so a captured CUDA graph of this call can be
- * replayed; `first_step` is informational -- , file-relative TSV row that was
- * being aligned -- the row whose Channel / Speaker_ID / Database the result row carries, :258);
- * the caller initialises it to -1.
- * Runs n_steps iterations numbered first_step...; status words say when every file is finished. */
+ * out_info [slots][2] int32: (ordinal, within its file, of the window that accepted the utterance;
+ * file-relative TSV row that was being aligned -- the row whose Channel / Speaker_ID / Database the
+ * result row carries, :258); the caller initialises it to -1.
+ * One call = the file's pending window (re)built from the state, then n_steps iterations of
+ * {all-prefix segmentation, tail: decision + accepted rows + state + next window}: 1 + 3 * n_steps
+ * launches.  Nothing in a launch depends on the call count (`first_step` is informational), so a
+ * CUDA graph captured around this call can be replayed; the status words say when every file is
+ * finished. */
 size_t ipfa_sweep_workspace_bytes(int n_files, int Tmax, int Cmax, int Kmax, int V);
 int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipfa_sweep_params *params,
                            const ipfa_sweep_state *state, double *out_seg, int32_t *out_info,
