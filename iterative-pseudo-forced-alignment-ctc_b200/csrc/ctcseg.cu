@@ -62,9 +62,20 @@ struct SegFillParams {
 // backpointer word address the panel with immediate offsets.
 // FAST: the reference's default flags (blank_transition_cost_zero = False,
 // preamble_transition_cost_zero = True) compiled in, so neither costs an instruction per cell.
-template <int KC, int WARPS, bool DENSE, int PITCH, bool FAST>
+// CL > 1 (experiment, see try_seg_fill_cluster): a window is spread over a thread-block CLUSTER of CL
+// CTAs (CTA `rank` owns the columns of threads rank*NT ...), for batches too small to fill the GPU: the per-frame instruction stream of
+// a window then issues on CL SMs.  The one value per frame that crosses the CTA boundary (last
+// column of rank r -> first column of rank r+1) travels through distributed shared memory: the
+// producer stores (value, frame) as one 8-byte remote store into a ring in the consumer's smem,
+// the consumer spins on its OWN smem until the tag is the frame it needs, and reports its progress
+// back with a remote store so the producer never laps the ring.  No cluster barrier per frame: the
+// CTAs of a window run skewed by the store latency, like pipeline stages.
+constexpr int kClusterRing = 64;
+
+template <int KC, int WARPS, bool DENSE, int PITCH, bool FAST, int CL = 1>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctcseg_fill_kernel(const SegFillParams prm) {
+    static_assert(CL == 1 || WARPS > 1, "clusters split multi-warp windows");
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     constexpr int NT = 32 * WARPS;
     constexpr int SPW = 32 / KC;  // frames per backpointer word
@@ -72,9 +83,11 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int group = (WARPS == 1) ? (threadIdx.x >> 5) : 0;
-    const int tid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    const int w = blockIdx.x * GROUPS + group;
-    if (w >= prm.N) return;
+    const int ltid = (WARPS == 1) ? (threadIdx.x & 31) : threadIdx.x;   // thread inside the CTA / group
+    const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int w = (CL > 1) ? (int)(blockIdx.x / CL) : (int)(blockIdx.x * GROUPS + group);
+    if (w >= prm.N) return;  // (whole clusters leave together)
+    const int tid = rank * NT + ltid;                                    // thread inside the window
     const int pitch = PITCH ? PITCH : prm.pitch;
 
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
@@ -90,7 +103,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     const bool preamble_cost_zero = FAST ? true : (prm.flags & IPFA_SEG_PREAMBLE_COST_ZERO) != 0;
     int32_t *colarg_w = prm.colarg + (int64_t)w * prm.Cmax;
 
-    for (int c = tid; c < prm.Cmax; c += NT) colarg_w[c] = -1;
+    for (int c = tid; c < prm.Cmax; c += CL * NT) colarg_w[c] = -1;
     if (T <= 0 || NC <= 1) return;
 
     int col[KC];
@@ -104,7 +117,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     int colb = DENSE ? blank : 0;
     int U = NC;  // panel columns
     if constexpr (!DENSE) {
-        for (int j = tid; j < NC; j += NT) {
+        for (int j = ltid; j < NC; j += NT) {
             int g = (j == 0) ? blank : gt[j];
             if (g < 0 || g >= prm.V) g = blank;
             cols[j] = g;
@@ -112,7 +125,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         group_sync<WARPS>();
         // ascending, unique column list; the emission ring (idle until the prologue) is scratch
         int *scratch = reinterpret_cast<int *>(ring);
-        U = sort_unique_columns<WARPS>(cols, NC, scratch, tid);
+        U = sort_unique_columns<WARPS>(cols, NC, scratch, ltid);
         const int *pos = scratch + 2 * NC;
 #pragma unroll
         for (int k = 0; k < KC; ++k) col[k] = pos[col[k]];
@@ -132,21 +145,37 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     }
     const bool warp_tracks = __any_sync(0xffffffffu, track);
     if constexpr (WARPS > 1) {
-        if (tid < 2) xline[tid * (NT + 1)] = 0.0f;  // z(t) = table[t, 0]; table[0, 0] = 0
+        if (ltid < 2) xline[ltid * (NT + 1)] = 0.0f;  // z(t) = table[t, 0]; table[0, 0] = 0
+    }
+    // cluster exchange: ring of (value bits, frame tag) written by the left neighbour, progress word
+    // written by the right neighbour
+    uint2 *xring = reinterpret_cast<uint2 *>(gsm + prm.group_smem - 32 - (kClusterRing + 2) * sizeof(uint2));
+    volatile int *progress = reinterpret_cast<volatile int *>(xring + kClusterRing);
+    uint32_t ring_next = 0, progress_prev = 0;  // remote addresses
+    if constexpr (CL > 1) {
+        for (int i = ltid; i < kClusterRing; i += NT)
+            xring[i] = make_uint2(__float_as_uint(kProbMax), i == 0 ? 0u : 0xffffffffu);  // frame 0: prob_max
+        if (ltid == 0) *progress = 0;
+        if (rank + 1 < CL) ring_next = cluster_map(xring, rank + 1);
+        if (rank > 0) progress_prev = cluster_map(const_cast<int *>(progress), rank - 1);
+        cluster_sync_all();  // every ring is initialised before any neighbour stores into it
     }
     group_sync<WARPS>();
 
     EmissionPipe<WARPS, DENSE> pipe;
     pipe.init(ring, cols, prm.lp + (prm.win_off ? prm.win_off[w] : (int64_t)w * prm.stride_n), prm.stride_t, T, U,
               prm.V, pitch, prm.tc,
-              reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
-    pipe.prologue(tid);
+              reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), ltid);
+    pipe.prologue(ltid);
 
     float val[KC], cmax[KC];
     int carg[KC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = kNegInf; carg[k] = -1; }
     float z = 0.0f;  // column 0 at the previous frame
+    float next_prev = 0.0f;    // cluster exchange: value fetched ahead for the next frame
+    bool have_next = false;
+    int seen_progress = 0;     // cluster exchange: cached progress of the right neighbour
     uint32_t word = 0;
     int shift = 0;
     uint32_t *bp_ptr = prm.bp + (int64_t)w * prm.words_per_window + tid;
@@ -160,10 +189,30 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
         float prev;
         if constexpr (WARPS > 1) {
-            prev = rd[tid];
+            prev = rd[ltid];
+            if constexpr (CL > 1) {
+                if (rank > 0 && ltid == 0) {  // table[t-1] of the left neighbour's last column
+                    if (have_next) {          // fetched during the previous frame
+                        prev = next_prev;
+                    } else {
+                        const volatile uint2 *slot = xring + ((t - 1) & (kClusterRing - 1));
+                        uint2 v;
+                        do { v.x = slot->x; v.y = slot->y; } while (v.y != (uint32_t)(t - 1));
+                        v.x = slot->x;  // (value and tag arrive as one 8-byte store; re-read after the tag matched)
+                        prev = __uint_as_float(v.x);
+                    }
+                    // look ahead: the neighbour usually leads by a few frames, so the value for the
+                    // NEXT frame is normally there already and its load hides behind this frame's work
+                    const volatile uint2 *nslot = xring + (t & (kClusterRing - 1));
+                    const uint32_t ntag = nslot->y;
+                    next_prev = __uint_as_float(nslot->x);
+                    have_next = (ntag == (uint32_t)t);
+                    if (have_next) next_prev = __uint_as_float(nslot->x);
+                }
+            }
         } else {
             prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
-            if (tid == 0) prev = z;
+            if (ltid == 0) prev = z;
         }
         uint32_t bits = 0;
 #pragma unroll
@@ -186,11 +235,21 @@ ctcseg_fill_kernel(const SegFillParams prm) {
                 if (cmax[k] < val[k]) { cmax[k] = val[k]; carg[k] = t; }
             }
         }
+        if constexpr (CL > 1) {
+            if (rank + 1 < CL && ltid == NT - 1) {
+                // slot t % R still holds frame t - R: wait until the neighbour has consumed it (the
+                // progress word is re-read only when the cached value says the ring could be full)
+                while (t - seen_progress > kClusterRing - 2) seen_progress = *progress;
+                st_cluster_v2(ring_next + (uint32_t)((t & (kClusterRing - 1)) * sizeof(uint2)),
+                              __float_as_uint(val[KC - 1]), (uint32_t)t);
+            }
+            if (rank > 0 && ltid == 0) st_cluster_u32(progress_prev, (uint32_t)t);  // consumed frame t - 1
+        }
         ++t;
         if (!preamble_cost_zero) z = fmaxf(kProbMax, __fadd_rn(z, eb));
         if constexpr (WARPS > 1) {
-            wr[tid + 1] = val[KC - 1];
-            if (!preamble_cost_zero && tid == 0) wr[0] = z;
+            wr[ltid + 1] = val[KC - 1];
+            if (!preamble_cost_zero && ltid == 0) wr[0] = z;
             __syncthreads();
         }
         return bits;
@@ -200,7 +259,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         shift += KC;
         if (shift == 32) {
             *bp_ptr = word;
-            bp_ptr += NT;
+            bp_ptr += CL * NT;
             word = 0;
             shift = 0;
         }
@@ -208,7 +267,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
 
     float *line0 = xline, *line1 = xline + NT + 1;
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
-        const float *panel = pipe.acquire(chunk, tid);
+        const float *panel = pipe.acquire(chunk, ltid);
         const int rows = min(pipe.tc, T - chunk * pipe.tc);
         int r = 0;
         if (chunk == 0) {
@@ -220,7 +279,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             push_bits(0);
             t = 1;
             if constexpr (WARPS > 1) {
-                line0[tid + 1] = kProbMax;
+                line0[ltid + 1] = kProbMax;
                 __syncthreads();
             }
             r = 1;
@@ -236,7 +295,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
                     acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0) << (f * KC);
                 }
                 *bp_ptr = acc;
-                bp_ptr += NT;
+                bp_ptr += CL * NT;
                 row += SPW * pitch;
                 r += SPW;
             } else {
@@ -247,6 +306,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         }
     }
     if (shift != 0) *bp_ptr = word;
+    if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a neighbour may still store into it
     if (warp_tracks) {
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -1138,6 +1198,58 @@ static int launch_seg_fill_p(SegFillParams prm, cudaStream_t stream) {
     return IPFA_OK;
 }
 
+// Cluster launch (CL CTAs per window, KC columns per thread, WARPS warps per CTA): dense 32-symbol
+// panel with the reference's default flags only -- the configuration of the anchor loop.
+template <int KC, int WARPS, int CL>
+static int launch_seg_fill_cluster(SegFillParams prm, cudaStream_t stream) {
+    PipeGeometry g = pipe_geometry(32, 160 * 1024);
+    prm.pitch = g.pitch;
+    prm.tc = g.tc;
+    prm.u_cap = 0;
+    size_t group_smem = g.ring_bytes + 2 * (32 * WARPS + 1) * sizeof(float) + (kClusterRing + 2) * sizeof(uint2) + 40;
+    group_smem = (group_smem + 15) & ~(size_t)15;
+    prm.group_smem = group_smem;
+    auto kern = ctcseg_fill_kernel<KC, WARPS, true, 32, true, CL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(prm.N * CL));
+    cfg.blockDim = dim3(32 * WARPS);
+    cfg.dynamicSmemBytes = group_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, prm);
+    ++g_launch_count;
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
+
+// Experiment switch: true and launched when asked for, the batch is too small to fill the GPU and a
+// 2-CTA instance exists for this width (2 columns per thread, 8 / 12 / 16 warps per window)
+static bool try_seg_fill_cluster(const SegFillParams &prm, SegShape s, cudaStream_t stream, int *rc) {
+    const bool fast = (prm.flags & (IPFA_SEG_BLANK_COST_ZERO | IPFA_SEG_PREAMBLE_COST_ZERO)) ==
+                      IPFA_SEG_PREAMBLE_COST_ZERO;
+    // Opt-in (IPFA_SEG_CLUSTER=1): measured on the anchor sweep it LOSES -- 177 us against 115 us per
+    // fill of one 2200-frame, 700-column window (tools/exp_sweep_floor.py).  With a dozen warps per
+    // window the frame time is already the dependent-chain latency of one warp (~100 cycles), not
+    // the issue rate of the SM, so a second SM has nothing to take over and the exchange only adds.
+    if (!getenv("IPFA_SEG_CLUSTER")) return false;
+    if (!fast || prm.V > 32 || s.PER != 2) return false;
+    if ((long long)prm.N * s.WARPS >= 148LL * 4 * 3) return false;  // enough warps without splitting
+    switch (s.WARPS) {
+#define IPFA_C(W_) case W_: *rc = launch_seg_fill_cluster<2, W_ / 2, 2>(prm, stream); return true;
+        IPFA_C(8) IPFA_C(12) IPFA_C(16)
+#undef IPFA_C
+        default: return false;
+    }
+}
+
 template <int KC, int WARPS, bool DENSE>
 static int launch_seg_fill(const SegFillParams &prm, cudaStream_t stream) {
     const bool fast = (prm.flags & (IPFA_SEG_BLANK_COST_ZERO | IPFA_SEG_PREAMBLE_COST_ZERO)) ==
@@ -1210,7 +1322,9 @@ int ctcseg_run(const float *lp, const int64_t *win_off, int64_t stride_n, int64_
     fp.Kmax = Kmax;
     fp.N = N; fp.Tmax = Tmax; fp.Cmax = Cmax; fp.V = V; fp.blank = blank; fp.flags = flags;
     fp.bp = bp; fp.words_per_window = wpw; fp.colarg = colarg;
-    int rc = use_dense_panel(V, Cmax) ? dispatch_seg_fill<true>(fp, s, st) : dispatch_seg_fill<false>(fp, s, st);
+    int rc = IPFA_OK;
+    if (!(use_dense_panel(V, Cmax) && try_seg_fill_cluster(fp, s, st, &rc)))
+        rc = use_dense_panel(V, Cmax) ? dispatch_seg_fill<true>(fp, s, st) : dispatch_seg_fill<false>(fp, s, st);
     if (rc) return rc;
 
     SegBackParams bk{};
