@@ -214,7 +214,11 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
             if (ltid == 0) prev = z;
         }
-        uint32_t bits = 0;
+        // Only table[t-1] -> table[t] is on the chain that the next frame (and the neighbour thread,
+        // through the exchange line and the CTA barrier) waits for; the transition test and the
+        // arg-max bookkeeping of this frame are computed AFTER the barrier, in the shadow of the next
+        // frame's shared-memory loads.
+        float left_[KC], up_[KC], stayp_[KC];
 #pragma unroll
         for (int k = KC - 1; k >= 0; --k) {
             const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
@@ -222,19 +226,10 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             const float sw = __fadd_rn(left, ec[k]);
             const float stay_p = fmaxf(eb, ec[k]);
             const float st = blank_cost_zero ? up : __fadd_rn(up, stay_p);
-            const float v = fmaxf(sw, st);
-            // the reference backtrace's transition test, on the same fp32 values
-            const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left)));
-            const float d_st = fabsf(__fsub_rn(stay_p, __fsub_rn(v, up)));
-            bits |= (d_st > d_sw) ? (1u << k) : 0u;
-            val[k] = v;
+            left_[k] = left; up_[k] = up; stayp_[k] = stay_p;
+            val[k] = fmaxf(sw, st);
         }
-        if (warp_tracks) {
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (cmax[k] < val[k]) { cmax[k] = val[k]; carg[k] = t; }
-            }
-        }
+        const int t_now = t;
         if constexpr (CL > 1) {
             if (rank + 1 < CL && ltid == NT - 1) {
                 // slot t % R still holds frame t - R: wait until the neighbour has consumed it (the
@@ -251,6 +246,21 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             wr[ltid + 1] = val[KC - 1];
             if (!preamble_cost_zero && ltid == 0) wr[0] = z;
             __syncthreads();
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            // the reference backtrace's transition test, on the same fp32 values
+            const float v = val[k];
+            const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left_[k])));
+            const float d_st = fabsf(__fsub_rn(stayp_[k], __fsub_rn(v, up_[k])));
+            bits |= (d_st > d_sw) ? (1u << k) : 0u;
+        }
+        if (warp_tracks) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (cmax[k] < val[k]) { cmax[k] = val[k]; carg[k] = t_now; }
+            }
         }
         return bits;
     };
