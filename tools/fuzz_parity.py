@@ -1,0 +1,95 @@
+"""Randomised parity sweep on the GPU (not part of the test suite; run under gpurun):
+   python tools/fuzz_parity.py [seconds]
+Random shapes through every kernel family against the CPU oracle; prints and counts mismatches."""
+import os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ipfa_b200 as ipfa
+from cases import ctc_case, seg_case
+from oracle import ctc as octc
+from oracle import ctcseg as oseg
+from test_gpu_ctcseg import _pack
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+rng = np.random.default_rng(int(time.time()) % 100000)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+t_end = time.time() + budget
+n_cases = n_bad = 0
+while time.time() < t_end:
+    kind = rng.choice(["alpha", "viterbi", "seg", "windowed"])
+    seed = int(rng.integers(1 << 30))
+    try:
+        if kind in ("alpha", "viterbi"):
+            v = int(rng.choice([3, 8, 29, 32, 33, 64, 100, 700]))
+            l = int(rng.integers(0, 300)) if rng.random() < 0.8 else int(rng.integers(300, 1200))
+            t = int(rng.integers(max(1, l), 2 * l + 60))
+            n = int(rng.choice([1, 2, 5, 17, 64, 300])) if l < 200 else int(rng.choice([1, 3, 9]))
+            if rng.random() < 0.15 and l <= 48:
+                n, t = int(rng.integers(4096, 5000)), int(rng.integers(max(8, l), 64))   # length buckets
+            lp, tg, il, tl = ctc_case(seed, n, t, max(l, 1), v, ragged=bool(rng.random() < 0.7),
+                                      repeats=bool(rng.random() < 0.5), peaked=bool(rng.random() < 0.5))
+            if l == 0:
+                tl[:] = 0
+            desc = f"{kind} n={n} t={t} l={l} v={v}"
+            if kind == "alpha":
+                ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+                got = ipfa.ctc_alpha_nll(dev(lp), dev(tg), dev(il), dev(tl)).cpu().numpy()
+                fin = np.isfinite(ref)
+                ok = np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], ref[fin], rtol=1e-4, atol=1e-4)
+            else:
+                paths, scores, status = octc.ctc_viterbi(lp, tg, il, tl)
+                res = ipfa.ctc_forced_align(dev(lp), dev(tg), dev(il), dev(tl))
+                gp, gs, gst = res.paths.cpu().numpy(), res.scores.cpu().numpy(), res.status.cpu().numpy()
+                ok = np.array_equal(gst & 1, status)
+                for i in range(n):
+                    if not status[i]:
+                        ok &= np.array_equal(gp[i, :il[i]], paths[i, :il[i]]) and np.array_equal(gs[i, :il[i]], scores[i, :il[i]])
+        else:
+            v = int(rng.choice([8, 32, 40, 300]))
+            k_utts = int(rng.integers(1, 9))
+            lo = int(rng.integers(1, 30)); hi = lo + int(rng.integers(0, 60))
+            t = int(rng.integers(k_utts * hi + k_utts + 8, k_utts * hi * 4 + 200))
+            n = int(rng.choice([1, 2, 4]))
+            window = None
+            if kind == "windowed":
+                window = int(rng.integers(max(64, t // 4), t + 50))
+            lp, in_len, utts = seg_case(seed, n, t, v, k_utts, lo, hi, peaked=bool(rng.random() < 0.8),
+                                        ragged=(kind == "seg"))
+            cfg = oseg.CtcSegmentationParameters(index_duration=0.02, score_min_mean_over_L=int(rng.choice([5, 30])))
+            gt, ubs, n_cols, n_utts = _pack(cfg, utts)
+            desc = f"{kind} n={n} t={t} v={v} k={k_utts} tok={lo}-{hi} window={window}"
+            ok = True
+            for i in range(n):
+                if n_cols[i] > in_len[i]:
+                    continue
+                k = int(n_utts[i])
+                w = window
+                while True:
+                    res = ipfa.ctcseg_align(dev(lp[i:i + 1]), in_len[i:i + 1], gt[i:i + 1], n_cols[i:i + 1],
+                                            ubs[i:i + 1], n_utts[i:i + 1], 0.02, score_len=cfg.score_min_mean_over_L,
+                                            flags=2, window=w)
+                    if w is None or not int(res.status[0]) & 8:
+                        break
+                    w *= 2
+                if window is not None:
+                    cfg.min_window_size = window
+                g, ub = oseg.prepare_token_list(cfg, utts[i])
+                try:
+                    timings, char_probs, state_list = oseg.ctc_segmentation(cfg, lp[i, :in_len[i]], g)
+                except IndexError:
+                    continue
+                segs = oseg.determine_utterance_segments(cfg, ub, char_probs, timings, [""] * k)
+                timing = res.timing[0, k - 1, :len(g)].cpu().numpy()
+                ok &= np.array_equal(np.where(timing < 0, 0.0, timing * 0.02), timings)
+                ok &= np.array_equal(res.char_prob[0, k - 1, :in_len[i]].cpu().numpy().astype(np.float64), char_probs)
+                seg = res.seg[0, k - 1, :k].cpu().numpy()
+                ok &= all(seg[u, 0] == segs[u][0] and seg[u, 1] == segs[u][1] and
+                          np.isclose(seg[u, 2], segs[u][2], rtol=1e-12, atol=0) for u in range(k))
+    except Exception as exc:  # noqa: BLE001
+        ok, desc = False, f"{kind} seed={seed}: {exc!r}"
+    n_cases += 1
+    if not ok:
+        n_bad += 1
+        print("MISMATCH", desc, "seed", seed, flush=True)
+print(f"{n_cases} random cases, {n_bad} mismatches")
