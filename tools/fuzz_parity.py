@@ -16,8 +16,10 @@ rng = np.random.default_rng(int(time.time()) % 100000)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 t_end = time.time() + budget
 n_cases = n_bad = 0
+counts = {}
 while time.time() < t_end:
-    kind = rng.choice(["alpha", "viterbi", "seg", "windowed"])
+    kind = rng.choice(["alpha", "viterbi", "seg", "windowed", "sweep"], p=[0.3, 0.3, 0.2, 0.15, 0.05])
+    counts[kind] = counts.get(kind, 0) + 1
     seed = int(rng.integers(1 << 30))
     try:
         if kind in ("alpha", "viterbi"):
@@ -45,6 +47,32 @@ while time.time() < t_end:
                 for i in range(n):
                     if not status[i]:
                         ok &= np.array_equal(gp[i, :il[i]], paths[i, :il[i]]) and np.array_equal(gs[i, :il[i]], scores[i, :il[i]])
+        elif kind == "sweep":
+            import importlib
+            import sweep_corpus
+            from ipfa_b200 import sweep as sw
+            from oracle import sweep as osweep
+            stub = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+            n_files = int(rng.integers(1, 4))
+            specs = [sweep_corpus.make_spec(f"z{i}", float(rng.uniform(0.3, 1.2)), seed + i,
+                                            corrupt_frac=float(rng.uniform(0, 0.5)),
+                                            non_speech_every=int(rng.choice([0, 2, 4]))) for i in range(n_files)]
+            lps = [sweep_corpus.emissions(sp, "cuda", seed=seed + 7 * i, peak=float(rng.uniform(3, 8)))
+                   for i, sp in enumerate(specs)]
+            kw = dict(max_window_size=float(rng.choice([12.0, 25.0, 70.0])),
+                      min_text_to_audio_prop=float(rng.choice([0.8, 3.0])))
+            files = [sw.SweepFile(sp.file_id, sp.audio_path, lp_, sp.n_samples, sp.rows) for sp, lp_ in zip(specs, lps)]
+            run = sw.AnchorSweep(sw.SweepCorpus(files, stub.CharTokenizer()), index_duration=0.02,
+                                 samples_to_frames_ratio=320.0, groups=int(rng.integers(1, 3)),
+                                 use_graphs=bool(rng.random() < 0.5), **kw)
+            status = run.run(steps_per_poll=int(rng.choice([1, 4, 16])))
+            got = run.file_rows()
+            desc = f"sweep files={n_files} {kw}"
+            ok = True
+            for f, (sp, lp_) in enumerate(zip(specs, lps)):
+                ref_rows, ref_status, _ = osweep.sweep_file(sp.file_id, sp.audio_path, lp_.cpu().numpy(), sp.n_samples,
+                                                            sp.rows, stub.CharTokenizer(), **kw)
+                ok &= got[f] == ref_rows and sw.STATUS_NAMES[status[f]] == ref_status
         else:
             v = int(rng.choice([8, 32, 40, 300]))
             k_utts = int(rng.integers(1, 9))
@@ -92,4 +120,4 @@ while time.time() < t_end:
     if not ok:
         n_bad += 1
         print("MISMATCH", desc, "seed", seed, flush=True)
-print(f"{n_cases} random cases, {n_bad} mismatches")
+print(f"{n_cases} random cases {counts}, {n_bad} mismatches")
