@@ -390,22 +390,27 @@ __device__ __forceinline__ void score_segments(const int32_t *__restrict__ ub, c
             score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
                               : __longlong_as_double(0x7ff8000000000000LL);
         } else {
-            double best = 0.0;
-            bool has_nan = false;
+            // min over t of mean(char_probs[t : t + n]).  x -> x / n is monotone, so for the windows of
+            // full length the minimum of the means is the minimum of the sums divided once (the fp64
+            // division is a long instruction sequence); windows clipped by the end of the audio keep
+            // their own division.
+            double best = 0.0, best_sum = __longlong_as_double(0x7ff0000000000000LL);
             for (long long t = s_t + lane; t < e_t - n; t += 32) {
                 const int lo = (int)max(0LL, min(t, (long long)T));
                 const int hi = (int)max(0LL, min(t + n, (long long)T));
                 const int cnt = hi - lo;
-                if (cnt <= 0) { has_nan = true; continue; }
-                const double m = __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt);
-                best = fmin(best, m);
+                if (cnt <= 0) continue;
+                const double sum = np_pairwise_sum(cprob + lo, cnt);
+                if (cnt == n) best_sum = fmin(best_sum, sum);
+                else best = fmin(best, __ddiv_rn(sum, (double)cnt));
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                const double o = __shfl_xor_sync(0xffffffffu, best, off);
-                best = fmin(best, o);
+                best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
+                best_sum = fmin(best_sum, __shfl_xor_sync(0xffffffffu, best_sum, off));
             }
-            (void)has_nan;
+            if (best_sum < __longlong_as_double(0x7ff0000000000000LL))
+                best = fmin(best, __ddiv_rn(best_sum, (double)n));
             score = best;
         }
         if (lane == 0) {
