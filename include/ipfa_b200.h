@@ -138,8 +138,10 @@ int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
  *   status_out    [N] int32 IPFA_WIN_* bits (IPFA_WIN_TEXT_LONGER <-> AssertionError)
  *   With IPFA_SEG_ALL_PREFIXES clear only the full text is aligned: slot K_w - 1 is
  *   written, the other prefix slots are left untouched.  Slot k-1 fills seg[., k-1, 0..k-1].
- *   Tmax > 8000 frames (the reference's windowed table mode): use ipfa_ctcseg_windowed_device;
- *   this entry point returns IPFA_ERR_UNSUPPORTED.
+ *   Tmax > 8000 frames (the reference's windowed table mode): ipfa_ctcseg_device returns
+ *   IPFA_ERR_UNSUPPORTED (use ipfa_ctcseg_windowed_device); ipfa_ctcseg_host switches to the windowed
+ *   kernels itself and doubles the window like the reference (status keeps IPFA_WIN_WINDOW_TOO_SMALL
+ *   only if max_window_size = 100000 was reached).
  * ------------------------------------------------------------------------- */
 #define IPFA_SEG_BLANK_COST_ZERO 1
 #define IPFA_SEG_PREAMBLE_COST_ZERO 2

@@ -250,7 +250,18 @@ extern "C" int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t strid
         return IPFA_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(g_arena.mu);
     const int64_t per_window = (int64_t)Tmax * V;
-    const size_t ws = ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V);
+    // audio longer than ctc-segmentation's min_window_size (8000 frames): windowed table mode, the
+    // window doubled after IPFA_WIN_WINDOW_TOO_SMALL up to max_window_size (100000) like the
+    // reference's `except IndexError` loop
+    const bool windowed = Tmax > 8000;
+    int window = 8000;
+    size_t ws = windowed ? 0 : ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V);
+    if (windowed)
+        for (int wsz = window; wsz < 100000; wsz *= 2) {
+            const size_t b = ipfa_ctcseg_windowed_workspace_bytes(N, Tmax, Cmax, Kmax, wsz, 1, flags);
+            if (b > ws) ws = b;
+            if (wsz >= Tmax) break;
+        }
     const size_t n_seg = (size_t)N * Kmax * Kmax * 3;
     size_t need = pad256((size_t)N * per_window * 4) + pad256((size_t)N * Cmax * 4) +
                   pad256((size_t)N * (Kmax + 1) * 4) + 4 * pad256((size_t)N * 4) + pad256(n_seg * 8) +
@@ -281,10 +292,25 @@ extern "C" int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t strid
     IPFA_CUDA(cudaMemcpyAsync(d_nc, n_cols, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_nu, n_utts, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemsetAsync(d_seg, 0xff, n_seg * 8, st));  // unfilled slots read as NaN
-    rc = ipfa_ctcseg_device(d_lp, per_window, V, d_il, d_gt, Cmax, d_nc, d_ub, d_nu, N, Tmax, Cmax, Kmax, V,
-                            blank, index_duration, score_len, flags, d_seg, d_term, d_timing, d_cprob, d_state,
-                            d_status, d_ws, ws, st);
-    if (rc) return rc;
+    if (!windowed) {
+        rc = ipfa_ctcseg_device(d_lp, per_window, V, d_il, d_gt, Cmax, d_nc, d_ub, d_nu, N, Tmax, Cmax, Kmax, V,
+                                blank, index_duration, score_len, flags, d_seg, d_term, d_timing, d_cprob, d_state,
+                                d_status, d_ws, ws, st);
+        if (rc) return rc;
+    } else {
+        while (true) {
+            rc = ipfa_ctcseg_windowed_device(d_lp, nullptr, per_window, V, d_il, d_gt, Cmax, d_nc, d_ub, d_nu, N,
+                                             Tmax, Cmax, Kmax, V, blank, index_duration, score_len, flags, window,
+                                             1, d_seg, d_term, d_timing, d_cprob, d_state, d_status, d_ws, ws, st);
+            if (rc) return rc;
+            IPFA_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+            IPFA_CUDA(cudaStreamSynchronize(st));
+            bool too_small = false;
+            for (int i = 0; i < N; ++i) too_small |= (status_out[i] & IPFA_WIN_WINDOW_TOO_SMALL) != 0;
+            if (!too_small || window >= Tmax || window * 2 >= 100000) break;
+            window *= 2;
+        }
+    }
     IPFA_CUDA(cudaMemcpyAsync(seg_out, d_seg, n_seg * 8, cudaMemcpyDeviceToHost, st));
     IPFA_CUDA(cudaMemcpyAsync(term_t_out, d_term, (size_t)N * Kmax * 4, cudaMemcpyDeviceToHost, st));
     if (timing_out)

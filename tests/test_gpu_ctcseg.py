@@ -417,3 +417,14 @@ def test_classic_text_converter_through_the_mirror(cs):
     for a, b in zip(got["segments"], ref["segments"]):
         assert a[0] == b[0] and a[1] == b[1]
         np.testing.assert_allclose(a[2], b[2], rtol=1e-12)
+
+
+def test_host_entry_point_long_audio(ipfa):
+    """ipfa_ctcseg_host with more than 8000 frames: the windowed kernels, window doubling inside."""
+    from oracle import ctcseg as oseg
+    lp, in_len, utts = _aligned_case(81, 1, 8300, 32, 3, 30, 60)
+    cfg = oseg.CtcSegmentationParameters(index_duration=0.02)
+    gt, ubs, n_cols, n_utts = _pack(cfg, utts)
+    res = ipfa.ctcseg_align_host(lp, in_len, gt, n_cols, ubs, n_utts, 0.02, flags=2)
+    assert int(res.status[0]) == 0
+    _compare_window(cfg, res, 0, int(n_utts[0]), lp[0, :in_len[0]], utts[0], lambda x: x)
