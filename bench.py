@@ -684,26 +684,43 @@ def gpu_arm(args):
         # the step's kernels average ms_per_step of device time per step
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         legs = cpu_leg(wl, budget_s=12.0)
-        bound_note = {"alpha": "T-serial log-sum-exp recursion walked from both ends: MUFU bound (4 MUFU per state pair "
-                               "and frame), not HBM bound -- DESIGN.md 5.1",
+        lin = wl.kind == "alpha" and wl.v <= 64 and wl.l + 1 <= 256 and not os.environ.get("IPFA_ALPHA_LOG")
+        bound_note = {"alpha": ("T-serial recursion walked from both ends, states kept as scaled fp64 probabilities "
+                                "(linear-domain instance): issue / latency bound at 3.5 resident warps per SM "
+                                "sub-partition, not HBM bound -- DESIGN.md 5.1") if lin else
+                               ("T-serial log-sum-exp recursion walked from both ends: MUFU bound (4 MUFU per state "
+                                "pair and frame), not HBM bound -- DESIGN.md 5.1"),
                       "viterbi": "T-serial max-plus recursion + latency-bound backtrace: issue bound -- DESIGN.md 5.2",
                       "seg": "T-serial max-plus recursion with a CTA barrier per frame -- DESIGN.md 5.3"}[wl.kind]
         extra_roof = {}
         if wl.kind == "alpha" and wl.v <= 64:
-            # the bound that actually binds this kernel: 4 MUFU warp-instructions per
-            # 32 state pairs and frame, 8 cycles each per SM sub-partition (profiles/microbench_r01.txt)
             il = sets[0][2].cpu().numpy().astype(np.int64)
             tl = sets[0][3].cpu().numpy().astype(np.int64)
-            pair_warps = np.ceil((tl + 1) / 32.0)
-            mufu_cycles = float((il * pair_warps).sum()) * 4 * 8
             clk = (sampler.result().get("sm_mhz") or 1965.0) * 1e6
-            floor_ms = mufu_cycles / (148 * 4) / clk * 1e3
-            extra_roof = {"mufu_floor_ms": floor_ms, "frac_of_mufu_floor": floor_ms / ms_per_step}
+            if lin:
+                # the pipes that bound the linear-domain instance: per frame and warp of
+                # 32 lanes x P pairs, 3P + 1 FP64 warp-instructions (2 cycles each per SM sub-partition,
+                # profiles/microbench_fp64_r01.txt) out of ~9P + 1 issued instructions
+                pairs = int(tl.max()) + 1
+                per_lane = 1 if pairs <= 32 else 2 if pairs <= 64 else 4 if pairs <= 128 else 8
+                frames = float(il.sum())
+                fp64_ms = frames * (3 * per_lane + 1) * 2 / (148 * 4) / clk * 1e3
+                issue_ms = frames * (9 * per_lane + 1) / (148 * 4) / clk * 1e3
+                extra_roof = {"fp64_pipe_floor_ms": fp64_ms, "issue_floor_ms": issue_ms,
+                              "frac_of_issue_floor": issue_ms / ms_per_step}
+            else:
+                # the bound that actually binds the log-domain instance: 4 MUFU
+                # warp-instructions per 32 state pairs and frame, 8 cycles each per SM sub-partition
+                # (profiles/microbench_r01.txt)
+                pair_warps = np.ceil((tl + 1) / 32.0)
+                mufu_cycles = float((il * pair_warps).sum()) * 4 * 8
+                floor_ms = mufu_cycles / (148 * 4) / clk * 1e3
+                extra_roof = {"mufu_floor_ms": floor_ms, "frac_of_mufu_floor": floor_ms / ms_per_step}
         line = {
             "metric": "aligned_audio_hours_per_s", "value": world * hours / (ms_per_step * 1e-3),
             "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f64" if lin else "f32", "data": "synthetic",
             "config": dict({"workload": wl.text, "kernel": wl.kind,
                             "l2": f"{n_sets} rotating input sets of {wl.set_bytes / 1e6:.0f} MB per GPU (> 126 MB L2)",
                             "sharding": "independent windows per rank, no collective on the data path"}, **wl.shape),

@@ -41,7 +41,40 @@ struct AlphaParams {
     float *nll_out;
     float *join_vec;       // [N][2 halves][2][l_cap + 1] state vectors at the cut (workspace)
     int *join_count;       // [N] arrivals at the cut, zeroed before the launch (workspace)
+    int32_t *redo;         // linear-domain instance: windows handed to the log-domain instance
+    int *redo_count;
 };
+
+// ---- linear-domain instance (LIN) -----------------------------------------------------------
+// The log-domain recursion pays 4 MUFU operations (8 cycles each per warp) per state pair and
+// frame.  The LIN instance keeps the states as PROBABILITIES in fp64 -- the B200 FP64 pipe issues
+// a warp DADD / DMUL every 2 cycles (tools/microbench_fp64.cu) -- divided by the blank emission
+// of every frame walked so far (a factor common to the whole lattice, accumulated as a sum of
+// logs on the side), so that a pair costs 2 DADD + 1 DMUL + 1 select and no MUFU:
+//   blank_p <- blank_p + label_{p-1}
+//   label_p <- (label_p + (skip_p ? blank_p' : blank_p)) * r_p,   r = exp(lp[label] - lp[blank])
+// Range: every thread carries its own power-of-two scale 2^E for its 2P states, re-chosen once
+// per emission chunk (<= 32 frames) so that its largest state sits at 2^kLinTarget; the value
+// received from the left neighbour is rescaled by 2^(E - E_left), constant between two
+// re-scalings.  Exactness guard: at every re-scaling each state the lattice can have reached
+// (by the graph alone: frame index >= minimal arrival time) must hold a normal number
+// >= 2^kLinTinyExp, nothing may exceed 2^kLinHugeExp, every emission ratio must be a normal
+// fp32, and neighbouring scales must be within 2^1000 of each other.  A window that breaks any
+// of these (or whose total is zero: infeasible targets) is appended to the redo list and scored
+// by the log-domain instance right after -- the LIN instance never writes a result it cannot
+// vouch for.
+constexpr int kLinTarget = 100;
+constexpr int kLinTinyExp = -700;
+constexpr int kLinHugeExp = 1000;
+constexpr int kLinEmpty = -(1 << 28);
+
+__device__ __forceinline__ double lin_pow2(int d) {  // 2^d, d clamped to the normal range
+    d = max(-1022, min(1023, d));
+    return __hiloint2double((1023 + d) << 20, 0);
+}
+__device__ __forceinline__ int lin_exponent(double v) {  // floor(log2 v) of a positive normal v
+    return (__double2hiint(v) >> 20) - 1023;
+}
 
 // PITCH > 0: compile-time panel pitch (dense rows of <= 32 symbols), so the unrolled frames
 // address the panel with immediate offsets from one pointer per column.
@@ -55,9 +88,24 @@ struct AlphaParams {
 // them:  p = sum_s alpha_m(s) * sum_{s' in succ(s)} b_{m+1}(s').
 constexpr int kBidirMinFrames = 16;  // shorter windows are walked by group 0 alone
 
-template <int P, int WARPS, bool DENSE, int PITCH>
+// LIN: bits of the emission ratio exp(x - x_blank) as an fp32, and their packing into the high
+// word of the fp64 with the same value (mantissa rounded to 20 bits).  `ratio_range(bits)` is
+// <= kRatioRangeMax exactly when the ratio is a normal fp32 <= 1e38 (zero, denormals, inf and NaN
+// all map above it).
+__device__ __forceinline__ uint32_t ratio_raw(const float x, const float xb) {
+    return __float_as_uint(ex2_approx((x - xb) * kLog2e));
+}
+__device__ __forceinline__ uint32_t ratio_range(const uint32_t bits) { return bits - 0x00800000u; }
+constexpr uint32_t kRatioRangeMax = 0x7e967699u - 0x00800000u;
+__device__ __forceinline__ float ratio_pack(const uint32_t bits) {
+    return __uint_as_float(((bits + 4u) >> 3) + 0x38000000u);
+}
+
+template <int P, int WARPS, bool DENSE, int PITCH, bool LIN = false>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctc_alpha_kernel(const AlphaParams prm) {
+    static_assert(!LIN || (WARPS == 1 && DENSE), "the linear-domain instance is one warp per half window, dense panel");
+    using State = std::conditional_t<LIN, double, float>;
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     constexpr int NT = 32 * WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -99,6 +147,8 @@ ctc_alpha_kernel(const AlphaParams prm) {
     int col[P];      // panel column of label_p
     bool skip[P];    // s-2 transition allowed into label_p
     bool bad = false;
+    bool flag = false;   // LIN: this window goes to the redo list
+    int rep_excl = 0;    // LIN: repeated labels (target[k] == target[k-1]) before this thread's pairs
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int j = tid * P + p;  // target index of this pair's label
@@ -107,9 +157,22 @@ ctc_alpha_kernel(const AlphaParams prm) {
         const bool lab_ok = j < L;
         int lab = lab_ok ? target(j) : blank;
         if (lab < 0 || lab >= prm.V) { bad = true; lab = blank; }
+        // (the blank column of the LIN panel holds raw logs, not ratios: a target that names
+        // the blank symbol is left to the log-domain instance)
+        if (LIN && lab_ok && lab == blank) flag = true;
         const int prev = (j >= 1 && lab_ok) ? target(j - 1) : -1;
         skip[p] = lab_ok && j >= 1 && prev != lab;
+        if (LIN) rep_excl += (lab_ok && j >= 1 && prev == lab) ? 1 : 0;
         col[p] = DENSE ? lab : (lab_ok ? j + 1 : 0);
+    }
+    if constexpr (LIN) {  // exclusive prefix over the lanes
+        int incl = rep_excl;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (tid >= off) incl += v;
+        }
+        rep_excl = incl - rep_excl;
     }
     int colb = DENSE ? blank : 0;
     int U = L + 1;  // panel columns
@@ -138,9 +201,20 @@ ctc_alpha_kernel(const AlphaParams prm) {
               prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid, t_lo, rev);
     pipe.prologue(tid);
 
-    float ab[P], al[P];  // blank / label alphas (log2 domain)
+    int skipm[P];  // LIN: skip[p] as an all-ones / zero mask the compiler keeps in a register
 #pragma unroll
-    for (int p = 0; p < P; ++p) { ab[p] = kNegBig; al[p] = kNegBig; }
+    for (int p = 0; p < P; ++p) {
+        skipm[p] = skip[p] ? -1 : 0;
+        if constexpr (LIN) asm volatile("" : "+r"(skipm[p]));
+    }
+    State ab[P], al[P];  // blank / label alphas (log2 domain; LIN: scaled probabilities)
+#pragma unroll
+    for (int p = 0; p < P; ++p) { ab[p] = LIN ? State(0) : State(kNegBig); al[p] = ab[p]; }
+    // LIN: stored = true * 2^E / prod(blank emissions so far); rs = 2^(E - E of the left lane)
+    int E = 0;
+    double rs = (tid == 0) ? 0.0 : 1.0;
+    float sb = 0.0f;        // sum of the blank log-emissions since the last re-scaling (natural log)
+    double sb_total = 0.0;  // ... and before it
 
     // One frame of the recursion, `off` floats past the column cursors.  `rd`/`wr`: this frame's
     // read / write lines of the cross-warp exchange (WARPS > 1); inside a warp the neighbour
@@ -148,30 +222,102 @@ ctc_alpha_kernel(const AlphaParams prm) {
     const float *pb = nullptr;   // cursor on the blank column
     const float *pl[P];          // cursors on the label columns
     auto frame = [&](const int off, const float *rd, float *wr) {
-        const float eb = pb[off];
-        float el[P];
+        if constexpr (LIN) {
+            sb += pb[off];
+            double r[P];  // the panel holds the high word of the fp64 ratio (20 mantissa bits)
 #pragma unroll
-        for (int p = 0; p < P; ++p) el[p] = pl[p][off];
-        float prev;
-        if constexpr (WARPS > 1) {
-            prev = rd[tid];
+            for (int p = 0; p < P; ++p) r[p] = __hiloint2double(__float_as_int(pl[p][off]), 0);
+            // lane 0 has no left neighbour: its rs is 0
+            const double prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1) * rs;
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) {
+                const double lm1 = (p == 0) ? prev : al[p - 1];
+                const double nb = ab[p] + lm1;
+                // x = skip ? nb : ab, as one bit-select per word on a mask held in a register
+                const int m = skipm[p];
+                const double x = __hiloint2double((__double2hiint(nb) & m) | (__double2hiint(ab[p]) & ~m),
+                                                  (__double2loint(nb) & m) | (__double2loint(ab[p]) & ~m));
+                al[p] = (al[p] + x) * r[p];
+                ab[p] = nb;
+            }
         } else {
-            prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
-            if (tid == 0) prev = kNegBig;
-        }
+            const float eb = pb[off];
+            float el[P];
 #pragma unroll
-        for (int p = P - 1; p >= 0; --p) {
-            const float lm1 = (p == 0) ? prev : al[p - 1];
-            // blank_p <- lse(blank_p, label_{p-1});  label_p <- lse(label_p, blank_p [, label_{p-1}])
-            // and lse(blank_p, label_{p-1}) is shared between the two when the skip is allowed.
-            const float nb = lse2_2(ab[p], lm1);
-            const float x = skip[p] ? nb : ab[p];
-            al[p] = lse2_2(al[p], x) + el[p];
-            ab[p] = nb + eb;
+            for (int p = 0; p < P; ++p) el[p] = pl[p][off];
+            float prev;
+            if constexpr (WARPS > 1) {
+                prev = rd[tid];
+            } else {
+                prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+                if (tid == 0) prev = kNegBig;
+            }
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p) {
+                const float lm1 = (p == 0) ? prev : al[p - 1];
+                // blank_p <- lse(blank_p, label_{p-1});  label_p <- lse(label_p, blank_p [, label_{p-1}])
+                // and lse(blank_p, label_{p-1}) is shared between the two when the skip is allowed.
+                const float nb = lse2_2(ab[p], lm1);
+                const float x = skip[p] ? nb : ab[p];
+                al[p] = lse2_2(al[p], x) + el[p];
+                ab[p] = nb + eb;
+            }
+            if constexpr (WARPS > 1) {
+                wr[tid + 1] = al[P - 1];
+                __syncthreads();
+            }
         }
-        if constexpr (WARPS > 1) {
-            wr[tid + 1] = al[P - 1];
-            __syncthreads();
+    };
+    // LIN: re-scaling + exactness guard, between two frames; `tcur` = walk index of the last frame
+    // done.  Pair j's label is first alive at frame j + (repeats up to j), its blank one frame after
+    // the previous label.
+    auto renorm = [&](const int tcur) {
+        if constexpr (LIN) {
+            sb_total += (double)sb;
+            sb = 0.0f;
+            // The states are non-negative, so their order is the order of their high words as
+            // integers (a NaN or inf sorts above every finite value and trips the `huge` test; a
+            // negative value -- arithmetic on a flagged window -- sorts below `tiny`).
+            constexpr int tiny_hi = (1023 + kLinTinyExp) << 20, huge_hi = (1023 + kLinHugeExp) << 20;
+            int hmax = 0;
+            bool ok = true;
+            int cnt = rep_excl;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int j = tid * P + p;
+                const int isrep = (j < L && j >= 1 && !skip[p]) ? 1 : 0;
+                cnt += isrep;
+                const int need = j + cnt;
+                if (j > L) ab[p] = 0.0;   // the states past the target never feed a real one
+                if (j >= L) al[p] = 0.0;
+                const int hb = __double2hiint(ab[p]), hl = __double2hiint(al[p]);
+                if (j <= L && tcur >= need - isrep) ok = ok && (hb >= tiny_hi);
+                if (j < L && tcur >= need) ok = ok && (hl >= tiny_hi);
+                hmax = max(hmax, max(hb, hl));
+            }
+            ok = ok && (hmax < huge_hi);
+            // true exponents of this thread's largest state and of the value its left neighbour hands over
+            const int A = (hmax >= (1 << 20)) ? (hmax >> 20) - 1023 - E : kLinEmpty;
+            const double b = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+            const int El = __shfl_up_sync(0xffffffffu, E, 1);
+            const int B = (tid > 0 && __double2hiint(b) >= (1 << 20)) ? lin_exponent(b) - El : kLinEmpty;
+            const int X = max(A, B);
+            const bool empty = X <= kLinEmpty / 2;
+            int Enew = kLinTarget - X;
+            // the lanes right of the frontier take the scale of the frontier lane
+            const unsigned ne = __ballot_sync(0xffffffffu, !empty);
+            const int Ead = __shfl_sync(0xffffffffu, Enew, ne ? 31 - __clz(ne) : 0);
+            if (empty) Enew = Ead;
+            const int d = Enew - E;
+            if (!empty && (d > 1000 || d < -1000)) ok = false;
+            const double f = lin_pow2(max(-1000, min(1000, d)));
+#pragma unroll
+            for (int p = 0; p < P; ++p) { ab[p] *= f; al[p] *= f; }
+            E = Enew;
+            const int d2 = E - __shfl_up_sync(0xffffffffu, E, 1);
+            if (tid > 0 && !empty && (d2 > 1000 || d2 < -1000)) ok = false;
+            rs = (tid == 0) ? 0.0 : lin_pow2(max(-1000, min(1000, d2)));
+            flag = flag || !ok;
         }
     };
     float *line0 = xline, *line1 = xline + NT + 1;
@@ -179,8 +325,57 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // j has the parity of the frame's position in the walk).  DIR = +1: rows 0, 1, ...;
     // DIR = -1 (reverse half): rows rows-1, rows-2, ...; the 4 unrolled frames sit at immediate
     // offsets from the cursors either way.
-    auto run_rows = [&](auto dir, int j, const int rows) {
-        constexpr int DIR = decltype(dir)::value;
+    // LIN: an emission becomes the RATIO exp(x - x_blank), stored as the high word of its fp64
+    // (rounded to 20 mantissa bits); the blank column keeps its raw logs (summed on the side by
+    // frame()).  A ratio that is not a normal fp32 <= 1e38 (zero, denormal, inf, NaN) sends the
+    // window to the redo list.
+    const bool keep = tid == colb;  // PITCH == 32: one lane per column; this lane owns the blank column
+    uint32_t oor = 0;  // largest ratio_range() seen by this lane
+    // whole chunk at once (8 rows in flight: the loads of a batch precede its stores)
+    auto prescale_chunk = [&](float *panel, const int rows) {
+        if constexpr (LIN && PITCH == 32) {
+            float *cell = panel + tid;
+            const float *bcell = panel + colb;
+            for (int r0 = 0; r0 < rows; r0 += 8) {
+                float xv[8], bv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int rr = min(r0 + k, rows - 1);
+                    xv[k] = cell[rr * 32];
+                    bv[k] = bcell[rr * 32];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t raw = ratio_raw(xv[k], bv[k]);
+                    oor = max(oor, ratio_range(raw));
+                    if (!keep && r0 + k < rows) cell[(r0 + k) * 32] = ratio_pack(raw);
+                }
+            }
+        } else if constexpr (LIN) {
+            float4 *p4 = reinterpret_cast<float4 *>(panel);
+            const int n4 = (rows * pitch) >> 2;
+            for (int q = tid; q < n4; q += NT) {
+                const int e0 = q << 2, row = e0 / pitch, c0 = e0 - row * pitch;
+                const float xb = panel[row * pitch + colb];
+                float4 v = p4[q];
+                const uint32_t b0 = ratio_raw(v.x, xb), b1 = ratio_raw(v.y, xb);
+                const uint32_t b2 = ratio_raw(v.z, xb), b3 = ratio_raw(v.w, xb);
+                if (c0 != colb) { v.x = ratio_pack(b0); flag = flag || (ratio_range(b0) > kRatioRangeMax && c0 < prm.V); }
+                if (c0 + 1 != colb) { v.y = ratio_pack(b1); flag = flag || (ratio_range(b1) > kRatioRangeMax && c0 + 1 < prm.V); }
+                if (c0 + 2 != colb) { v.z = ratio_pack(b2); flag = flag || (ratio_range(b2) > kRatioRangeMax && c0 + 2 < prm.V); }
+                if (c0 + 3 != colb) { v.w = ratio_pack(b3); flag = flag || (ratio_range(b3) > kRatioRangeMax && c0 + 3 < prm.V); }
+                p4[q] = v;
+            }
+        }
+    };
+    // PRE (LIN, PITCH == 32): while walking a chunk, every group of 4 frames also converts 4 rows
+    // of the NEXT chunk (cursors qx / qb) -- independent work that fills the recursion's stalls,
+    // instead of a latency-bound conversion pass that all the warps of a sub-partition hit together.
+    float *qx = nullptr;
+    const float *qb = nullptr;
+    auto run_rows = [&](auto mode, int j, const int rows) {  // mode: +-1 walk, +-2 walk and convert
+        constexpr int DIR = decltype(mode)::value > 0 ? 1 : -1;
+        constexpr bool PRE = decltype(mode)::value == 2 || decltype(mode)::value == -2;
         const int step = DIR * pitch;
         auto bump = [&](const int frames) {
             pb += frames * step;
@@ -189,10 +384,28 @@ ctc_alpha_kernel(const AlphaParams prm) {
         };
         if ((j & 1) && j < rows) { frame(0, line0, line1); bump(1); ++j; }
         for (; j + 3 < rows; j += 4) {
+            uint32_t raw0 = 0, raw1 = 0, raw2 = 0, raw3 = 0;
+            if constexpr (PRE) {
+                raw0 = ratio_raw(qx[0], qb[0]);
+                raw1 = ratio_raw(qx[step], qb[step]);
+                raw2 = ratio_raw(qx[2 * step], qb[2 * step]);
+                raw3 = ratio_raw(qx[3 * step], qb[3 * step]);
+            }
             frame(0, line1, line0);
             frame(step, line0, line1);
             frame(2 * step, line1, line0);
             frame(3 * step, line0, line1);
+            if constexpr (PRE) {
+                oor = max(max(oor, ratio_range(raw0)), max(ratio_range(raw1), max(ratio_range(raw2), ratio_range(raw3))));
+                if (!keep) {
+                    qx[0] = ratio_pack(raw0);
+                    qx[step] = ratio_pack(raw1);
+                    qx[2 * step] = ratio_pack(raw2);
+                    qx[3 * step] = ratio_pack(raw3);
+                }
+                qx += 4 * step;
+                qb += 4 * step;
+            }
             bump(4);
         }
         for (; j + 1 < rows; j += 2) {
@@ -202,12 +415,46 @@ ctc_alpha_kernel(const AlphaParams prm) {
         }
         if (j < rows) frame(0, line1, line0);
     };
+    // LIN with bulk-copied chunks of PITCH == 32: chunk c+1 is converted while chunk c is walked
+    const bool lin_overlap = LIN && PITCH == 32 && pipe.bulk;
 
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
-        float *panel = const_cast<float *>(pipe.acquire(chunk, tid));
-        const int rows = pipe.chunk_rows(chunk);
-        // in-place: natural log -> log2, clamp log(0) to the finite stand-in
-        {
+        float *panel;
+        int rows;
+        bool pre = false;  // LIN: this walk converts the next chunk
+        if constexpr (!LIN) {
+            panel = const_cast<float *>(pipe.acquire(chunk, tid));
+            rows = pipe.chunk_rows(chunk);
+        } else if (lin_overlap) {
+            rows = pipe.chunk_rows(chunk);
+            if (chunk == 0) {
+                panel = const_cast<float *>(pipe.acquire(0, tid));
+                prescale_chunk(panel, rows);
+            } else {
+                // chunk `chunk` is converted already; the stage of chunk-1 is free: refill it
+                panel = pipe.stage_ptr(chunk);
+                fence_proxy_async();
+                __syncwarp();
+                pipe.issue(chunk + kStages - 1, tid);
+            }
+            if (chunk + 1 < pipe.nchunks) {
+                pipe.wait_landed(chunk + 1);
+                const int rows_next = pipe.chunk_rows(chunk + 1);
+                pre = chunk > 0 && rows_next == rows && (rows & 3) == 0;
+                if (!pre) prescale_chunk(pipe.stage_ptr(chunk + 1), rows_next);
+            }
+            __syncwarp();
+        } else {
+            panel = const_cast<float *>(pipe.acquire(chunk, tid));
+            rows = pipe.chunk_rows(chunk);
+        }
+        if constexpr (LIN) {
+            if (!lin_overlap) {
+                prescale_chunk(panel, rows);
+                group_sync<WARPS>();
+            }
+        } else {
+            // in-place: natural log -> log2, clamp log(0) to the finite stand-in
             float4 *p4 = reinterpret_cast<float4 *>(panel);
             const int n4 = (rows * pitch) >> 2;
             for (int q = tid; q < n4; q += NT) {
@@ -221,7 +468,13 @@ ctc_alpha_kernel(const AlphaParams prm) {
         const int first_row = rev ? rows - 1 : 0;  // the chunk's first frame in walking order
         int j = 0;
         if (chunk == 0) {  // first frame of the walk: only states 0 and 1 are alive
-            if (tid == 0) {
+            if constexpr (LIN) {
+                if (tid == 0) {
+                    ab[0] = 1.0;
+                    if (L > 0) al[0] = __hiloint2double(__float_as_int(panel[first_row * pitch + col[0]]), 0);
+                }
+                sb = panel[first_row * pitch + colb];
+            } else if (tid == 0) {
                 ab[0] = panel[first_row * pitch + colb];
                 if (L > 0) al[0] = panel[first_row * pitch + col[0]];
             }
@@ -231,21 +484,58 @@ ctc_alpha_kernel(const AlphaParams prm) {
             }
             j = 1;
         }
+        renorm(chunk * pipe.tc + j - 1);
         const int row = rev ? rows - 1 - j : j;
         pb = panel + row * pitch + colb;
 #pragma unroll
         for (int p = 0; p < P; ++p) pl[p] = panel + row * pitch + col[p];
-        if (rev) run_rows(std::integral_constant<int, -1>{}, j, rows);
-        else run_rows(std::integral_constant<int, 1>{}, j, rows);
+        if constexpr (LIN && PITCH == 32) {
+            if (pre) {  // j == 0 here: the 4-frame groups cover the whole chunk
+                float *nxt = pipe.stage_ptr(chunk + 1) + row * pitch;
+                qx = nxt + tid;
+                qb = nxt + colb;
+                if (rev) run_rows(std::integral_constant<int, -2>{}, j, rows);
+                else run_rows(std::integral_constant<int, 2>{}, j, rows);
+                __syncwarp();
+            }
+        }
+        if (!pre) {
+            if (rev) run_rows(std::integral_constant<int, -1>{}, j, rows);
+            else run_rows(std::integral_constant<int, 1>{}, j, rows);
+        }
     }
 
+    // state -> log2 of its true value (LIN: undo the scale and the blank normalisation)
+    bool flag_any = false;
+    double lin_bias = 0.0;
+    if constexpr (LIN) {
+        if (oor > kRatioRangeMax && !keep && tid < prm.V) flag = true;
+        renorm(T - 1);
+        flag_any = __any_sync(0xffffffffu, flag);
+        lin_bias = sb_total * 1.4426950408889634 - (double)E;
+    }
+    auto log2_of = [&](const State v) -> float {
+        if constexpr (LIN) {
+            if (!(v >= 2.2250738585072014e-308)) return kNegBig;
+            const int hi = __double2hiint(v);
+            const double mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+            return (float)((double)((hi >> 20) - 1023) + lin_bias + (double)lg2_approx((float)mant));
+        } else {
+            return v;
+        }
+    };
+    // LIN: hand the window to the log-domain instance instead of writing a result
+    auto redo_window = [&]() {
+        prm.redo[atomicAdd(prm.redo_count, 1)] = w;
+        prm.join_count[w] = 0;
+    };
     if (!bidir) {
         // final states 2L (blank of pair L) and 2L-1 (label of pair L-1)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const int j = tid * P + p;
-            if (j == L) fin[0] = ab[p];
-            if (j == L - 1) fin[1] = al[p];
+            if (j == L) fin[0] = log2_of(ab[p]);
+            if (j == L - 1) fin[1] = log2_of(al[p]);
         }
         if (L == 0 && tid == 0) fin[1] = kNegBig;
         group_sync<WARPS>();
@@ -253,7 +543,8 @@ ctc_alpha_kernel(const AlphaParams prm) {
             const float v = lse2_2(fin[0], fin[1]);
             float nll = -v * kLn2;
             if (v < kNegThreshold || bad) nll = __int_as_float(0x7f800000);
-            prm.nll_out[w] = nll;
+            if (LIN && !bad && (flag_any || !(v >= kNegThreshold))) redo_window();
+            else prm.nll_out[w] = nll;
         }
         return;
     }
@@ -268,15 +559,17 @@ ctc_alpha_kernel(const AlphaParams prm) {
     for (int p = 0; p < P; ++p) {
         const int j = tid * P + p;
         if (j <= L) {
-            mine[j] = ab[p];
-            mine[vstride + j] = (j < L) ? al[p] : kNegBig;
+            mine[j] = log2_of(ab[p]);
+            mine[vstride + j] = (j < L) ? log2_of(al[p]) : kNegBig;
         }
     }
     __threadfence();
     group_sync<WARPS>();
-    if (tid == 0) fin[0] = __int_as_float(atomicAdd(prm.join_count + w, 1));
+    // (LIN: bit 8 of the arrival counter carries the first half's redo flag to the joiner)
+    if (tid == 0) fin[0] = __int_as_float(atomicAdd(prm.join_count + w, flag_any ? 257 : 1));
     group_sync<WARPS>();
-    if (__float_as_int(fin[0]) == 0) return;  // the other half is still walking; it will join
+    if ((__float_as_int(fin[0]) & 255) == 0) return;  // the other half is still walking; it will join
+    flag_any = flag_any || (__float_as_int(fin[0]) >> 8) != 0;
     __threadfence();
     // In forward numbering: A = alpha_m, B = b_{m+1}.  Reverse pair i holds the blank of forward
     // pair L - i and the label of forward pair L - 1 - i.
@@ -309,7 +602,8 @@ ctc_alpha_kernel(const AlphaParams prm) {
     if (tid == 0) {
         float nll = -acc * kLn2;
         if (acc < kNegThreshold || bad) nll = __int_as_float(0x7f800000);
-        prm.nll_out[w] = nll;
+        if (LIN && !bad && (flag_any || !(acc >= kNegThreshold))) redo_window();
+        else prm.nll_out[w] = nll;
     }
 }
 
@@ -319,7 +613,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
 extern cudaError_t g_last_cuda_error;
 extern uint64_t g_launch_count;
 
-template <int P, int WARPS, bool DENSE, int PITCH>
+template <int P, int WARPS, bool DENSE, int PITCH, bool LIN = false>
 static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     const int U = PITCH ? PITCH : (DENSE ? prm.V : (Lmax + 1));
@@ -334,9 +628,18 @@ static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
-    auto kern = ctc_alpha_kernel<P, WARPS, DENSE, PITCH>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = ctc_alpha_kernel<P, WARPS, DENSE, PITCH, LIN>;
+    // (one attribute call per instance and device while the request does not grow: it costs a
+    // microsecond of host time per launch, which shows next to a 60 us kernel)
+    static size_t smem_set[16] = {0};
+    int dev_id = 0;
+    cudaError_t e = cudaGetDevice(&dev_id);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    if (dev_id < 0 || dev_id >= 16 || smem > smem_set[dev_id]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+        if (dev_id >= 0 && dev_id < 16) smem_set[dev_id] = smem;
+    }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
     const int blocks = (prm.halves * prm.N + GROUPS - 1) / GROUPS;
     kern<<<blocks, threads, smem, stream>>>(prm);
@@ -365,6 +668,20 @@ static int dispatch_alpha(const AlphaParams &prm, int Lmax, LatticeShape s, cuda
     return IPFA_ERR_UNSUPPORTED;
 }
 
+// linear-domain instance: one warp per half window, P pairs per lane
+static int launch_alpha_lin(const AlphaParams &prm, int Lmax, int P, cudaStream_t stream) {
+#define IPFA_LIN(P_)                                                                          \
+    if (P == P_) {                                                                            \
+        if (prm.V <= 32) return launch_alpha_p<P_, 1, true, 32, true>(prm, Lmax, stream);     \
+        return launch_alpha_p<P_, 1, true, 0, true>(prm, Lmax, stream);                       \
+    }
+    IPFA_LIN(1) IPFA_LIN(2) IPFA_LIN(4) IPFA_LIN(8)
+#undef IPFA_LIN
+    return IPFA_ERR_UNSUPPORTED;
+}
+constexpr int kLinMaxPairs = 256;
+static int lin_pairs_per_lane(int units) { return units <= 32 ? 1 : units <= 64 ? 2 : units <= 128 ? 4 : 8; }
+
 bool use_dense_panel(int V, int Lmax) { return V <= 64 || V <= 2 * (Lmax + 1); }
 
 }  // namespace ipfa
@@ -376,9 +693,10 @@ static inline size_t alpha_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 // arrival counters [N] + the two halves' state vectors at the cut [N][2][2][Lmax + 1]
 extern "C" size_t ipfa_ctc_alpha_workspace_bytes(int N, int, int Lmax, int) {
     const size_t n = (size_t)(N > 0 ? N : 1), l1 = (size_t)(Lmax > 0 ? Lmax : 0) + 1;
-    // arrival counters, join vectors, length-bucket lists [2][N] + their counters
-    return alpha_pad256(n * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
-           alpha_pad256(n * 2 * sizeof(int32_t)) + 256 + 256;
+    // arrival counters (+ the redo counter right behind them: one memset), join vectors,
+    // length-bucket lists [2][N] + their counters, redo list [N]
+    return alpha_pad256((n + 1) * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
+           alpha_pad256(n * 2 * sizeof(int32_t)) + 256 + alpha_pad256(n * sizeof(int32_t)) + 256;
 }
 
 extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
@@ -410,9 +728,43 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     prm.join_count = static_cast<int *>(workspace);
     prm.join_vec = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) +
-                                             alpha_pad256((size_t)N * sizeof(int32_t)));
-    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, (size_t)N * sizeof(int32_t), st);
+                                             alpha_pad256(((size_t)N + 1) * sizeof(int32_t)));
+    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, ((size_t)N + 1) * sizeof(int32_t), st);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    // Dense panels whose lattice fits one warp: the linear-domain instance scores the windows and
+    // lists the ones it cannot vouch for; the log-domain instance below then runs over that list.
+    const bool lin = dense && Lmax + 1 <= kLinMaxPairs && !getenv("IPFA_ALPHA_LOG");
+    const size_t l1 = (size_t)Lmax + 1;
+    int32_t *order = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(prm.join_vec) +
+                                                 alpha_pad256((size_t)N * 4 * l1 * sizeof(float)));
+    int32_t *count = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(order) +
+                                                 alpha_pad256((size_t)N * 2 * sizeof(int32_t)));
+    int32_t *redo = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(count) + 256);
+    if (lin) {
+        prm.redo = redo;
+        prm.redo_count = prm.join_count + N;
+        const int P = lin_pairs_per_lane(Lmax + 1);
+        if (N >= kBucketMinWindows && P >= 2 && !getenv("IPFA_NO_BUCKETS")) {
+            e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
+            if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+            length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, 32 * P / 2, order, count);
+            ++g_launch_count;
+            for (int cls = 0; cls < 2; ++cls) {
+                prm.order = order + (int64_t)cls * N;
+                prm.count = count + cls;
+                const int rc = launch_alpha_lin(prm, Lmax, cls == 0 ? P / 2 : P, st);
+                if (rc) return rc;
+            }
+        } else {
+            const int rc = launch_alpha_lin(prm, Lmax, P, st);
+            if (rc) return rc;
+        }
+        prm.order = redo;
+        prm.count = prm.redo_count;
+        prm.redo = nullptr;
+        prm.redo_count = nullptr;
+        if (dense) return dispatch_alpha<true>(prm, Lmax, s, st);
+    }
     // two length buckets when the batch is large and a half-width instance exists (decided on the
     // device, see length_bucket_kernel)
     const int big_units = 32 * s.WARPS * s.PER, small_units = big_units / 2;
@@ -424,11 +776,6 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
         if (dense) return dispatch_alpha<true>(prm, Lmax, s, st);
         return dispatch_alpha<false>(prm, Lmax, s, st);
     }
-    const size_t l1 = (size_t)Lmax + 1;
-    int32_t *order = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(prm.join_vec) +
-                                                 alpha_pad256((size_t)N * 4 * l1 * sizeof(float)));
-    int32_t *count = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(order) +
-                                                 alpha_pad256((size_t)N * 2 * sizeof(int32_t)));
     e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, small_units, order, count);

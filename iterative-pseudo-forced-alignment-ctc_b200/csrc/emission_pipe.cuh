@@ -152,6 +152,11 @@ struct EmissionPipe {
         for (int c = 0; c < kStages - 1; ++c) issue(c, tid);
     }
 
+    // bulk mode: block until chunk `chunk` has landed (may be called again for the same chunk)
+    __device__ __forceinline__ void wait_landed(int chunk) {
+        mbar_wait(&bars[chunk % kStages], (uint32_t)(chunk / kStages) & 1u);
+    }
+
     // Make chunk `chunk` visible to the group and refill the stage freed by chunk-1.
     __device__ __forceinline__ const float *acquire(int chunk, int tid) {
         if (bulk) {

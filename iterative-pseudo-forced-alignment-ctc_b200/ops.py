@@ -103,6 +103,18 @@ def ctc_alpha_nll(lp, targets, in_len, tgt_len, blank=0, batch_first=True):
     return out
 
 
+def ctc_alpha_redo_count(n, device=None):
+    """How many of the `n` windows of the last :func:`ctc_alpha_nll` call on this device / stream the
+    linear-domain instance handed to the log-domain instance (its exactness guard fired, or the
+    targets were infeasible).  Diagnostic: reads the counter kept behind the `n` arrival counters at
+    the head of the workspace (csrc/ctc_alpha.cu); synchronises."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    buf = _ws_cache.get((dev.index, torch.cuda.current_stream(dev).cuda_stream))
+    if buf is None:
+        return 0
+    return int(buf[4 * n:4 * n + 4].view(torch.int32).item())
+
+
 def _np(a, dtype):
     if isinstance(a, torch.Tensor):
         a = a.numpy()

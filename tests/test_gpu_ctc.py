@@ -247,3 +247,93 @@ def test_alpha_length_buckets(ipfa, monkeypatch):
     fin = torch.isfinite(one)
     assert torch.equal(torch.isfinite(nll), fin)
     assert torch.allclose(nll[fin], one[fin], rtol=1e-5, atol=1e-5)
+
+
+# --- kernel (1), linear-domain (fp64) instance and its hand-over to the log-domain instance --------
+LIN_SHAPES = [(64, 200, 40, 32), (16, 400, 31, 32), (16, 400, 32, 32), (16, 400, 63, 8), (8, 900, 128, 32),
+              (4, 1200, 255, 64), (16, 17, 3, 32), (16, 15, 3, 32), (32, 257, 64, 33), (8, 30, 0, 32)]
+
+
+@pytest.mark.parametrize("shape", LIN_SHAPES)
+@pytest.mark.parametrize("peaked", [False, True])
+def test_alpha_linear_instance(ipfa, monkeypatch, shape, peaked):
+    """Dense panels with <= 256 state pairs run the linear-domain instance (csrc/ctc_alpha.cu, LIN):
+    same results as the oracle and as the log-domain instance, nothing handed over on ordinary
+    emissions."""
+    from oracle import ctc as octc
+    n, t, l, v = shape
+    lp, tg, il, tl = ctc_case(40 + l, n, t, l, v, ragged=True, repeats=True, peaked=peaked)
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    dev = [_dev(x) for x in (lp, tg, il, tl)]
+    lin = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+    assert ipfa.ctc_alpha_redo_count(n) == 0
+    _check_nll(lin, ref)
+    monkeypatch.setenv("IPFA_ALPHA_LOG", "1")
+    log = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+    monkeypatch.delenv("IPFA_ALPHA_LOG")
+    _check_nll(log, ref)
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(lin[fin], log[fin], rtol=2e-5)
+
+
+def test_alpha_linear_guard_hands_over(ipfa):
+    """Inputs the linear-domain instance cannot vouch for go through the redo list to the
+    log-domain instance: emissions sharper than its range, -inf emissions, a target that names the
+    blank, infeasible targets.  Results equal the oracle's either way."""
+    import torch
+    from oracle import ctc as octc
+    rng = np.random.default_rng(7)
+    n, t, l, v = 32, 300, 30, 32
+    tg = rng.integers(1, v, (n, l)).astype(np.int32)
+    il, tl = np.full(n, t, np.int32), np.full(n, l, np.int32)
+    for scale, expect_redo in ((8.0, False), (40.0, True), (200.0, True)):
+        raw = (rng.standard_normal((n, t, v)) * scale).astype(np.float32)
+        lp = torch.from_numpy(raw).log_softmax(-1).numpy()
+        got = ipfa.ctc_alpha_nll(_dev(lp), _dev(tg), _dev(il), _dev(tl)).cpu().numpy()
+        redo = ipfa.ctc_alpha_redo_count(n)
+        assert (redo > 0) == expect_redo, (scale, redo)
+        _check_nll(got, octc.ctc_alpha_nll(lp, tg, il, tl))
+    # -inf emissions: one symbol on a few frames of every other window, the blank everywhere in one
+    lp, tg, il, tl = ctc_case(3, 16, 120, 12, 32)
+    lp[::2, 5:9, 3] = -np.inf
+    lp[1, :, 0] = -np.inf
+    got = ipfa.ctc_alpha_nll(_dev(lp), _dev(tg), _dev(il), _dev(tl)).cpu().numpy()
+    assert ipfa.ctc_alpha_redo_count(16) >= 9
+    _check_nll(got, octc.ctc_alpha_nll(lp, tg, il, tl))
+    # infeasible (T < L + repeats): inf from the log-domain instance, like torch
+    lp, tg, il, tl = ctc_case(5, 8, 40, 30, 32, repeats=True)
+    il[:] = 33
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    assert np.isinf(ref).any()
+    got = ipfa.ctc_alpha_nll(_dev(lp), _dev(tg), _dev(il), _dev(tl)).cpu().numpy()
+    assert ipfa.ctc_alpha_redo_count(8) == int(np.isinf(ref).sum())
+    _check_nll(got, ref)
+
+
+def test_alpha_linear_blank_in_target(ipfa, monkeypatch):
+    """A target that names the blank symbol is handed over (the linear panel keeps raw logs in
+    the blank column); both instances agree."""
+    lp, tg, il, tl = ctc_case(4, 16, 120, 12, 32)
+    tg[::3, 4] = 0
+    dev = [_dev(x) for x in (lp, tg, il, tl)]
+    lin = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+    assert ipfa.ctc_alpha_redo_count(16) == 6
+    monkeypatch.setenv("IPFA_ALPHA_LOG", "1")
+    log = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+    monkeypatch.delenv("IPFA_ALPHA_LOG")
+    np.testing.assert_allclose(lin, log, rtol=1e-6)
+
+
+def test_alpha_linear_large_batch_buckets(ipfa, monkeypatch):
+    """Linear-domain instance on a large ragged batch (two length buckets, P and P/2 pairs per lane)."""
+    from oracle import ctc as octc
+    n, t, l, v = 4300, 64, 60, 32
+    lp, tg, il, tl = ctc_case(33, n, t, l, v, ragged=True, repeats=True)
+    tl[:6] = [0, 1, 31, 32, 33, 60]
+    il[:6] = t
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    dev = [_dev(x) for x in (lp, tg, il, tl)]
+    got = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+    n_inf = int(np.isinf(ref).sum())
+    assert ipfa.ctc_alpha_redo_count(n) == n_inf
+    _check_nll(got, ref)
