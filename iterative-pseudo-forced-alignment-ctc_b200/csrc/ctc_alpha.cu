@@ -15,7 +15,10 @@
 // CTA barrier per frame across warps.  Emission columns arrive through the
 // cp.async ring of emission_pipe.cuh, several frames ahead of the recursion.
 // The T-serial chain is MUFU/latency bound (2 ex2 + 1 lg2 per label state,
-// 1 + 1 per blank state), not HBM bound; see DESIGN.md.
+// 1 + 1 per blank state), not HBM bound; see DESIGN.md.  The same template has a second,
+// linear-domain instance (LIN, below: fp64 probabilities, per-thread power-of-two scales, an
+// exactness guard) that runs first on dense panels of <= 256 pairs and hands the windows it
+// cannot vouch for to this log-domain instance through a redo list.
 #include "emission_pipe.cuh"
 #include "lattice_shapes.cuh"
 
@@ -201,6 +204,22 @@ ctc_alpha_kernel(const AlphaParams prm) {
               prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid, t_lo, rev);
     pipe.prologue(tid);
 
+    // LIN: first frame (walk index) at which the lattice can have reached blank_p / label_p by the
+    // graph alone -- pair index + repeated labels so far (a repeat needs a blank in between);
+    // kNever for the states past the target.
+    constexpr int kNever = 0x7fffffff;
+    int needb[P], needl[P];
+    {
+        int cnt = rep_excl;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int j = tid * P + p;
+            const int isrep = (j < L && j >= 1 && !skip[p]) ? 1 : 0;
+            cnt += isrep;
+            needb[p] = (j <= L) ? j + cnt - isrep : kNever;
+            needl[p] = (j < L) ? j + cnt : kNever;
+        }
+    }
     int skipm[P];  // LIN: skip[p] as an all-ones / zero mask the compiler keeps in a register
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -223,7 +242,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
     const float *pl[P];          // cursors on the label columns
     auto frame = [&](const int off, const float *rd, float *wr) {
         if constexpr (LIN) {
-            sb += pb[off];
+            if constexpr (PITCH != 32) sb += pb[off];  // (PITCH == 32: summed by the conversion)
             double r[P];  // the panel holds the high word of the fp64 ratio (20 mantissa bits)
 #pragma unroll
             for (int p = 0; p < P; ++p) r[p] = __hiloint2double(__float_as_int(pl[p][off]), 0);
@@ -281,18 +300,15 @@ ctc_alpha_kernel(const AlphaParams prm) {
             constexpr int tiny_hi = (1023 + kLinTinyExp) << 20, huge_hi = (1023 + kLinHugeExp) << 20;
             int hmax = 0;
             bool ok = true;
-            int cnt = rep_excl;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const int j = tid * P + p;
-                const int isrep = (j < L && j >= 1 && !skip[p]) ? 1 : 0;
-                cnt += isrep;
-                const int need = j + cnt;
-                if (j > L) ab[p] = 0.0;   // the states past the target never feed a real one
-                if (j >= L) al[p] = 0.0;
-                const int hb = __double2hiint(ab[p]), hl = __double2hiint(al[p]);
-                if (j <= L && tcur >= need - isrep) ok = ok && (hb >= tiny_hi);
-                if (j < L && tcur >= need) ok = ok && (hl >= tiny_hi);
+                // the states past the target never feed a real one: their high word is cleared
+                // (what is left is a denormal, i.e. nothing) so that they stay out of the maximum
+                int hb = __double2hiint(ab[p]), hl = __double2hiint(al[p]);
+                if (needb[p] == kNever) { hb = 0; ab[p] = __hiloint2double(0, __double2loint(ab[p])); }
+                if (needl[p] == kNever) { hl = 0; al[p] = __hiloint2double(0, __double2loint(al[p])); }
+                if (tcur >= needb[p]) ok = ok && (hb >= tiny_hi);
+                if (tcur >= needl[p]) ok = ok && (hl >= tiny_hi);
                 hmax = max(hmax, max(hb, hl));
             }
             ok = ok && (hmax < huge_hi);
@@ -346,6 +362,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
+                    if (r0 + k < rows) sb += bv[k];
                     const uint32_t raw = ratio_raw(xv[k], bv[k]);
                     oor = max(oor, ratio_range(raw));
                     if (!keep && r0 + k < rows) cell[(r0 + k) * 32] = ratio_pack(raw);
@@ -386,10 +403,12 @@ ctc_alpha_kernel(const AlphaParams prm) {
         for (; j + 3 < rows; j += 4) {
             uint32_t raw0 = 0, raw1 = 0, raw2 = 0, raw3 = 0;
             if constexpr (PRE) {
-                raw0 = ratio_raw(qx[0], qb[0]);
-                raw1 = ratio_raw(qx[step], qb[step]);
-                raw2 = ratio_raw(qx[2 * step], qb[2 * step]);
-                raw3 = ratio_raw(qx[3 * step], qb[3 * step]);
+                const float b0 = qb[0], b1 = qb[step], b2 = qb[2 * step], b3 = qb[3 * step];
+                sb += (b0 + b1) + (b2 + b3);
+                raw0 = ratio_raw(qx[0], b0);
+                raw1 = ratio_raw(qx[step], b1);
+                raw2 = ratio_raw(qx[2 * step], b2);
+                raw3 = ratio_raw(qx[3 * step], b3);
             }
             frame(0, line1, line0);
             frame(step, line0, line1);
@@ -473,7 +492,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
                     ab[0] = 1.0;
                     if (L > 0) al[0] = __hiloint2double(__float_as_int(panel[first_row * pitch + col[0]]), 0);
                 }
-                sb = panel[first_row * pitch + colb];
+                if constexpr (PITCH != 32) sb = panel[first_row * pitch + colb];
             } else if (tid == 0) {
                 ab[0] = panel[first_row * pitch + colb];
                 if (L > 0) al[0] = panel[first_row * pitch + col[0]];
