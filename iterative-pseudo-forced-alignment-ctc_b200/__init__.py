@@ -8,7 +8,8 @@ the ``ipfa_b200`` alias module at the repository root.
 """
 from . import _lib  # noqa: F401
 from .ops import (ctc_alpha_nll, ctc_alpha_nll_host, ctc_forced_align, ctc_forced_align_host,  # noqa: F401
-                  ctcseg_align, ctcseg_align_host, anchor_select, launch_count, ctc_alpha_redo_count)
+                  ctcseg_align, ctcseg_align_host, anchor_select, launch_count, ctc_alpha_redo_count,
+                  ctc_alpha_redo_reasons)
 
 __all__ = ["ctc_alpha_nll", "ctc_alpha_nll_host", "ctc_forced_align", "ctc_forced_align_host",
-           "ctcseg_align", "ctcseg_align_host", "anchor_select", "launch_count", "ctc_alpha_redo_count"]
+           "ctcseg_align", "ctcseg_align_host", "anchor_select", "launch_count", "ctc_alpha_redo_count", "ctc_alpha_redo_reasons"]

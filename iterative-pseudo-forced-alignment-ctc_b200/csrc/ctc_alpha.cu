@@ -107,7 +107,7 @@ __device__ __forceinline__ float ratio_pack(const uint32_t bits) {
 template <int P, int WARPS, bool DENSE, int PITCH, bool LIN = false>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
 ctc_alpha_kernel(const AlphaParams prm) {
-    static_assert(!LIN || (WARPS == 1 && DENSE), "the linear-domain instance is one warp per half window, dense panel");
+    static_assert(!LIN || (WARPS <= 2 && DENSE), "the linear-domain instance: one or two warps per half window, dense panel");
     using State = std::conditional_t<LIN, double, float>;
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     constexpr int NT = 32 * WARPS;
@@ -128,6 +128,11 @@ ctc_alpha_kernel(const AlphaParams prm) {
     float *xline = ring + (size_t)kStages * prm.tc * pitch;  // [2][NT + 1] neighbour exchange (WARPS > 1)
     float *fin = xline + 2 * (NT + 1);                        // [2 + WARPS]
     int *cols = reinterpret_cast<int *>(fin + 2 + WARPS);     // [u_cap] (gather mode)
+    // LIN with two warps: fp64 exchange lines [2][NT + 1], scale exchange [NT + 1], scratch [NT]
+    double *dline = reinterpret_cast<double *>(
+        (reinterpret_cast<uintptr_t>(cols + prm.u_cap) + 7) & ~(uintptr_t)7);
+    int *eline = reinterpret_cast<int *>(dline + 2 * (NT + 1));
+    double *dscratch = reinterpret_cast<double *>(eline + NT + 2);
 
     const int T_all = prm.in_len[w];
     const int L = max(0, min(prm.tgt_len[w], prm.l_cap));
@@ -151,6 +156,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
     bool skip[P];    // s-2 transition allowed into label_p
     bool bad = false;
     bool flag = false;   // LIN: this window goes to the redo list
+    int why = 0;         // ... and why (diagnostic bits, OR-ed into redo_count[1])
     int rep_excl = 0;    // LIN: repeated labels (target[k] == target[k-1]) before this thread's pairs
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -162,20 +168,26 @@ ctc_alpha_kernel(const AlphaParams prm) {
         if (lab < 0 || lab >= prm.V) { bad = true; lab = blank; }
         // (the blank column of the LIN panel holds raw logs, not ratios: a target that names
         // the blank symbol is left to the log-domain instance)
-        if (LIN && lab_ok && lab == blank) flag = true;
+        if (LIN && lab_ok && lab == blank) { flag = true; why |= 1; }
         const int prev = (j >= 1 && lab_ok) ? target(j - 1) : -1;
         skip[p] = lab_ok && j >= 1 && prev != lab;
         if (LIN) rep_excl += (lab_ok && j >= 1 && prev == lab) ? 1 : 0;
         col[p] = DENSE ? lab : (lab_ok ? j + 1 : 0);
     }
-    if constexpr (LIN) {  // exclusive prefix over the lanes
+    if constexpr (LIN) {  // exclusive prefix over the lanes (two warps: + the first warp's total)
         int incl = rep_excl;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, off);
-            if (tid >= off) incl += v;
+            if ((tid & 31) >= off) incl += v;
         }
         rep_excl = incl - rep_excl;
+        if constexpr (WARPS > 1) {
+            if (tid == 31) fin[0] = __int_as_float(incl);
+            __syncthreads();
+            if (tid >= 32) rep_excl += __float_as_int(fin[0]);
+            __syncthreads();
+        }
     }
     int colb = DENSE ? blank : 0;
     int U = L + 1;  // panel columns
@@ -196,6 +208,8 @@ ctc_alpha_kernel(const AlphaParams prm) {
     }
     if constexpr (WARPS > 1) {
         if (tid < 2) xline[tid * (NT + 1)] = kNegBig;  // left neighbour of thread 0: log(0)
+        if (LIN && tid < 2) dline[tid * (NT + 1)] = 0.0;
+        if (LIN && tid == 0) eline[0] = 0;
     }
     group_sync<WARPS>();
 
@@ -247,7 +261,9 @@ ctc_alpha_kernel(const AlphaParams prm) {
 #pragma unroll
             for (int p = 0; p < P; ++p) r[p] = __hiloint2double(__float_as_int(pl[p][off]), 0);
             // lane 0 has no left neighbour: its rs is 0
-            const double prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1) * rs;
+            double prev;
+            if constexpr (WARPS > 1) prev = dline[(rd - xline) + tid] * rs;
+            else prev = __shfl_up_sync(0xffffffffu, al[P - 1], 1) * rs;
 #pragma unroll
             for (int p = P - 1; p >= 0; --p) {
                 const double lm1 = (p == 0) ? prev : al[p - 1];
@@ -258,6 +274,10 @@ ctc_alpha_kernel(const AlphaParams prm) {
                                                   (__double2loint(nb) & m) | (__double2loint(ab[p]) & ~m));
                 al[p] = (al[p] + x) * r[p];
                 ab[p] = nb;
+            }
+            if constexpr (WARPS > 1) {
+                dline[(wr - xline) + tid + 1] = al[P - 1];
+                __syncthreads();
             }
         } else {
             const float eb = pb[off];
@@ -290,7 +310,9 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // LIN: re-scaling + exactness guard, between two frames; `tcur` = walk index of the last frame
     // done.  Pair j's label is first alive at frame j + (repeats up to j), its blank one frame after
     // the previous label.
-    auto renorm = [&](const int tcur) {
+    // (two warps: `rdl` = offset of the exchange line the next frame reads, i.e. the one the last
+    // frame wrote; it is rewritten in the new scales)
+    auto renorm = [&](const int tcur, const int rdl) {
         if constexpr (LIN) {
             sb_total += (double)sb;
             sb = 0.0f;
@@ -311,27 +333,59 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 if (tcur >= needl[p]) ok = ok && (hl >= tiny_hi);
                 hmax = max(hmax, max(hb, hl));
             }
+            if (!ok) why |= 4;
+            if (!(hmax < huge_hi)) why |= 8;
             ok = ok && (hmax < huge_hi);
             // true exponents of this thread's largest state and of the value its left neighbour hands over
             const int A = (hmax >= (1 << 20)) ? (hmax >> 20) - 1023 - E : kLinEmpty;
-            const double b = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
-            const int El = __shfl_up_sync(0xffffffffu, E, 1);
-            const int B = (tid > 0 && __double2hiint(b) >= (1 << 20)) ? lin_exponent(b) - El : kLinEmpty;
+            double b;
+            int El;
+            if constexpr (WARPS > 1) {
+                eline[tid + 1] = E;
+                __syncthreads();
+                b = dline[rdl + tid];
+                El = eline[tid];
+            } else {
+                b = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+                El = __shfl_up_sync(0xffffffffu, E, 1);
+            }
+            // (the line holds what the last frame wrote: a left neighbour past the target has not
+            // been cleared there)
+            const int B = (tid > 0 && tid * P - 1 < L && __double2hiint(b) >= (1 << 20)) ? lin_exponent(b) - El
+                                                                                       : kLinEmpty;
             const int X = max(A, B);
             const bool empty = X <= kLinEmpty / 2;
             int Enew = kLinTarget - X;
-            // the lanes right of the frontier take the scale of the frontier lane
-            const unsigned ne = __ballot_sync(0xffffffffu, !empty);
-            const int Ead = __shfl_sync(0xffffffffu, Enew, ne ? 31 - __clz(ne) : 0);
+            // the lanes right of the frontier take the scale of the frontier lane (the lanes that
+            // hold something are a prefix of the group)
+            int Ead;
+            if constexpr (WARPS > 1) {
+                int *etmp = reinterpret_cast<int *>(dscratch);
+                etmp[tid] = Enew;
+                const int n_holding = __syncthreads_count(!empty);
+                Ead = etmp[max(n_holding - 1, 0)];
+            } else {
+                const unsigned ne = __ballot_sync(0xffffffffu, !empty);
+                Ead = __shfl_sync(0xffffffffu, Enew, ne ? 31 - __clz(ne) : 0);
+            }
             if (empty) Enew = Ead;
             const int d = Enew - E;
-            if (!empty && (d > 1000 || d < -1000)) ok = false;
+            if (!empty && (d > 1000 || d < -1000)) { ok = false; why |= 16; }
             const double f = lin_pow2(max(-1000, min(1000, d)));
 #pragma unroll
             for (int p = 0; p < P; ++p) { ab[p] *= f; al[p] *= f; }
             E = Enew;
-            const int d2 = E - __shfl_up_sync(0xffffffffu, E, 1);
-            if (tid > 0 && !empty && (d2 > 1000 || d2 < -1000)) ok = false;
+            int d2;
+            if constexpr (WARPS > 1) {
+                __syncthreads();  // everybody has read the old scales and the old line
+                eline[tid + 1] = E;
+                dline[rdl + tid + 1] = al[P - 1];
+                __syncthreads();
+                d2 = E - eline[tid];
+            } else {
+                d2 = E - __shfl_up_sync(0xffffffffu, E, 1);
+            }
+            if (tid > 0 && !empty && (d2 > 1000 || d2 < -1000)) { ok = false; why |= 32; }
             rs = (tid == 0) ? 0.0 : lin_pow2(max(-1000, min(1000, d2)));
             flag = flag || !ok;
         }
@@ -345,27 +399,30 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // (rounded to 20 mantissa bits); the blank column keeps its raw logs (summed on the side by
     // frame()).  A ratio that is not a normal fp32 <= 1e38 (zero, denormal, inf, NaN) sends the
     // window to the redo list.
-    const bool keep = tid == colb;  // PITCH == 32: one lane per column; this lane owns the blank column
+    const int lane = tid & 31, wrp = tid >> 5;
+    const bool keep = lane == colb;  // PITCH == 32: one lane per column; this lane owns the blank column
     uint32_t oor = 0;  // largest ratio_range() seen by this lane
     // whole chunk at once (8 rows in flight: the loads of a batch precede its stores)
     auto prescale_chunk = [&](float *panel, const int rows) {
         if constexpr (LIN && PITCH == 32) {
-            float *cell = panel + tid;
+            // (two warps: rows wrp, wrp + 2, ...; each warp sums the blank logs of its own rows)
+            float *cell = panel + lane;
             const float *bcell = panel + colb;
-            for (int r0 = 0; r0 < rows; r0 += 8) {
+            for (int r0 = wrp; r0 < rows; r0 += 8 * WARPS) {
                 float xv[8], bv[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int rr = min(r0 + k, rows - 1);
+                    const int rr = min(r0 + k * WARPS, rows - 1);
                     xv[k] = cell[rr * 32];
                     bv[k] = bcell[rr * 32];
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (r0 + k < rows) sb += bv[k];
+                    const bool in = r0 + k * WARPS < rows;
+                    if (in) sb += bv[k];
                     const uint32_t raw = ratio_raw(xv[k], bv[k]);
-                    oor = max(oor, ratio_range(raw));
-                    if (!keep && r0 + k < rows) cell[(r0 + k) * 32] = ratio_pack(raw);
+                    if (in) oor = max(oor, ratio_range(raw));
+                    if (!keep && in) cell[(r0 + k * WARPS) * 32] = ratio_pack(raw);
                 }
             }
         } else if constexpr (LIN) {
@@ -401,26 +458,27 @@ ctc_alpha_kernel(const AlphaParams prm) {
         };
         if ((j & 1) && j < rows) { frame(0, line0, line1); bump(1); ++j; }
         for (; j + 3 < rows; j += 4) {
-            uint32_t raw0 = 0, raw1 = 0, raw2 = 0, raw3 = 0;
+            // the 4 rows of the next chunk that go with these 4 frames: 4 / WARPS per warp (the
+            // cursors of warp w start w rows in)
+            constexpr int RPW = PRE ? 4 / WARPS : 1;
+            uint32_t raw[RPW];
             if constexpr (PRE) {
-                const float b0 = qb[0], b1 = qb[step], b2 = qb[2 * step], b3 = qb[3 * step];
-                sb += (b0 + b1) + (b2 + b3);
-                raw0 = ratio_raw(qx[0], b0);
-                raw1 = ratio_raw(qx[step], b1);
-                raw2 = ratio_raw(qx[2 * step], b2);
-                raw3 = ratio_raw(qx[3 * step], b3);
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    const float b = qb[i * WARPS * step];
+                    sb += b;
+                    raw[i] = ratio_raw(qx[i * WARPS * step], b);
+                }
             }
             frame(0, line1, line0);
             frame(step, line0, line1);
             frame(2 * step, line1, line0);
             frame(3 * step, line0, line1);
             if constexpr (PRE) {
-                oor = max(max(oor, ratio_range(raw0)), max(ratio_range(raw1), max(ratio_range(raw2), ratio_range(raw3))));
-                if (!keep) {
-                    qx[0] = ratio_pack(raw0);
-                    qx[step] = ratio_pack(raw1);
-                    qx[2 * step] = ratio_pack(raw2);
-                    qx[3 * step] = ratio_pack(raw3);
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    oor = max(oor, ratio_range(raw[i]));
+                    if (!keep) qx[i * WARPS * step] = ratio_pack(raw[i]);
                 }
                 qx += 4 * step;
                 qb += 4 * step;
@@ -437,6 +495,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // LIN with bulk-copied chunks of PITCH == 32: chunk c+1 is converted while chunk c is walked
     const bool lin_overlap = LIN && PITCH == 32 && pipe.bulk;
 
+    int last_par = 0;  // parity of the exchange line the last frame wrote
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
         float *panel;
         int rows;
@@ -453,7 +512,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 // chunk `chunk` is converted already; the stage of chunk-1 is free: refill it
                 panel = pipe.stage_ptr(chunk);
                 fence_proxy_async();
-                __syncwarp();
+                group_sync<WARPS>();
                 pipe.issue(chunk + kStages - 1, tid);
             }
             if (chunk + 1 < pipe.nchunks) {
@@ -462,7 +521,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 pre = chunk > 0 && rows_next == rows && (rows & 3) == 0;
                 if (!pre) prescale_chunk(pipe.stage_ptr(chunk + 1), rows_next);
             }
-            __syncwarp();
+            group_sync<WARPS>();
         } else {
             panel = const_cast<float *>(pipe.acquire(chunk, tid));
             rows = pipe.chunk_rows(chunk);
@@ -498,24 +557,26 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 if (L > 0) al[0] = panel[first_row * pitch + col[0]];
             }
             if constexpr (WARPS > 1) {
-                line0[tid + 1] = al[P - 1];
+                if constexpr (LIN) dline[tid + 1] = al[P - 1];
+                else line0[tid + 1] = al[P - 1];
                 __syncthreads();
             }
             j = 1;
         }
-        renorm(chunk * pipe.tc + j - 1);
+        renorm(chunk * pipe.tc + j - 1, ((j - 1) & 1) ? NT + 1 : 0);
+        last_par = (rows - 1) & 1;
         const int row = rev ? rows - 1 - j : j;
         pb = panel + row * pitch + colb;
 #pragma unroll
         for (int p = 0; p < P; ++p) pl[p] = panel + row * pitch + col[p];
         if constexpr (LIN && PITCH == 32) {
             if (pre) {  // j == 0 here: the 4-frame groups cover the whole chunk
-                float *nxt = pipe.stage_ptr(chunk + 1) + row * pitch;
-                qx = nxt + tid;
+                float *nxt = pipe.stage_ptr(chunk + 1) + (rev ? row - wrp : row + wrp) * pitch;
+                qx = nxt + lane;
                 qb = nxt + colb;
                 if (rev) run_rows(std::integral_constant<int, -2>{}, j, rows);
                 else run_rows(std::integral_constant<int, 2>{}, j, rows);
-                __syncwarp();
+                group_sync<WARPS>();
             }
         }
         if (!pre) {
@@ -528,9 +589,21 @@ ctc_alpha_kernel(const AlphaParams prm) {
     bool flag_any = false;
     double lin_bias = 0.0;
     if constexpr (LIN) {
-        if (oor > kRatioRangeMax && !keep && tid < prm.V) flag = true;
-        renorm(T - 1);
-        flag_any = __any_sync(0xffffffffu, flag);
+        if (oor > kRatioRangeMax && !keep && lane < prm.V) { flag = true; why |= 2; }
+        renorm(T - 1, last_par ? NT + 1 : 0);
+        if constexpr (WARPS > 1) {
+            flag_any = __syncthreads_or(flag) != 0;
+            if constexpr (PITCH == 32) {  // each warp summed the blank logs of its own rows
+                dscratch[tid] = sb_total;
+                __syncthreads();
+                sb_total = 0.0;
+#pragma unroll
+                for (int q = 0; q < WARPS; ++q) sb_total += dscratch[lane + 32 * q];
+            }
+        } else {
+            flag_any = __any_sync(0xffffffffu, flag);
+        }
+        if (flag) atomicOr(prm.redo_count + 1, why ? why : 64);
         lin_bias = sb_total * 1.4426950408889634 - (double)E;
     }
     auto log2_of = [&](const State v) -> float {
@@ -644,6 +717,8 @@ static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
     prm.l_cap = Lmax;
     size_t group_smem = g.ring_bytes + (2 * (32 * WARPS + 1) + 2 + WARPS) * sizeof(float) + (size_t)prm.u_cap * sizeof(int) + 40;
+    if (LIN && WARPS > 1)  // fp64 exchange lines, scale line, scratch (+ alignment)
+        group_smem += 2 * (32 * WARPS + 1) * sizeof(double) + (32 * WARPS + 2) * sizeof(int) + 32 * WARPS * sizeof(double) + 16;
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     const size_t smem = group_smem * GROUPS;
@@ -687,19 +762,34 @@ static int dispatch_alpha(const AlphaParams &prm, int Lmax, LatticeShape s, cuda
     return IPFA_ERR_UNSUPPORTED;
 }
 
-// linear-domain instance: one warp per half window, P pairs per lane
-static int launch_alpha_lin(const AlphaParams &prm, int Lmax, int P, cudaStream_t stream) {
-#define IPFA_LIN(P_)                                                                          \
-    if (P == P_) {                                                                            \
-        if (prm.V <= 32) return launch_alpha_p<P_, 1, true, 32, true>(prm, Lmax, stream);     \
-        return launch_alpha_p<P_, 1, true, 0, true>(prm, Lmax, stream);                       \
+// linear-domain instance: W (1 or 2) warps per half window, P pairs per lane
+static int launch_alpha_lin(const AlphaParams &prm, int Lmax, int P, int W, cudaStream_t stream) {
+#define IPFA_LIN(P_, W_)                                                                      \
+    if (P == P_ && W == W_) {                                                                 \
+        if (prm.V <= 32) return launch_alpha_p<P_, W_, true, 32, true>(prm, Lmax, stream);    \
+        return launch_alpha_p<P_, W_, true, 0, true>(prm, Lmax, stream);                      \
     }
-    IPFA_LIN(1) IPFA_LIN(2) IPFA_LIN(4) IPFA_LIN(8)
+    IPFA_LIN(1, 1) IPFA_LIN(2, 1) IPFA_LIN(4, 1) IPFA_LIN(8, 1)
+    IPFA_LIN(1, 2) IPFA_LIN(2, 2) IPFA_LIN(4, 2)
 #undef IPFA_LIN
     return IPFA_ERR_UNSUPPORTED;
 }
 constexpr int kLinMaxPairs = 256;
-static int lin_pairs_per_lane(int units) { return units <= 32 ? 1 : units <= 64 ? 2 : units <= 128 ? 4 : 8; }
+// pairs per lane / warps per half window for `units` state pairs: one warp per half window.
+// The two-warp instances (fp64 exchange line + CTA barrier per frame, as in the log-domain
+// instance) double the resident chains but measured slower on BASELINE configs[1] (113.6 us
+// against 106.4 us, profiles/r01_alpha_lin_parity_timing.txt); they stay reachable through
+// IPFA_ALPHA_LIN_SHAPE=P,W (tuning).
+static void lin_shape(int units, long long chains, int *P, int *W) {
+    *W = 1;
+    *P = units <= 32 ? 1 : units <= 64 ? 2 : units <= 128 ? 4 : 8;
+    (void)chains;
+    if (const char *e = getenv("IPFA_ALPHA_LIN_SHAPE")) {
+        int p = 0, w = 0;
+        if (sscanf(e, "%d,%d", &p, &w) == 2 && (w == 1 || w == 2) && (p == 1 || p == 2 || p == 4 || p == 8) &&
+            !(p == 8 && w == 2) && 32 * p * w >= units) { *P = p; *W = w; }
+    }
+}
 
 bool use_dense_panel(int V, int Lmax) { return V <= 64 || V <= 2 * (Lmax + 1); }
 
@@ -712,9 +802,9 @@ static inline size_t alpha_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 // arrival counters [N] + the two halves' state vectors at the cut [N][2][2][Lmax + 1]
 extern "C" size_t ipfa_ctc_alpha_workspace_bytes(int N, int, int Lmax, int) {
     const size_t n = (size_t)(N > 0 ? N : 1), l1 = (size_t)(Lmax > 0 ? Lmax : 0) + 1;
-    // arrival counters (+ the redo counter right behind them: one memset), join vectors,
+    // arrival counters (+ the redo counter and its reason bits right behind them: one memset), join vectors,
     // length-bucket lists [2][N] + their counters, redo list [N]
-    return alpha_pad256((n + 1) * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
+    return alpha_pad256((n + 2) * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
            alpha_pad256(n * 2 * sizeof(int32_t)) + 256 + alpha_pad256(n * sizeof(int32_t)) + 256;
 }
 
@@ -747,8 +837,8 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     prm.join_count = static_cast<int *>(workspace);
     prm.join_vec = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) +
-                                             alpha_pad256(((size_t)N + 1) * sizeof(int32_t)));
-    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, ((size_t)N + 1) * sizeof(int32_t), st);
+                                             alpha_pad256(((size_t)N + 2) * sizeof(int32_t)));
+    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, ((size_t)N + 2) * sizeof(int32_t), st);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     // Dense panels whose lattice fits one warp: the linear-domain instance scores the windows and
     // lists the ones it cannot vouch for; the log-domain instance below then runs over that list.
@@ -762,8 +852,9 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     if (lin) {
         prm.redo = redo;
         prm.redo_count = prm.join_count + N;
-        const int P = lin_pairs_per_lane(Lmax + 1);
-        if (N >= kBucketMinWindows && P >= 2 && !getenv("IPFA_NO_BUCKETS")) {
+        int P = 0, W = 0;
+        lin_shape(Lmax + 1, (long long)halves * N, &P, &W);
+        if (N >= kBucketMinWindows && W == 1 && P >= 2 && !getenv("IPFA_NO_BUCKETS")) {
             e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
             if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
             length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, 32 * P / 2, order, count);
@@ -771,11 +862,11 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
             for (int cls = 0; cls < 2; ++cls) {
                 prm.order = order + (int64_t)cls * N;
                 prm.count = count + cls;
-                const int rc = launch_alpha_lin(prm, Lmax, cls == 0 ? P / 2 : P, st);
+                const int rc = launch_alpha_lin(prm, Lmax, cls == 0 ? P / 2 : P, 1, st);
                 if (rc) return rc;
             }
         } else {
-            const int rc = launch_alpha_lin(prm, Lmax, P, st);
+            const int rc = launch_alpha_lin(prm, Lmax, P, W, st);
             if (rc) return rc;
         }
         prm.order = redo;

@@ -115,6 +115,17 @@ def ctc_alpha_redo_count(n, device=None):
     return int(buf[4 * n:4 * n + 4].view(torch.int32).item())
 
 
+def ctc_alpha_redo_reasons(n, device=None):
+    """OR of the reasons behind :func:`ctc_alpha_redo_count` (1 blank named by a target, 2 emission
+    ratio out of fp32 range, 4 a reachable state too small, 8 a state too large, 16 / 32 a scale
+    step / neighbouring scales too far apart); totals of zero (infeasible targets) set no bit."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    buf = _ws_cache.get((dev.index, torch.cuda.current_stream(dev).cuda_stream))
+    if buf is None:
+        return 0
+    return int(buf[4 * n + 4:4 * n + 8].view(torch.int32).item())
+
+
 def _np(a, dtype):
     if isinstance(a, torch.Tensor):
         a = a.numpy()

@@ -337,3 +337,19 @@ def test_alpha_linear_large_batch_buckets(ipfa, monkeypatch):
     n_inf = int(np.isinf(ref).sum())
     assert ipfa.ctc_alpha_redo_count(n) == n_inf
     _check_nll(got, ref)
+
+
+@pytest.mark.parametrize("shape_env", ["1,2", "2,2", "4,2", "8,1"])
+def test_alpha_linear_instance_shapes(ipfa, monkeypatch, shape_env):
+    """The other instances of the linear-domain kernel (two warps per half window, 8 pairs per
+    lane), forced through IPFA_ALPHA_LIN_SHAPE: same results, nothing handed over."""
+    from oracle import ctc as octc
+    p, w = (int(x) for x in shape_env.split(","))
+    l = min(32 * p * w - 1, 200)
+    lp, tg, il, tl = ctc_case(50 + l, 12, 3 * l + 40, l, 32, ragged=True, repeats=True, peaked=(p == 2))
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    monkeypatch.setenv("IPFA_ALPHA_LIN_SHAPE", shape_env)
+    got = ipfa.ctc_alpha_nll(*[_dev(x) for x in (lp, tg, il, tl)]).cpu().numpy()
+    monkeypatch.delenv("IPFA_ALPHA_LIN_SHAPE")
+    assert ipfa.ctc_alpha_redo_count(12) == int(np.isinf(ref).sum())
+    _check_nll(got, ref)

@@ -26,6 +26,8 @@ def run(lp, tg, il, tl, log):
         os.environ.pop("IPFA_ALPHA_LOG", None)
     out = ipfa.ctc_alpha_nll(torch.from_numpy(lp).to(dev), tg, il, tl).cpu().numpy()
     redo = 0 if log else ops.ctc_alpha_redo_count(len(il), dev)
+    if redo and "--why" in sys.argv:
+        print("   redo reasons:", ops.ctc_alpha_redo_reasons(len(il), dev))
     os.environ.pop("IPFA_ALPHA_LOG", None)
     return out, redo
 
@@ -49,10 +51,17 @@ for seed, (n, t, l, v) in enumerate([(64, 200, 40, 32), (32, 1000, 100, 32), (16
         cases.append((seed, n, t, l, v, ragged, repeats, peaked))
 if TIMING_ONLY:
     cases = []
+FORCED = os.environ.get("IPFA_ALPHA_LIN_SHAPE")
 for seed, n, t, l, v, ragged, repeats, peaked in cases:
     lp, tg, il, tl = ctc_case(seed, n, t, l, v, ragged=ragged, repeats=repeats, peaked=peaked)
     ref = octc.ctc_alpha_nll(lp, tg, il, tl)
     lin, redo = run(lp, tg, il, tl, False)
+    if not FORCED:  # the one-warp instances with the most pairs per lane as well
+        for shape in ("8,1", "4,2"):
+            os.environ["IPFA_ALPHA_LIN_SHAPE"] = shape
+            lin2, redo2 = run(lp, tg, il, tl, False)
+            os.environ.pop("IPFA_ALPHA_LIN_SHAPE")
+            assert relerr(lin2, ref) < 1e-4 and redo2 == redo, (shape, relerr(lin2, ref), redo2, redo)
     log, _ = run(lp, tg, il, tl, True)
     e_lin, e_log = relerr(lin, ref), relerr(log, ref)
     worst = max(worst, e_lin)
@@ -105,8 +114,10 @@ for k in range(3):
     sets.append((lp, tg))
 il = torch.full((n,), t, dtype=torch.int32, device=dev)
 tl = torch.full((n,), l, dtype=torch.int32, device=dev)
-for label, env in [("log", {"IPFA_ALPHA_LOG": "1"}), ("lin", {})]:
+for label, env in [("log", {"IPFA_ALPHA_LOG": "1"}), ("lin 4,1", {"IPFA_ALPHA_LIN_SHAPE": "4,1"}),
+                   ("lin 2,2", {"IPFA_ALPHA_LIN_SHAPE": "2,2"}), ("lin", {})]:
     os.environ.pop("IPFA_ALPHA_LOG", None)
+    os.environ.pop("IPFA_ALPHA_LIN_SHAPE", None)
     os.environ.update(env)
     for i in range(6):
         out = ipfa.ctc_alpha_nll(*sets[i % 3], il, tl)
@@ -118,7 +129,7 @@ for label, env in [("log", {"IPFA_ALPHA_LOG": "1"}), ("lin", {})]:
     b.record()
     torch.cuda.synchronize()
     print(f"c2 {label}: {a.elapsed_time(b) / 30 * 1000:.1f} us per call; nll[0]={float(out[0]):.4f}"
-          f" redo={ops.ctc_alpha_redo_count(n, dev) if label == 'lin' else '-'}")
+          f" redo={ops.ctc_alpha_redo_count(n, dev) if label != 'log' else '-'}")
     # host time per call (no synchronisation inside the loop)
     import time
     torch.cuda.synchronize()
@@ -149,4 +160,5 @@ for label, env in [("log", {"IPFA_ALPHA_LOG": "1"}), ("lin", {})]:
         side.synchronize()
     print(f"c2 {label}: graph replay {a.elapsed_time(b) / 30 * 1000:.1f} us per call; nll[0]={float(outs[0][0]):.4f}")
 os.environ.pop("IPFA_ALPHA_LOG", None)
+os.environ.pop("IPFA_ALPHA_LIN_SHAPE", None)
 print("worst lin rel err", worst)
