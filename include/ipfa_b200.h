@@ -68,6 +68,14 @@ int ipfa_device_count(void);
  *   targets   [N, Lmax] int32 (row stride tgt_stride), no blanks required
  *   in_len    [N] int32 frames per window, tgt_len [N] int32 labels per window
  *   nll_out   [N] fp32: -log p(target | window); +inf when infeasible
+ *   workspace caller-owned scratch of ipfa_ctc_alpha_workspace_bytes() bytes; its first
+ *             N + 2 int32 words end a call as: [0, N) arrival counters, [N] number
+ *             of windows the linear-domain (fp64) instance handed to the log-domain
+ *             instance, [N + 1] OR of the reasons (1 target names the blank, 2 emission
+ *             ratio outside fp32, 4 reachable state too small, 8 state too large,
+ *             16 / 32 scale step / neighbouring scales too far apart).  Diagnostic
+ *             only: results are the same either way (csrc/ctc_alpha.cu).
+ * Environment: IPFA_ALPHA_LOG=1 scores with the log-domain instance alone.
  * ------------------------------------------------------------------------- */
 size_t ipfa_ctc_alpha_workspace_bytes(int N, int Tmax, int Lmax, int V);
 int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
