@@ -12,6 +12,7 @@ from oracle import ctcseg as oseg
 from test_gpu_ctcseg import _pack
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None   # e.g. "alpha" or "alpha,viterbi"
 rng = np.random.default_rng(int(time.time()) % 100000)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 t_end = time.time() + budget
@@ -19,6 +20,8 @@ n_cases = n_bad = 0
 counts = {}
 while time.time() < t_end:
     kind = rng.choice(["alpha", "viterbi", "seg", "windowed", "sweep"], p=[0.3, 0.3, 0.2, 0.15, 0.05])
+    if only and kind not in only:
+        continue
     counts[kind] = counts.get(kind, 0) + 1
     seed = int(rng.integers(1 << 30))
     try:
@@ -36,7 +39,25 @@ while time.time() < t_end:
             desc = f"{kind} n={n} t={t} l={l} v={v}"
             if kind == "alpha":
                 ref = octc.ctc_alpha_nll(lp, tg, il, tl)
-                got = ipfa.ctc_alpha_nll(dev(lp), dev(tg), dev(il), dev(tl)).cpu().numpy()
+                # the window scorer's instances: default choice, a forced linear-domain shape, log-domain alone
+                mode = rng.choice(["default", "shape", "log"], p=[0.5, 0.35, 0.15])
+                if mode == "shape":
+                    os.environ["IPFA_ALPHA_LIN_SHAPE"] = str(rng.choice(["1,1", "2,1", "4,1", "8,1", "1,2", "2,2", "4,2"]))
+                    desc += " lin_shape=" + os.environ["IPFA_ALPHA_LIN_SHAPE"]
+                elif mode == "log":
+                    os.environ["IPFA_ALPHA_LOG"] = "1"
+                    desc += " log"
+                if rng.random() < 0.2:   # sharper emissions: some windows go through the redo list
+                    sc = float(rng.choice([4.0, 20.0, 60.0]))
+                    lp = torch.from_numpy(lp * sc).log_softmax(-1).numpy()
+                    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+                    desc += f" sharp x{sc}"
+                try:
+                    got = ipfa.ctc_alpha_nll(dev(lp), dev(tg), dev(il), dev(tl)).cpu().numpy()
+                finally:
+                    os.environ.pop("IPFA_ALPHA_LIN_SHAPE", None)
+                    os.environ.pop("IPFA_ALPHA_LOG", None)
+                counts["alpha_redo"] = counts.get("alpha_redo", 0) + ipfa.ctc_alpha_redo_count(n)
                 fin = np.isfinite(ref)
                 ok = np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], ref[fin], rtol=1e-4, atol=1e-4)
             else:
