@@ -57,7 +57,8 @@ struct AlphaParams {
 //   blank_p <- blank_p + label_{p-1}
 //   label_p <- (label_p + (skip_p ? blank_p' : blank_p)) * r_p,   r = exp(lp[label] - lp[blank])
 // Range: every thread carries its own power-of-two scale 2^E for its 2P states, re-chosen once
-// per emission chunk (<= 32 frames) so that its largest state sits at 2^kLinTarget; the value
+// per emission chunk (<= 32 frames) so that its largest state (or the value handed over by its
+// left neighbour, if larger) sits at 2^kLinTarget; the value
 // received from the left neighbour is rescaled by 2^(E - E_left), constant between two
 // re-scalings.  Exactness guard: at every re-scaling each state the lattice can have reached
 // (by the graph alone: frame index >= minimal arrival time) must hold a normal number
@@ -396,9 +397,9 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // DIR = -1 (reverse half): rows rows-1, rows-2, ...; the 4 unrolled frames sit at immediate
     // offsets from the cursors either way.
     // LIN: an emission becomes the RATIO exp(x - x_blank), stored as the high word of its fp64
-    // (rounded to 20 mantissa bits); the blank column keeps its raw logs (summed on the side by
-    // frame()).  A ratio that is not a normal fp32 <= 1e38 (zero, denormal, inf, NaN) sends the
-    // window to the redo list.
+    // (rounded to 20 mantissa bits); the blank column keeps its raw logs, which the conversion
+    // also sums on the side (PITCH == 32; frame() does it for the generic pitch).  A ratio that is
+    // not a normal fp32 <= 1e38 (zero, denormal, inf, NaN) sends the window to the redo list.
     const int lane = tid & 31, wrp = tid >> 5;
     const bool keep = lane == colb;  // PITCH == 32: one lane per column; this lane owns the blank column
     uint32_t oor = 0;  // largest ratio_range() seen by this lane
