@@ -56,8 +56,8 @@ struct AlphaParams {
 // logs on the side), so that a pair costs 2 DADD + 1 DMUL + 1 select and no MUFU:
 //   blank_p <- blank_p + label_{p-1}
 //   label_p <- (label_p + (skip_p ? blank_p' : blank_p)) * r_p,   r = exp(lp[label] - lp[blank])
-// Range: every thread carries its own power-of-two scale 2^E for its 2P states, re-chosen once
-// per emission chunk (<= 32 frames) so that its largest state (or the value handed over by its
+// Range: every thread carries its own power-of-two scale 2^E for its 2P states, re-chosen every
+// second emission chunk (<= 64 frames) so that its largest state (or the value handed over by its
 // left neighbour, if larger) sits at 2^kLinTarget; the value
 // received from the left neighbour is rescaled by 2^(E - E_left), constant between two
 // re-scalings.  Exactness guard: at every re-scaling each state the lattice can have reached
@@ -71,6 +71,7 @@ constexpr int kLinTarget = 100;
 constexpr int kLinTinyExp = -700;
 constexpr int kLinHugeExp = 1000;
 constexpr int kLinEmpty = -(1 << 28);
+constexpr int kLinRescaleChunks = 2;  // chunks (of <= 32 frames) between two re-scalings
 
 __device__ __forceinline__ double lin_pow2(int d) {  // 2^d, d clamped to the normal range
     d = max(-1022, min(1023, d));
@@ -402,7 +403,11 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // not a normal fp32 <= 1e38 (zero, denormal, inf, NaN) sends the window to the redo list.
     const int lane = tid & 31, wrp = tid >> 5;
     const bool keep = lane == colb;  // PITCH == 32: one lane per column; this lane owns the blank column
-    uint32_t oor = 0;  // largest ratio_range() seen by this lane
+    // PITCH == 32: largest |x - x_blank| this lane has converted; the ratio is a normal fp32 exactly
+    // when it is <= kMaxLogRatio (one FMNMX per emission; a NaN slips through here and is caught as
+    // a state above 2^kLinHugeExp, its packed ratio being 2^128)
+    float dmax = 0.0f;
+    constexpr float kMaxLogRatio = 87.0f;
     // whole chunk at once (8 rows in flight: the loads of a batch precede its stores)
     auto prescale_chunk = [&](float *panel, const int rows) {
         if constexpr (LIN && PITCH == 32) {
@@ -421,8 +426,9 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 for (int k = 0; k < 8; ++k) {
                     const bool in = r0 + k * WARPS < rows;
                     if (in) sb += bv[k];
-                    const uint32_t raw = ratio_raw(xv[k], bv[k]);
-                    if (in) oor = max(oor, ratio_range(raw));
+                    const float d = xv[k] - bv[k];
+                    if (in) dmax = fmaxf(dmax, fabsf(d));
+                    const uint32_t raw = __float_as_uint(ex2_approx(d * kLog2e));
                     if (!keep && in) cell[(r0 + k * WARPS) * 32] = ratio_pack(raw);
                 }
             }
@@ -468,7 +474,9 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 for (int i = 0; i < RPW; ++i) {
                     const float b = qb[i * WARPS * step];
                     sb += b;
-                    raw[i] = ratio_raw(qx[i * WARPS * step], b);
+                    const float d = qx[i * WARPS * step] - b;
+                    dmax = fmaxf(dmax, fabsf(d));
+                    raw[i] = __float_as_uint(ex2_approx(d * kLog2e));
                 }
             }
             frame(0, line1, line0);
@@ -478,7 +486,6 @@ ctc_alpha_kernel(const AlphaParams prm) {
             if constexpr (PRE) {
 #pragma unroll
                 for (int i = 0; i < RPW; ++i) {
-                    oor = max(oor, ratio_range(raw[i]));
                     if (!keep) qx[i * WARPS * step] = ratio_pack(raw[i]);
                 }
                 qx += 4 * step;
@@ -564,7 +571,8 @@ ctc_alpha_kernel(const AlphaParams prm) {
             }
             j = 1;
         }
-        renorm(chunk * pipe.tc + j - 1, ((j - 1) & 1) ? NT + 1 : 0);
+        // re-scaling + guard: after the first frame, then every kLinRescaleChunks-th chunk
+        if (chunk % kLinRescaleChunks == 0) renorm(chunk * pipe.tc + j - 1, ((j - 1) & 1) ? NT + 1 : 0);
         last_par = (rows - 1) & 1;
         const int row = rev ? rows - 1 - j : j;
         pb = panel + row * pitch + colb;
@@ -590,7 +598,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
     bool flag_any = false;
     double lin_bias = 0.0;
     if constexpr (LIN) {
-        if (oor > kRatioRangeMax && !keep && lane < prm.V) { flag = true; why |= 2; }
+        if (!(dmax <= kMaxLogRatio) && !keep && lane < prm.V) { flag = true; why |= 2; }
         renorm(T - 1, last_par ? NT + 1 : 0);
         if constexpr (WARPS > 1) {
             flag_any = __syncthreads_or(flag) != 0;
@@ -667,10 +675,21 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // In forward numbering: A = alpha_m, B = b_{m+1}.  Reverse pair i holds the blank of forward
     // pair L - i and the label of forward pair L - 1 - i.
     const float *fwd = vec_w, *bwd = vec_w + 2 * vstride;
-    auto A_b = [&](int j) { return __ldcg(fwd + j); };
-    auto A_l = [&](int j) { return __ldcg(fwd + vstride + j); };
-    auto B_b = [&](int j) { return __ldcg(bwd + (L - j)); };
-    auto B_l = [&](int j) { return __ldcg(bwd + vstride + (L - 1 - j)); };
+    if constexpr (LIN) {
+        // both halves' vectors (4 x (l_cap + 1) floats <= 4 KB) come through the emission ring,
+        // idle by now: independent loads, one L2 round trip instead of one per dependent step
+        float *stage = ring;
+        const int nvec = 4 * (int)vstride;
+        for (int i = tid; i < nvec; i += NT) stage[i] = __ldcg(vec_w + i);
+        group_sync<WARPS>();
+        fwd = stage;
+        bwd = stage + 2 * vstride;
+    }
+    auto ld = [&](const float *q) { return LIN ? *q : __ldcg(q); };
+    auto A_b = [&](int j) { return ld(fwd + j); };
+    auto A_l = [&](int j) { return ld(fwd + vstride + j); };
+    auto B_b = [&](int j) { return ld(bwd + (L - j)); };
+    auto B_l = [&](int j) { return ld(bwd + vstride + (L - 1 - j)); };
     float acc = kNegBig;
     for (int j = tid; j <= L; j += NT) {
         // blank j -> {blank j, label j}
