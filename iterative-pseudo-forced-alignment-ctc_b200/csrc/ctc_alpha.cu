@@ -675,17 +675,22 @@ ctc_alpha_kernel(const AlphaParams prm) {
     // In forward numbering: A = alpha_m, B = b_{m+1}.  Reverse pair i holds the blank of forward
     // pair L - i and the label of forward pair L - 1 - i.
     const float *fwd = vec_w, *bwd = vec_w + 2 * vstride;
+    bool staged = false;
     if constexpr (LIN) {
         // both halves' vectors (4 x (l_cap + 1) floats <= 4 KB) come through the emission ring,
         // idle by now: independent loads, one L2 round trip instead of one per dependent step
-        float *stage = ring;
+        // (unless a tuning override shrank the ring below that)
         const int nvec = 4 * (int)vstride;
-        for (int i = tid; i < nvec; i += NT) stage[i] = __ldcg(vec_w + i);
-        group_sync<WARPS>();
-        fwd = stage;
-        bwd = stage + 2 * vstride;
+        staged = nvec <= kStages * prm.tc * pitch;
+        if (staged) {
+            float *stage = ring;
+            for (int i = tid; i < nvec; i += NT) stage[i] = __ldcg(vec_w + i);
+            group_sync<WARPS>();
+            fwd = stage;
+            bwd = stage + 2 * vstride;
+        }
     }
-    auto ld = [&](const float *q) { return LIN ? *q : __ldcg(q); };
+    auto ld = [&](const float *q) { return staged ? *q : __ldcg(q); };
     auto A_b = [&](int j) { return ld(fwd + j); };
     auto A_l = [&](int j) { return ld(fwd + vstride + j); };
     auto B_b = [&](int j) { return ld(bwd + (L - j)); };
