@@ -70,3 +70,16 @@ def test_invalid_arguments_are_rejected(libmod):
     assert L.ipfa_ctc_alpha_workspace_bytes(4, 10, 2, 8) > 0
     assert L.ipfa_ctc_viterbi_workspace_bytes(4, 10, 2, 8) >= 4 * 3 * 32 * 4
     assert L.ipfa_ctcseg_workspace_bytes(2, 100, 20, 3, 8) > 0
+
+
+def test_alpha_workspace_holds_its_documented_parts(libmod):
+    """include/ipfa_b200.h: N + 2 counter words, the two halves' state vectors of every window
+    ([N][2][2][Lmax + 1] fp32), the two length-bucket lists and the redo list ([3][N] int32)."""
+    L = libmod.lib()
+    for n, lmax in ((1, 0), (7, 1), (1024, 100), (4300, 40), (65536, 40)):
+        need = (n + 2) * 4 + n * 4 * (lmax + 1) * 4 + 3 * n * 4
+        got = L.ipfa_ctc_alpha_workspace_bytes(n, 1000, lmax, 32)
+        assert need <= got <= need + 8 * 256, (n, lmax, got, need)
+    # monotone in N (the host entry point sizes one workspace for all its chunks)
+    sizes = [L.ipfa_ctc_alpha_workspace_bytes(n, 1000, 100, 32) for n in (1, 100, 132, 1024)]
+    assert sizes == sorted(sizes)
