@@ -96,3 +96,54 @@ def test_infeasible_target_has_zero_total():
         got = lin_nll(lp[i, :33], tg[i].astype(np.int64))
         ref = octc.ctc_alpha_nll(lp[i:i + 1, :33], tg[i:i + 1], np.array([33], np.int32), tl[i:i + 1])[0]
         assert np.isinf(got) == np.isinf(ref)
+
+
+def _arrival_formula(tg):
+    """First frame (0-based) at which blank_j / label_j can be alive, as csrc/ctc_alpha.cu computes it
+    for its exactness guard: pair index + repeated labels so far (a repeat needs a blank in between)."""
+    L = len(tg)
+    reps = 0
+    need_l, need_b = [], [0]
+    for j in range(L):
+        isrep = 1 if (j >= 1 and tg[j] == tg[j - 1]) else 0
+        reps += isrep
+        need_l.append(j + reps)
+        if j >= 1:
+            need_b[j] = need_l[j] - isrep
+        need_b.append(0)
+    need_b[L] = (need_l[L - 1] + 1) if L else 0
+    return need_b[:L + 1], need_l
+
+
+def _arrival_bruteforce(tg, T):
+    L = len(tg)
+    S = 2 * L + 1
+    alive = np.zeros(S, bool)
+    alive[0] = True
+    if L:
+        alive[1] = True
+    first = np.where(alive, 0, -1)
+    for t in range(1, T):
+        new = alive.copy()
+        new[1:] |= alive[:-1]
+        for s in range(3, S, 2):              # skip s-2 -> s between different labels
+            if tg[s // 2] != tg[s // 2 - 1]:
+                new[s] |= alive[s - 2]
+        first[(first < 0) & new] = t
+        alive = new
+    return first
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_guard_arrival_times_are_exact(seed):
+    """The guard of the linear-domain instance only vouches for a window if every state that CAN be
+    alive holds a normal number, so its arrival times must be the graph's, not an over-estimate."""
+    rng = np.random.default_rng(seed)
+    L = int(rng.integers(0, 24))
+    tg = rng.integers(1, 4, L)                # small alphabet: many repeats
+    need_b, need_l = _arrival_formula(tg)
+    first = _arrival_bruteforce(tg, 3 * L + 4)
+    for j in range(L + 1):
+        assert first[2 * j] == need_b[j], (tg, j)
+    for j in range(L):
+        assert first[2 * j + 1] == need_l[j], (tg, j)
