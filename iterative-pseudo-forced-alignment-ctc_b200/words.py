@@ -20,16 +20,31 @@ SOS_COLUMNS = ['Sample_ID', 'Sample_Path', 'Audio_Length', 'Start', 'End', 'Segm
                'Database']
 
 
+def _spanish_number_words():
+    """``num2words(n, lang='es')`` when the package is installed (text_utils.py:4, :39-46)."""
+    try:
+        from num2words import num2words
+    except ImportError:
+        return None
+    return lambda n: num2words(n, lang='es')
+
+
 def normalize_transcript(transcript, number_to_words=None):
-    """text_utils.py:49-78 without the num2words dependency (absent in this image):
-    ``number_to_words`` is an optional callable int -> str; digits are kept otherwise."""
+    """text_utils.py:49-78.  Numbers are spelled out through ``number_to_words`` (int -> str),
+    by default num2words' Spanish like the reference; where that package is missing (this image)
+    a transcript that contains digits is an error rather than a silently different ground truth."""
     out = re.sub(r"<font color=\"#[0-9a-fA-F]{6}\">", "", transcript)
     out = re.sub(r"</font>", "", out).replace('\n', ' ')
     out = out.translate(str.maketrans('', '', string.punctuation)).lower()
     out = out.replace('!', '').replace('¡', '').replace('?', '').replace('¿', '')
     out = out.replace('   ', ' ').replace('  ', ' ')
-    if number_to_words is not None:
-        for number in [int(s) for s in out.split() if s.isdigit()]:
+    numbers = [int(s) for s in out.split() if s.isdigit()]
+    if numbers:
+        number_to_words = number_to_words or _spanish_number_words()
+        if number_to_words is None:
+            raise ImportError("the transcript contains numbers and num2words is not installed "
+                              "(pass number_to_words=...)")
+        for number in numbers:
             out = out.replace(str(number), number_to_words(number))
     return out
 

@@ -2,10 +2,15 @@
 /root/reference/src/postprocess/postprocess_and_filter.py:54-77 (same CLI, same output name)."""
 import argparse
 import os
+import wave
 
 import pandas as pd
 
-from _common import hostglue
+
+def _audio_seconds(path):
+    """torchaudio.info(path).num_frames / sample_rate (:22-23) from the WAV header."""
+    with wave.open(path, 'rb') as w:
+        return w.getnframes() / w.getframerate()
 
 
 def main(args):
@@ -26,8 +31,7 @@ def main(args):
         for _, row in out.iterrows():
             path = row['Sample_Path']
             if path not in lengths:
-                info = hostglue.audio_info(path)
-                lengths[path] = info.num_frames / info.sample_rate
+                lengths[path] = _audio_seconds(path)
             end = float(row['End'])
             ends.append(lengths[path] if (end + delta) > lengths[path] else end + delta)
         out = out.drop('End', axis=1)

@@ -252,3 +252,9 @@ class WordsCase:
         with open(os.path.join(root, self.config_rel), "w") as f:
             json.dump({"words": self.wanted}, f)
         return self
+
+
+def asr_factory(savedir, device):
+    """``--asr_hub py:ref_cases:asr_factory --asr_savedir <case name>``: the acoustic-model double
+    of an anchor case for the product's entry points (``src/_common.load_asr``)."""
+    return anchor_cases()[savedir].asr(device)

@@ -117,7 +117,7 @@ def test_search_words_and_stm_cli(tmp_path):
     assert out['Sample_ID'].tolist() == ['a', 'c'] and out['Wanted_Text'].tolist() == ['HOLA', 'HOLA']
     stm_dir = tmp_path / "stm"
     stm_dir.mkdir()
-    subprocess.run([sys.executable, os.path.join(ROOT, "src", "tsv_to_stm.py"), "--src_path", str(tmp_path),
+    subprocess.run([sys.executable, os.path.join(ROOT, "src", "scripts", "tsv_to_stm.py"), "--src_path", str(tmp_path),
                     "--dst_path", str(stm_dir)], check=True, env=env, capture_output=True)
     lines = (stm_dir / "set.stm").read_text().splitlines()
     assert lines[2] == "set 1 s 2.0 3.123 <,,> hola otra vez"

@@ -107,9 +107,9 @@ def test_post_step_writers_match_the_reference_scripts(tmp_path):
         shutil.copy(os.path.join(GOLDEN, "results", name + ".tsv"), os.path.join(root, "results"))
     pd.concat([c.df for c in cases.values()], ignore_index=True).to_csv(os.path.join(root, "tsv", "all.tsv"), sep="\t",
                                                                         index=None)
-    _run_src("merge_aligned_files.py", "--global_tsv", "tsv/all.tsv", "--src", "results", cwd=root)
-    _run_src("tsv_to_stm.py", "--src_path", "results", "--dst_path", "results/stm", cwd=root)
-    _run_src("postprocess_and_filter.py", "--tsv", "results/all_aligned.tsv", "--score", "-1.0", "--comp", "gt",
+    _run_src("postprocess/merge_aligned_files.py", "--global_tsv", "tsv/all.tsv", "--src", "results", cwd=root)
+    _run_src("scripts/tsv_to_stm.py", "--src_path", "results", "--dst_path", "results/stm", cwd=root)
+    _run_src("postprocess/postprocess_and_filter.py", "--tsv", "results/all_aligned.tsv", "--score", "-1.0", "--comp", "gt",
              "--collar", "0.2", "--left_offset", "-0.05", "--right_offset", "0.05", cwd=root)
     for rel in ["results/all_aligned.tsv", "results/all_aligned_gt_-1.0_filtered.tsv"] + \
             ["results/stm/" + f for f in sorted(os.listdir(os.path.join(GOLDEN, "results", "stm")))]:
