@@ -205,6 +205,12 @@ int ipfa_anchor_select_device(const double *seg, const int32_t *n_utts,
                               int N, int Kmax, double threshold, int short_len,
                               int32_t *decision_out, double *anchor_out, void *stream);
 
+/* out[i] = float(f"{x[i]:.{decimals}f}"): the text round trip every start / end (2 decimals) and
+ * score (4 decimals) goes through between `str(task)` and `float(segment[i])`
+ * (/root/reference/src/iterative_utterance_alignment.py:218-230), as kernel (3) and the anchor sweep
+ * apply it on the device: the exact binary value rounded half-to-even at that decimal, like printf. */
+int ipfa_text_round_device(const double *x, int64_t n, int decimals, double *out, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * ipfa_ctcseg_device for windows that are SLICES of resident emissions: window w
  * starts at lp + win_off[w] (elements; device array) instead of lp + w * stride_n.
@@ -284,7 +290,7 @@ typedef struct ipfa_sweep_corpus {
 
 /* Per-file loop state (device arrays [F], read and written by the sweep).  Initial values:
  * row = utt = exc = next_ns = n_windows = cells = frames = 0, anchor = follow_start = NaN (None),
- * prop = 0.0, status = IPFA_SWEEP_ACTIVE, recalc_row = -1. */
+ * prop = 0.0, status = IPFA_SWEEP_ACTIVE, recalc_row = -1, clip = (-1, -1). */
 typedef struct ipfa_sweep_state {
     int32_t *row;          /* next TSV row of the file */
     int32_t *utt;          /* first utterance not accepted yet (the pending/discarded ones follow) */
@@ -299,6 +305,10 @@ typedef struct ipfa_sweep_state {
     int32_t *n_windows;    /* windows aligned so far */
     int64_t *cells;        /* trellis cells (frames x columns) filled so far */
     int64_t *frames;       /* window frames aligned so far */
+    int64_t *clip;         /* [F][2] (first sample, samples) of the last clip torchaudio.load accepted
+                              (:149-156); -1 = none yet.  A clip that ends before it starts is refused
+                              by torchaudio==0.11 ("num_frames must be -1 or greater than 0") and the
+                              reference goes on with the previous clip's audio (:157-159). */
 } ipfa_sweep_state;
 
 typedef struct ipfa_sweep_params {
@@ -323,6 +333,8 @@ typedef struct ipfa_sweep_params {
 #define IPFA_SWEEP_NEEDS_RECALC 4    /* :119-146 fix_text_to_time_proportion is host policy: re-spread the
                                         rows, upload them, set recalc_row = row, status = ACTIVE */
 #define IPFA_SWEEP_CAPACITY 5        /* window exceeds (Tmax, Cmax, Kmax): see need[], grow and continue */
+#define IPFA_SWEEP_NO_AUDIO 6        /* the file's FIRST clip was refused by torchaudio.load: the reference
+                                        dies of a NameError at :162; host policy */
 
 /* out_seg [slots][4] fp64: (clip_start, start, end, score) of every accepted utterance --
  * start/end rounded to 0.01 s and score to 1e-4 like the `str(task)` round trip (:219-230), the

@@ -46,6 +46,7 @@ _SIGNATURES = {
                                c_void, c_void, c_void, c_void, c_void, c_void]),
     "ipfa_anchor_select_device": (c_i, [c_void, c_void, c_void, c_void, c_i, c_i, c_d, c_i,
                                         c_void, c_void, c_void]),
+    "ipfa_text_round_device": (c_i, [c_void, c_i64, c_i, c_void, c_void]),
     "ipfa_ctcseg_windows_device": (c_i, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void,
                                          c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_i,
                                          c_void, c_void, c_void, c_void, c_void, c_void,

@@ -126,6 +126,7 @@ def get_file_iterative_segmentation(asr_model, aligner, audio_path, file_df, vad
     text_to_audio_proportion = 0.0
     next_row_is_non_speech = False
     following_row = None
+    audio_normalized, audio_length, sr = None, 0, info.sample_rate
 
     for row_index in range(n_rows):
         row = file_df.iloc[row_index]
@@ -169,10 +170,17 @@ def get_file_iterative_segmentation(asr_model, aligner, audio_path, file_df, vad
             clip_end = float(row['End'])
             clip_length = clip_end - clip_start
 
-        audio, sr = hg.audio_load(audio_path, frame_offset=int(clip_start * info.sample_rate),
-                                  num_frames=int(clip_length * info.sample_rate), channels_first=False)
-        audio_normalized = asr_model.audio_normalizer(audio, sr)
-        audio_length = audio.shape[0]
+        try:  # :147-159
+            audio, sr = hg.audio_load(audio_path, frame_offset=int(clip_start * info.sample_rate),
+                                      num_frames=int(clip_length * info.sample_rate), channels_first=False)
+            audio_normalized = asr_model.audio_normalizer(audio, sr)
+            audio_length = audio.shape[0]
+        except RuntimeError:
+            # A clip that ends before it starts (Non-Speech rows land one row early when a file has
+            # several VAD gaps, alignment_utils.py:160-169) makes torchaudio.load refuse its num_frames;
+            # the reference prints and goes on with the audio of the previous clip of the file.
+            if audio_normalized is None:
+                raise NameError("name 'audio_normalized' is not defined")  # what the reference dies of
 
         if audio_length > 0:
             text_to_audio_proportion = hg.get_text_to_audio_proportion(audio_length, text_length, sr)

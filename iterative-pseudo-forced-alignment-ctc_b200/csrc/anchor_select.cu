@@ -38,9 +38,28 @@ __global__ void anchor_select_kernel(const double *__restrict__ seg, const int32
     decision_out[w * 4 + 3] = d.anchor_u;
     anchor_out[w] = d.anchor;
 }
+
+__global__ void text_round_kernel(const double *__restrict__ x, int64_t n, double scale, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = round_decimals(x[i], scale);
+}
 }  // namespace ipfa
 
 using namespace ipfa;
+
+extern "C" int ipfa_text_round_device(const double *x, int64_t n, int decimals, double *out, void *stream) {
+    if (n == 0) return IPFA_OK;
+    if (!x || !out || n < 0 || decimals < 0 || decimals > 9) return IPFA_ERR_INVALID_ARG;
+    double scale = 1.0;
+    for (int i = 0; i < decimals; ++i) scale *= 10.0;
+    const int threads = 256;
+    text_round_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, n, scale, out);
+    ++g_launch_count;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
 
 extern "C" int ipfa_anchor_select_device(const double *seg, const int32_t *n_utts, const int32_t *text_len,
                                          const int32_t *is_last, int N, int Kmax, double threshold,

@@ -6,9 +6,22 @@
 
 namespace ipfa {
 
+// float(f"{x:.Nf}") with scale = 10^N -- the text round trip of `str(task)` (:218-230).  printf rounds
+// the EXACT binary value (ties to even), so the product x * scale may not be rounded before the
+// nearest integer is taken: p + e is the exact product (e from the fused multiply-add), the integer is
+// chosen from p's fraction and, when that is exactly one half, from the sign of e.  The quotient of two
+// exactly representable numbers, correctly rounded, is the double strtod returns for the digits.
 __device__ __forceinline__ double round_decimals(double x, double scale) {
-    if (!(fabs(x) < 1.0e15)) return x;
-    return __ddiv_rn(rint(__dmul_rn(x, scale)), scale);
+    if (!(fabs(x) < 1.0e11)) return x;
+    const double p = __dmul_rn(x, scale);
+    const double e = __fma_rn(x, scale, -p);
+    const double f = floor(p);
+    const double h = __dsub_rn(__dsub_rn(p, f), 0.5);
+    double r;
+    if (h > 0.0 || (h == 0.0 && e > 0.0)) r = f + 1.0;
+    else if (h < 0.0 || e < 0.0) r = f;
+    else r = (fmod(f, 2.0) == 0.0) ? f : f + 1.0;
+    return copysign(fabs(__ddiv_rn(r, scale)), x);  // "-0.0000" stays -0.0
 }
 
 struct AnchorDecision {

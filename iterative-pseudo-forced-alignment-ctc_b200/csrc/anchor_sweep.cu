@@ -128,6 +128,7 @@ __device__ __forceinline__ void build_window(const ipfa_sweep_corpus &c, const i
             u0 = s.utt[f];
             double anchor = s.anchor[f], prop = s.prop[f], follow_start = s.follow_start[f];
             int next_ns = s.next_ns[f], exc = s.exc[f];
+            long long clip_off = s.clip[2 * f], clip_len = s.clip[2 * f + 1];
             const int recalc_row = s.recalc_row[f];
             const int sr = p.sample_rate;
             while (true) {
@@ -166,10 +167,21 @@ __device__ __forceinline__ void build_window(const ipfa_sweep_corpus &c, const i
                     break;
                 }
                 // :149-160 torchaudio.load(frame_offset=int(clip_start*sr), num_frames=int(clip_length*sr))
-                const long long offset = (long long)__dmul_rn(clip_start, (double)sr);
+                // torchaudio 0.11 accepts num_frames == -1 (the rest of the file) or > 0 and refuses anything
+                // else; the reference then keeps the audio of the file's previous clip (:157-159)
+                long long offset = (long long)__dmul_rn(clip_start, (double)sr);
                 long long audio_length = (long long)__dmul_rn(clip_length, (double)sr);
-                if (audio_length > c.file_samples[f] - offset) audio_length = c.file_samples[f] - offset;
-                if (audio_length < 0) audio_length = 0;
+                if (offset >= 0 && (audio_length > 0 || audio_length == -1)) {
+                    if (offset > c.file_samples[f]) offset = c.file_samples[f];
+                    if (audio_length == -1 || audio_length > c.file_samples[f] - offset)
+                        audio_length = c.file_samples[f] - offset;
+                    clip_off = offset;
+                    clip_len = audio_length;
+                } else {
+                    if (clip_off < 0) { status = IPFA_SWEEP_NO_AUDIO; break; }
+                    offset = clip_off;
+                    audio_length = clip_len;
+                }
                 if (audio_length > 0) prop = text_to_audio(text_length, sr, audio_length);  // :163
                 if (!is_last) {  // :167-192
                     if (audio_length <= 0) { ++r; continue; }                        // :170-173
@@ -215,6 +227,8 @@ __device__ __forceinline__ void build_window(const ipfa_sweep_corpus &c, const i
             s.follow_start[f] = follow_start;
             s.next_ns[f] = next_ns;
             s.exc[f] = exc;
+            s.clip[2 * f] = clip_off;
+            s.clip[2 * f + 1] = clip_len;
             s.status[f] = status;
         }
         sh_active = active; sh_u0 = u0; sh_K = K; sh_ncols = n_cols;
@@ -318,7 +332,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
         !c.file_frames || !c.file_samples || !c.row_first || !c.row_type || !c.row_start || !c.row_end ||
         !c.row_utt_end || !c.utt_first || !c.utt_col || !c.utt_chars || !c.file_tok0 || !c.tokens ||
         !s.row || !s.utt || !s.anchor || !s.prop || !s.next_ns || !s.follow_start || !s.exc || !s.status ||
-        !s.need || !s.recalc_row || !s.n_windows || !s.cells || !s.frames || params->sample_rate <= 0 ||
+        !s.need || !s.recalc_row || !s.n_windows || !s.cells || !s.frames || !s.clip || params->sample_rate <= 0 ||
         params->frame_shift <= 0 || !(params->samples_to_frames_ratio > 0.0) || !(params->index_duration > 0.0) || params->score_len <= 0)
         return IPFA_ERR_INVALID_ARG;
     if (Tmax > 8000) return IPFA_ERR_UNSUPPORTED;  // windowed table mode

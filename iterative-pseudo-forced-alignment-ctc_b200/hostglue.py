@@ -214,12 +214,20 @@ def audio_info(path):
 
 
 def audio_load(path, frame_offset=0, num_frames=-1, channels_first=False):
-    """Stand-in for torchaudio.load(..., frame_offset, num_frames, channels_first=False): float32 in [-1, 1)."""
+    """Stand-in for torchaudio.load(..., frame_offset, num_frames, channels_first=False) of the
+    reference's torchaudio==0.11.0 (sox_io backend): float32 in [-1, 1).  Like that backend it raises
+    ``RuntimeError`` for ``frame_offset < 0`` and for ``num_frames`` other than -1 or a positive count;
+    the anchor loop depends on that (see ``anchor.get_file_iterative_segmentation``)."""
+    if frame_offset < 0:
+        raise RuntimeError("Invalid argument: frame_offset must be non-negative.")
+    if num_frames is None:
+        num_frames = -1
+    if not (num_frames == -1 or num_frames > 0):
+        raise RuntimeError("Invalid argument: num_frames must be -1 or greater than 0.")
     with wave.open(path, 'rb') as w:
         sr, ch, width, total = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-        frame_offset = max(0, min(int(frame_offset), total))
-        n = total - frame_offset if num_frames is None or num_frames < 0 else max(0, min(int(num_frames),
-                                                                                       total - frame_offset))
+        frame_offset = min(int(frame_offset), total)
+        n = total - frame_offset if num_frames == -1 else min(int(num_frames), total - frame_offset)
         w.setpos(frame_offset)
         raw = w.readframes(n)
     if width == 2:

@@ -338,3 +338,14 @@ def anchor_select(seg, n_utts, text_len, is_last, threshold=-2.0, short_len=30):
                                              _ptr(anchor), _stream(dev))
     check(rc, "ipfa_anchor_select_device")
     return decision, anchor
+
+
+def text_round(x, decimals):
+    """``float(f"{v:.{decimals}f}")`` of every element of a CUDA float64 tensor (see ipfa_b200.h)."""
+    _need_cuda(x, "x")
+    x = x.contiguous().double()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib().ipfa_text_round_device(_ptr(x), x.numel(), int(decimals), _ptr(out), _stream(x.device))
+    check(rc, "ipfa_text_round_device")
+    return out

@@ -18,7 +18,7 @@ import torch
 from . import hostglue as hg
 from ._lib import check, lib
 
-ACTIVE, DONE, STOP_WINDOW, STOP_EXCEPTIONS, NEEDS_RECALC, CAPACITY = range(6)
+ACTIVE, DONE, STOP_WINDOW, STOP_EXCEPTIONS, NEEDS_RECALC, CAPACITY, NO_AUDIO = range(7)
 STATUS_NAMES = ["active", "done", "window_to_stop", "exceptions_limit", "needs_recalc", "capacity"]
 
 _vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
@@ -34,7 +34,7 @@ class _Corpus(ctypes.Structure):
 
 class _State(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("row", "utt", "anchor", "prop", "next_ns", "follow_start", "exc", "status",
-                                   "need", "recalc_row", "n_windows", "cells", "frames")]
+                                   "need", "recalc_row", "n_windows", "cells", "frames", "clip")]
 
 
 class _Params(ctypes.Structure):
@@ -214,11 +214,12 @@ class AnchorSweep:
             self.state = dict(row=i32(n), utt=i32(n), anchor=f64(), prop=f64(), next_ns=i32(n), follow_start=f64(),
                               exc=i32(n), status=i32(n), need=i32(n, 3), recalc_row=i32(n), n_windows=i32(n),
                               cells=torch.zeros(n, dtype=torch.int64, device=dev),
-                              frames=torch.zeros(n, dtype=torch.int64, device=dev))
+                              frames=torch.zeros(n, dtype=torch.int64, device=dev),
+                              clip=torch.zeros((n, 2), dtype=torch.int64, device=dev))
             self.out_seg = torch.zeros((self.corpus.n_slots, 4), dtype=torch.float64, device=dev)
             self.out_info = torch.zeros((self.corpus.n_slots, 2), dtype=torch.int32, device=dev)
         for k, t in self.state.items():
-            t.fill_(nan if k in ("anchor", "follow_start") else (-1 if k == "recalc_row" else 0))
+            t.fill_(nan if k in ("anchor", "follow_start") else (-1 if k in ("recalc_row", "clip") else 0))
         self.out_seg.zero_()
         self.out_info.fill_(-1)
         self.steps = 0

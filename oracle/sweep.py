@@ -56,6 +56,7 @@ def sweep_file(file_id, audio_path, lpz, n_samples, rows, tokenizer, index_durat
     text_to_audio_proportion = 0.0
     next_row_is_non_speech = False
     following_row = None
+    last_clip = None
     n_rows = len(rows)
     status = "done"
     stats = {"windows": 0, "alignments": 0, "cells": 0, "frames": 0}
@@ -96,9 +97,17 @@ def sweep_file(file_id, audio_path, lpz, n_samples, rows, tokenizer, index_durat
             clip_end = float(row["End"])
             clip_length = clip_end - clip_start
 
-        # :149-160 torchaudio.load(frame_offset, num_frames) clamps to the file
-        offset = max(0, min(int(clip_start * sample_rate), n_samples))
-        audio_length = max(0, min(int(clip_length * sample_rate), n_samples - offset))
+        # :149-160 torchaudio.load(frame_offset, num_frames) of torchaudio==0.11 clamps to the file and
+        # refuses num_frames other than -1 or > 0; the reference then keeps the previous clip (:157-159)
+        offset, num_frames = int(clip_start * sample_rate), int(clip_length * sample_rate)
+        if offset >= 0 and (num_frames > 0 or num_frames == -1):
+            offset = min(offset, n_samples)
+            audio_length = n_samples - offset if num_frames == -1 else min(num_frames, n_samples - offset)
+            last_clip = (offset, audio_length)
+        elif last_clip is None:
+            raise NameError("name 'audio_length' is not defined")  # :162 of the reference
+        else:
+            offset, audio_length = last_clip
         if audio_length > 0:
             text_to_audio_proportion = _text_to_audio(audio_length, text_length, sample_rate)
         if not is_last_segment:  # :167-192

@@ -55,11 +55,12 @@ def run_reference(root, aligner_cls=None, device="cpu"):
                 args = argparse.Namespace(tsv=case.tsv_rel, vad_segments_tsv=case.vad_rel, dst="results",
                                           logs_path="logs", asr_hub="synthetic", asr_savedir="unused", **case.loop)
                 ns.iua.main(args)
+                refused = ns.stdout.getvalue().count("Start frame:")  # the print of :158
             ref_shim.close_logger(name)
             log = open(os.path.join("logs", name + ".log")).read()
             n_rows = sum(1 for _ in open(os.path.join("results", name + ".tsv"))) - 1
             manifest["anchor"][name] = {"emissions_sha256": asr.digest(), "loop": case.loop, "rows": n_rows,
-                                        "branches": ref_cases.count_marks(log)}
+                                        "branches": dict(ref_cases.count_marks(log), load_refused=refused)}
         import pandas as pd
         pd.concat(all_df, ignore_index=True).to_csv("tsv/all.tsv", sep="\t", index=None)
         # post-steps, the reference's own scripts as __main__

@@ -9,8 +9,8 @@ One definition of every case serves three users:
 * the ``-m gpu`` tests -- run the product's entry points (CUDA path) on the same cases and compare
   the files byte for byte with the fixtures (the GPU box has no reference tree).
 
-Everything a case needs is rebuilt from a seed: the WAV (a ramp, so the emitter can tell where a
-clip starts), the TSVs, and the acoustic-model double whose emissions are quantised to a
+Everything a case needs is rebuilt from a seed: the WAV (samples that spell their own position, so the
+emitter can tell where a clip starts), the TSVs, and the acoustic-model double whose emissions are quantised to a
 2^-10 grid so they are bit-identical on every machine.
 """
 import hashlib
@@ -31,14 +31,30 @@ STRIDE = 320
 SR = 16000
 
 
-def write_wav(path, samples):
-    pcm = np.clip(np.asarray(samples, dtype=np.float64), -1.0, 1.0 - 1.0 / 32768)
-    pcm = (pcm * 32768.0).astype("<i2")
+def position_pcm(total):
+    """16-bit samples from which ANY clip can tell its absolute start: sample pair q = p // 2 holds the
+    low 15 bits of q at the even position (>= 0) and -(q >> 15) - 1 at the odd one (< 0)."""
+    q = np.arange((total + 1) // 2, dtype=np.int64)
+    pcm = np.empty(2 * q.size, np.int64)
+    pcm[0::2] = q & 0x7fff
+    pcm[1::2] = -(q >> 15) - 1
+    return pcm[:total].astype("<i2")
+
+
+def clip_position(x0, x1):
+    """Absolute sample index of a clip from its first two samples (floats, int16 / 32768)."""
+    a, b = int(round(float(x0) * 32768.0)), int(round(float(x1) * 32768.0))
+    if a >= 0:
+        return 2 * (a + ((-b - 1) << 15))
+    return 2 * (((-a - 1) << 15) + ((b - 1) & 0x7fff)) + 1
+
+
+def write_wav(path, pcm):
     with wave.open(path, "wb") as w:
         w.setnchannels(1)
         w.setsampwidth(2)
         w.setframerate(SR)
-        w.writeframes(pcm.tobytes())
+        w.writeframes(np.asarray(pcm, dtype="<i2").tobytes())
 
 
 class GridASR:
@@ -48,7 +64,7 @@ class GridASR:
     The file's log-probabilities are fixed at construction: seeded logits peaked on a
     character schedule, normalised in fp64 and rounded to multiples of 2^-10, so the fp32 values
     do not depend on the machine's exp/log.  ``encode_batch`` returns the rows of the clip it is
-    handed (the audio is a ramp: sample value = position / total); ``log_softmax`` is the identity.
+    handed (the samples spell their own position, ``position_pcm``); ``log_softmax`` is the identity.
     """
 
     def __init__(self, frame_tokens, total_samples, device="cpu", peak=7.0, noise=1.0, seed=0, corrupt=()):
@@ -84,8 +100,7 @@ class GridASR:
         if n == 0:
             return torch.zeros(1, 0, self.lp.shape[1], device=self.device)
         # (estimate_samples_to_frames_ratio hands in noise: any rows do, only their count matters)
-        first = int(round(float(x[0].double()) * self.total))
-        f0 = first // STRIDE
+        f0 = max(0, clip_position(x[0], x[1])) // STRIDE
         idx = torch.arange(f0, f0 + n, device=self.device).clamp(max=self.lp.shape[0] - 1)
         return self.lp[idx].unsqueeze(0)
 
@@ -158,7 +173,7 @@ class AnchorCase:
         """Write the WAV and the TSVs under ``root`` (paths inside the TSVs stay relative to it)."""
         os.makedirs(os.path.join(root, "audio"), exist_ok=True)
         os.makedirs(os.path.join(root, "tsv"), exist_ok=True)
-        write_wav(os.path.join(root, self.wav_rel), np.arange(self.total, dtype=np.float64) / self.total)
+        write_wav(os.path.join(root, self.wav_rel), position_pcm(self.total))
         self.tsv_rel = f"tsv/{self.name}.tsv"
         self.vad_rel = f"tsv/{self.name}_vad_segments_filtered.tsv"
         self.df.to_csv(os.path.join(root, self.tsv_rel), sep="\t", index=None)
@@ -216,6 +231,7 @@ LOG_MARKS = {
     "shorter_than_text": "is shorter than text",
     "exception_limit": "Number of reached the limit",
 }
+# plus "load_refused": clips torchaudio.load refused (counted from the print at :158, not a log line)
 
 
 def count_marks(log_text):

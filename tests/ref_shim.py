@@ -51,12 +51,21 @@ def _ta_info(path):
 
 
 def _ta_load(path, frame_offset=0, num_frames=-1, normalize=True, channels_first=True, format=None):
-    """torchaudio.load for 16-bit PCM WAV: float32 in [-1, 1), [channels, time] unless channels_first=False."""
+    """torchaudio.load of torchaudio==0.11.0 (/root/reference/requirements.txt:94, sox_io backend) for
+    16-bit PCM WAV: float32 in [-1, 1), [channels, time] unless channels_first=False.  Like that
+    backend it REJECTS ``frame_offset < 0`` and ``num_frames`` other than -1 or a positive count
+    ("Invalid argument: num_frames must be -1 or greater than 0.") -- the reference reaches that with
+    a clip whose end lies before its start and then carries on with the previous clip's audio
+    (iterative_utterance_alignment.py:147-159, bare ``except``)."""
+    if frame_offset < 0:
+        raise RuntimeError("Invalid argument: frame_offset must be non-negative.")
+    if not (num_frames == -1 or num_frames > 0):
+        raise RuntimeError("Invalid argument: num_frames must be -1 or greater than 0.")
     with wave.open(path, "rb") as w:
         sr, ch, width, total = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
         assert width == 2, "shimmed torchaudio.load reads 16-bit PCM only"
-        frame_offset = max(0, min(int(frame_offset), total))
-        n = total - frame_offset if num_frames < 0 else max(0, min(int(num_frames), total - frame_offset))
+        frame_offset = min(int(frame_offset), total)
+        n = total - frame_offset if num_frames == -1 else min(int(num_frames), total - frame_offset)
         w.setpos(frame_offset)
         raw = w.readframes(n)
     data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0

@@ -178,3 +178,21 @@ def test_seg_wide_lattice_and_long_window(ipfa):
     with pytest.raises(RuntimeError, match="wider than the widest|unsupported|status 2"):
         big = torch.zeros(1, 8001, 4, device="cuda").log_softmax(-1)
         ipfa.ctcseg_align(big, [8001], [[-1, 0, 1, 0]], [4], [[1, 3]], [1], 0.02)
+
+
+def test_text_round_equals_the_format_round_trip(ipfa):
+    """Device rounding of times (.2f) and scores (.4f) == Python's float(f"{x:.Nf}") -- including the
+    values where x * 10^N rounds to an exact half although x itself lies beside it (means of grid-valued
+    emissions hit these: -1.08125 is not a binary fraction)."""
+    import torch
+    rng = np.random.default_rng(0)
+    ks = rng.integers(-400000, 400000, 20000)
+    halves = np.concatenate([(2 * ks + 1) / 20000.0, (2 * ks[:5000] + 1) / 200.0])
+    vals = np.concatenate([halves, np.nextafter(halves, np.inf), np.nextafter(halves, -np.inf),
+                           rng.standard_normal(20000) * 3, -rng.random(2000) * 1e-4, ks[:2000] / 30720.0,
+                           [0.0, -0.0, -0.00004, 0.00005, -1.08125, 1e10, -1e10, -1e-300]])
+    x = torch.as_tensor(vals, dtype=torch.float64, device="cuda")
+    for decimals in (2, 4):
+        got = ipfa.ops.text_round(x, decimals).cpu().numpy()
+        want = np.array([float(f"{v:.{decimals}f}") for v in vals])
+        assert np.array_equal(got, want) and np.array_equal(np.signbit(got), np.signbit(want))
