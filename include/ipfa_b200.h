@@ -155,6 +155,13 @@ int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
 #define IPFA_SEG_PREAMBLE_COST_ZERO 2
 #define IPFA_SEG_ROUND_NEAREST 4
 #define IPFA_SEG_ALL_PREFIXES 8
+/* Windowed table mode only (T > window).  ctc-segmentation's source is not available to this build, so
+ * the two spots of its sliding-window bookkeeping that could not be re-checked each have a switch;
+ * clear = the package as recalled, set = the other reading:
+ *   the largest per-column window step is int(mean_offset) + 1  /  ceil(mean_offset);
+ *   cur_offset[s+1] = cur_offset[s] + offset runs in ascending order  /  as a shift (multi-column gt). */
+#define IPFA_SEG_WINDOW_STEP_CEIL 16
+#define IPFA_SEG_OFFSET_SHIFT 32
 
 size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int V);
 int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t stride_t,

@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
     __shared__ int s_ri[kWinThreads / 32];
 
     const float mean_offset = (float)(T - W) / (float)NC;
-    const int higher_offset = (int)ceilf(mean_offset);
+    const int higher_offset = (prm.flags & IPFA_SEG_WINDOW_STEP_CEIL) ? (int)ceilf(mean_offset) : (int)mean_offset + 1;
     if (tid == 0) { s_off = 0; s_offsum = 0; s_arg = -1; s_max = 0.0f; }
     __syncthreads();
 
@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_multi_fill_kernel(const Se
     __shared__ float s_max, s_carry;
 
     const float mean_offset = (float)(T - W) / (float)NC;
-    const int higher_offset = (int)ceilf(mean_offset);
+    const int higher_offset = (prm.flags & IPFA_SEG_WINDOW_STEP_CEIL) ? (int)ceilf(mean_offset) : (int)mean_offset + 1;
     if (tid == 0) {
         s_off = 0; s_offsum = 0; s_arg = -1; s_max = 0.0f;
         for (int s = 0; s < G; ++s) s_curoff[s] = -1;  // np.zeros(G) - 1
@@ -979,7 +979,11 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_multi_fill_kernel(const Se
                 const int hi = min(higher_offset, lim);
                 const int lo = max(s_arg - W / 2, 0);
                 const int offset = min(lo, hi);
-                for (int s = G - 2; s >= 0; --s) s_curoff[s + 1] = s_curoff[s] + offset;
+                if (prm.flags & IPFA_SEG_OFFSET_SHIFT) {
+                    for (int s = G - 2; s >= 0; --s) s_curoff[s + 1] = s_curoff[s] + offset;
+                } else {  // ascending: every entry builds on the one just written
+                    for (int s = 0; s < G - 1; ++s) s_curoff[s + 1] = s_curoff[s] + offset;
+                }
                 s_curoff[0] = offset;
                 s_off = offset;
                 s_offsum += offset;

@@ -47,6 +47,10 @@ class CtcSegmentationParameters:
     char_list = None
     # scoring-window index rounding: "floor" or "round" (see oracle/ctcseg.py SEG_INDEX_ROUNDING)
     seg_index_rounding = "floor"
+    # windowed table mode (T > min_window_size), the two spots of the package that could not be
+    # re-checked here: largest window step "int+1" | "ceil"; cur_offset carry "ascending" | "shift"
+    window_step_rule = "int+1"
+    offset_cascade = "ascending"
 
     def __init__(self, **kwargs):
         self.set(**kwargs)
@@ -64,6 +68,10 @@ class CtcSegmentationParameters:
         f = int(self.blank_transition_cost_zero) + 2 * int(self.preamble_transition_cost_zero)
         if self.seg_index_rounding == "round":
             f |= ops.SEG_ROUND_NEAREST
+        if self.window_step_rule == "ceil":
+            f |= ops.SEG_WINDOW_STEP_CEIL
+        if self.offset_cascade == "shift":
+            f |= ops.SEG_OFFSET_SHIFT
         return f
 
     def __str__(self):

@@ -26,6 +26,8 @@ SEG_BLANK_COST_ZERO = 1
 SEG_PREAMBLE_COST_ZERO = 2
 SEG_ROUND_NEAREST = 4
 SEG_ALL_PREFIXES = 8
+SEG_WINDOW_STEP_CEIL = 16
+SEG_OFFSET_SHIFT = 32
 WIN_WINDOW_TOO_SMALL = 8
 
 

@@ -41,6 +41,9 @@ class CtcSegmentationParameters:
     excluded_characters = ".,»«•❍·"
     tokenized_meta_symbol = "▁"
     char_list = None
+    # the two [verify] spots of the windowed table mode (T > min_window_size), one switch each:
+    window_step_rule = "int+1"       # or "ceil": largest per-column window step
+    offset_cascade = "ascending"     # or "shift": how cur_offset[s] is carried to the next column
 
     def __init__(self, **kwargs):
         self.set(**kwargs)
@@ -55,7 +58,8 @@ class CtcSegmentationParameters:
 
     @property
     def flags(self):
-        return int(self.blank_transition_cost_zero) + 2 * int(self.preamble_transition_cost_zero)
+        return (int(self.blank_transition_cost_zero) + 2 * int(self.preamble_transition_cost_zero)
+                + 16 * int(self.window_step_rule == "ceil") + 32 * int(self.offset_cascade == "shift"))
 
 
 def prepare_token_list(config, text):

@@ -46,7 +46,10 @@ static inline float fmax2(float a, float b) { return a > b ? a : b; }
  * lpz:   [T, V] row-major (row stride V)
  * gt:    [N, G] int64 row-major (-1 = no token)
  * offsets: [N] out
- * flags: bit0 blank_transition_cost_zero, bit1 preamble_transition_cost_zero
+ * flags: bit0 blank_transition_cost_zero, bit1 preamble_transition_cost_zero,
+ *        bit4 (16) the largest window step is ceil(mean_offset) instead of int(mean_offset) + 1,
+ *        bit5 (32) the per-candidate offsets are SHIFTED instead of cascaded in ascending order
+ *        (the two [verify] spots of the windowed mode; defaults = the package as recalled)
  * argmax_out (nullable): [N] first-argmax row of every column
  * returns t (argmax row of the last column); c is N-1.
  */
@@ -62,7 +65,8 @@ int oracle_ctcseg_fill(float *table, int W, int N, const float *lpz, int T, int 
     for (int s = 0; s < G; ++s) cur_offset[s] = -1; /* np.zeros(G) - 1 */ /* [verify] */
     /* mean offset between two window positions */
     const float mean_offset = (float)(T - W) / (float)N;
-    const int higher_offset = (int)ceilf(mean_offset);
+    /* lower_offset = int(mean_offset); higher_offset = lower_offset + 1   [verify] (flag 16: ceil) */
+    const int higher_offset = (flags & 16) ? (int)ceilf(mean_offset) : (int)mean_offset + 1;
 
     table[0] = 0.0f;
     for (int c = 0; c < N; ++c) {
@@ -72,7 +76,14 @@ int oracle_ctcseg_fill(float *table, int W, int N, const float *lpz, int T, int 
             int lo = last_argmax - W / 2;
             if (lo < 0) lo = 0;
             offset = lo < hi ? lo : hi;
-            for (int s = G - 2; s >= 0; --s) cur_offset[s + 1] = cur_offset[s] + offset;
+            /* for s in range(G - 1): cur_offset[s + 1] = cur_offset[s] + offset   [verify] -- in
+             * ascending order every entry builds on the one just written; flag 32 shifts instead
+             * (entry s = the window movement over the last s+1 columns). */
+            if (flags & 32) {
+                for (int s = G - 2; s >= 0; --s) cur_offset[s + 1] = cur_offset[s] + offset;
+            } else {
+                for (int s = 0; s < G - 1; ++s) cur_offset[s + 1] = cur_offset[s] + offset;
+            }
             cur_offset[0] = offset;
             offset_sum += offset;
         }

@@ -250,9 +250,10 @@ def test_windowed_mode_equals_full_table_when_the_audio_fits(ipfa):
             assert int(full.term_t[i, k - 1]) == int(win.term_t[i, k - 1])
 
 
+@pytest.mark.parametrize("step_rule", ["int+1", "ceil"])
 @pytest.mark.parametrize("t,window,k_utts,lo,hi", [(700, 256, 3, 10, 20), (1000, 300, 5, 8, 16),
                                                    (2300, 2100, 4, 20, 40)])
-def test_windowed_mode_vs_oracle(ipfa, t, window, k_utts, lo, hi):
+def test_windowed_mode_vs_oracle(ipfa, t, window, k_utts, lo, hi, step_rule):
     """T > window: per-column sliding offsets, one fill per prefix; the oracle doubles its window on
     IndexError exactly where the CUDA path reports WIN_WINDOW_TOO_SMALL."""
     import torch
@@ -270,12 +271,14 @@ def test_windowed_mode_vs_oracle(ipfa, t, window, k_utts, lo, hi):
             while True:
                 res = ipfa.ctcseg_align(dev[i:i + 1], in_len[i:i + 1], gt[i:i + 1, :ubs[i, k] + 1],
                                         np.array([ubs[i, k] + 1], np.int32), ubs[i:i + 1, :k + 1],
-                                        np.array([k], np.int32), 0.02, flags=2, window=w)
+                                        np.array([k], np.int32), 0.02, window=w,
+                                        flags=2 | (16 if step_rule == "ceil" else 0))
                 if not int(res.status[0]) & 8:
                     break
                 w *= 2
                 assert w < 100000
-            cfg = oseg.CtcSegmentationParameters(index_duration=0.02, min_window_size=window)
+            cfg = oseg.CtcSegmentationParameters(index_duration=0.02, min_window_size=window,
+                                                 window_step_rule=step_rule)
             _compare_window(cfg, res, 0, k, lp[i, :in_len[i]], utts[i], to_np)
             checked += 1
             # the offsets really moved
@@ -284,6 +287,52 @@ def test_windowed_mode_vs_oracle(ipfa, t, window, k_utts, lo, hi):
             if w < in_len[i] and k == int(n_utts[i]):
                 assert offsets[-1] > 0  # the full text spans the audio: the window had to slide
     assert checked >= n
+
+
+def _integral_step_case(seed, window, step):
+    """A window whose mean offset (T - W) / N is the integer ``step``: the one situation in which
+    the two readings of the largest window step (int(mean) + 1, ceil(mean)) differ."""
+    rng = np.random.default_rng(seed)
+    utts = [rng.integers(1, 32, int(rng.integers(12, 24))).astype(np.int64) for _ in range(4)]
+    flat = []
+    for u in utts:
+        flat += [0] + u.tolist()
+    flat += [0]
+    n_cols = len(flat) + 1
+    t = window + step * n_cols
+    lp = rng.standard_normal((t, 32)).astype(np.float32)
+    pos = np.sort(rng.permutation(t)[:len(flat)])
+    for j, (a, b) in enumerate(zip(pos, list(pos[1:]) + [t])):
+        lp[a:b, flat[j]] += 4.0
+    lp = lp - np.log(np.exp(lp.astype(np.float64)).sum(-1, keepdims=True)).astype(np.float32)
+    return lp, utts, n_cols
+
+
+@pytest.mark.parametrize("step_rule", ["int+1", "ceil"])
+def test_windowed_mode_integral_mean_offset(ipfa, step_rule):
+    import torch
+    from oracle import ctcseg as oseg
+    window = 256
+    lp, utts, n_cols = _integral_step_case(63, window, 3)
+    cfg = oseg.CtcSegmentationParameters(index_duration=0.02, min_window_size=window, window_step_rule=step_rule)
+    gt, ub = oseg.prepare_token_list(cfg, utts)
+    assert len(gt) == n_cols and (lp.shape[0] - window) % n_cols == 0
+    k = len(utts)
+    w = window
+    while True:
+        res = ipfa.ctcseg_align(torch.from_numpy(lp).cuda()[None], [lp.shape[0]], gt[:, 0].astype(np.int32)[None],
+                                [n_cols], np.asarray(ub, np.int32)[None], [k], 0.02, window=w,
+                                flags=cfg.flags)
+        if not int(res.status[0]) & 8:
+            break
+        w *= 2
+    _compare_window(cfg, res, 0, k, lp, utts, lambda x: x.cpu().numpy())
+    # and the two rules are not the same algorithm on this input
+    other = oseg.CtcSegmentationParameters(min_window_size=window,
+                                           window_step_rule="ceil" if step_rule == "int+1" else "int+1")
+    off_a = oseg.fill_table(cfg, lp, gt, window)[1]
+    off_b = oseg.fill_table(other, lp, gt, window)[1]
+    assert not np.array_equal(off_a, off_b)
 
 
 def test_long_audio_through_the_ctcsegmentation_mirror(cs):
@@ -346,19 +395,22 @@ def _classic_case(seed, t_len, n_utts, v=None):
     return cfg, utts, gt, ub, lp
 
 
+@pytest.mark.parametrize("cascade", ["ascending", "shift"])
 @pytest.mark.parametrize("t_len,window", [(300, None), (500, 160)])
-def test_multi_column_ground_truth_vs_oracle(ipfa, t_len, window):
+def test_multi_column_ground_truth_vs_oracle(ipfa, t_len, window, cascade):
     """ctc-segmentation's `classic` converter: up to G switch transitions per cell,
     full table (window = T) and sliding window."""
     import torch
     from oracle import ctcseg as oseg
     cfg, utts, gt, ub, lp = _classic_case(71, t_len, 4)
+    cfg.offset_cascade = cascade
     assert gt.shape[1] >= 3 and (gt[:, 1:3] >= 0).any() and (gt[:, 3:] < 0).all()
     n_cols, k = len(gt), len(ub) - 1
     w = window
     while True:
         res = ipfa.ctcseg_align(torch.from_numpy(lp).cuda()[None], [t_len], gt.astype(np.int32)[None],
-                                [n_cols], np.asarray(ub, np.int32)[None], [k], 0.02, flags=2, window=w)
+                                [n_cols], np.asarray(ub, np.int32)[None], [k], 0.02, window=w,
+                                flags=2 | (32 if cascade == "shift" else 0))
         if not int(res.status[0]) & 8:
             break
         w *= 2

@@ -156,3 +156,25 @@ def test_prepare_text_product_mirror_equals_oracle():
         assert ga.shape[1] == len("<blank>") and (ga[0] == -1).all()  # max_char_len counts '<blank>' too
         # a multi-character token sits in the column of its length - 1
         assert (ga[:, 2] >= 0).sum() >= 1
+
+
+def test_windowed_switches_change_only_what_they_name():
+    """The two [verify] switches of the windowed mode: the window-step rule matters only when
+    (T - W) / N is an integer, the cascade order only with a multi-column ground truth."""
+    rng = np.random.default_rng(9)
+    toks = [rng.integers(1, 5, 12), rng.integers(1, 5, 9)]
+    cfg = oseg.CtcSegmentationParameters(index_duration=0.02, min_window_size=64)
+    gt, ub = oseg.prepare_token_list(cfg, toks)
+    n = len(gt)
+    for t_len, differs in ((64 + 2 * n, True), (64 + 2 * n + 5, False)):
+        lpz = rng.standard_normal((t_len, 5)).astype(np.float32)
+        offs = {}
+        for rule in ("int+1", "ceil"):
+            c = oseg.CtcSegmentationParameters(min_window_size=64, window_step_rule=rule)
+            offs[rule] = oseg.fill_table(c, lpz, gt, 64)[1]
+            assert offs[rule][-1] <= t_len - 64 and np.all(np.diff(offs[rule]) >= 0)
+        assert (not np.array_equal(offs["int+1"], offs["ceil"])) == differs
+        # single-column ground truth: the cascade order cannot matter
+        a = oseg.fill_table(oseg.CtcSegmentationParameters(min_window_size=64, offset_cascade="shift"), lpz, gt, 64)
+        b = oseg.fill_table(oseg.CtcSegmentationParameters(min_window_size=64), lpz, gt, 64)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
