@@ -43,6 +43,9 @@ extern "C" {
 #define IPFA_ERR_WORKSPACE 3     /* workspace too small */
 #define IPFA_ERR_CUDA 4          /* CUDA runtime error (ipfa_last_cuda_error()) */
 #define IPFA_ERR_AUDIO_SHORTER_THAN_TEXT 5 /* ctcseg: N > T (reference raises AssertionError) */
+#define IPFA_ERR_WINDOW 6        /* ipfa_ctcseg_host: the backtrace left the table window even at
+                                    max_window_size (ctc-segmentation raises IndexError); the outputs
+                                    hold the last attempt, status_out carries IPFA_WIN_WINDOW_TOO_SMALL */
 
 /* per-window status bits written to the status_out arrays */
 #define IPFA_WIN_OK 0
@@ -58,6 +61,9 @@ const char *ipfa_last_cuda_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t ipfa_launch_count(void);
 int ipfa_device_count(void);
+/* The IPFA_* tuning switches (kernel-instance overrides used by tools/ and the tests) are read from
+ * the environment once per process, not inside compute calls; this reads them again. */
+void ipfa_tuning_reload(void);
 
 /* ------------------------------------------------------------------------- *
  * Kernel (1): batched CTC alpha recursion over the blank-interleaved 2L+1

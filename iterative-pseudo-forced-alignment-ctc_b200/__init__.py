@@ -9,7 +9,7 @@ the ``ipfa_b200`` alias module at the repository root.
 from . import _lib  # noqa: F401
 from .ops import (ctc_alpha_nll, ctc_alpha_nll_host, ctc_forced_align, ctc_forced_align_host,  # noqa: F401
                   ctcseg_align, ctcseg_align_host, anchor_select, launch_count, ctc_alpha_redo_count,
-                  ctc_alpha_redo_reasons)
+                  ctc_alpha_redo_reasons, text_round, tuning)
 
 __all__ = ["ctc_alpha_nll", "ctc_alpha_nll_host", "ctc_forced_align", "ctc_forced_align_host",
-           "ctcseg_align", "ctcseg_align_host", "anchor_select", "launch_count", "ctc_alpha_redo_count", "ctc_alpha_redo_reasons"]
+           "ctcseg_align", "ctcseg_align_host", "anchor_select", "launch_count", "ctc_alpha_redo_count", "ctc_alpha_redo_reasons", "text_round", "tuning"]

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "ipfa_last_cuda_error": (ctypes.c_char_p, []),
     "ipfa_launch_count": (ctypes.c_uint64, []),
     "ipfa_device_count": (c_i, []),
+    "ipfa_tuning_reload": (None, []),
     "ipfa_ctc_alpha_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "ipfa_ctc_alpha_device": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
                                     c_i, c_i, c_i, c_i, c_i, c_void, c_void, c_sz, c_void]),
@@ -69,6 +70,7 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(ipfa_[a-z0-9_]+)\s*\(", text)))
 
 
+ABI_VERSION = 200  # ipfa_version(): bumped whenever a signature or struct in include/ipfa_b200.h changes
 _lib = None
 
 
@@ -79,10 +81,18 @@ def lib():
         if not _build.up_to_date():
             try:
                 path = _build.build()
-            except Exception as exc:  # no nvcc on the box: use the shipped .so if there is one
+            except Exception as exc:
+                # no nvcc on the box.  A shipped .so older than its sources may have another ABI than the
+                # signatures below: loading it is an explicit decision, not a fallback.
                 if not os.path.exists(path):
                     raise ImportError(f"libipfa_b200.so is missing and could not be built: {exc}")
+                if os.environ.get("IPFA_ALLOW_STALE_LIB") != "1":
+                    raise ImportError(f"libipfa_b200.so is older than csrc/ or include/ and could not be rebuilt "
+                                      f"({exc}); set IPFA_ALLOW_STALE_LIB=1 to load it anyway")
         L = ctypes.CDLL(path)
+        L.ipfa_version.restype = ctypes.c_int
+        if L.ipfa_version() != ABI_VERSION:
+            raise ImportError(f"{path} reports ABI version {L.ipfa_version()}, this package binds {ABI_VERSION}")
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res
@@ -106,5 +116,8 @@ def check(status, where):
         # the reference's callers catch AssertionError for this condition
         # (/root/reference/src/iterative_utterance_alignment.py:390)
         raise AssertionError("Audio is shorter than text!")
+    if status == 6:
+        # ctc-segmentation gives up with IndexError when doubling the table window does not help
+        raise IndexError("Maximum window size reached. Check data for large repetitions or noise.")
     if status != 0:
         raise IpfaError(status, where)

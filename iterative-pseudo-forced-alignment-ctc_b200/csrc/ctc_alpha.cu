@@ -809,7 +809,7 @@ static void lin_shape(int units, long long chains, int *P, int *W) {
     *W = 1;
     *P = units <= 32 ? 1 : units <= 64 ? 2 : units <= 128 ? 4 : 8;
     (void)chains;
-    if (const char *e = getenv("IPFA_ALPHA_LIN_SHAPE")) {
+    if (const char *e = tuning("IPFA_ALPHA_LIN_SHAPE")) {
         int p = 0, w = 0;
         if (sscanf(e, "%d,%d", &p, &w) == 2 && (w == 1 || w == 2) && (p == 1 || p == 2 || p == 4 || p == 8) &&
             !(p == 8 && w == 2) && 32 * p * w >= units) { *P = p; *W = w; }
@@ -867,7 +867,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     // Dense panels whose lattice fits one warp: the linear-domain instance scores the windows and
     // lists the ones it cannot vouch for; the log-domain instance below then runs over that list.
-    const bool lin = dense && Lmax + 1 <= kLinMaxPairs && !getenv("IPFA_ALPHA_LOG");
+    const bool lin = dense && Lmax + 1 <= kLinMaxPairs && !tuning("IPFA_ALPHA_LOG");
     const size_t l1 = (size_t)Lmax + 1;
     int32_t *order = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(prm.join_vec) +
                                                  alpha_pad256((size_t)N * 4 * l1 * sizeof(float)));
@@ -879,7 +879,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
         prm.redo_count = prm.join_count + N;
         int P = 0, W = 0;
         lin_shape(Lmax + 1, (long long)halves * N, &P, &W);
-        if (N >= kBucketMinWindows && W == 1 && P >= 2 && !getenv("IPFA_NO_BUCKETS")) {
+        if (N >= kBucketMinWindows && W == 1 && P >= 2 && !tuning("IPFA_NO_BUCKETS")) {
             e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
             if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
             length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, 32 * P / 2, order, count);
@@ -904,7 +904,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     // device, see length_bucket_kernel)
     const int big_units = 32 * s.WARPS * s.PER, small_units = big_units / 2;
     LatticeShape s_small;
-    const bool bucketed = N >= kBucketMinWindows && small_units >= 32 && !getenv("IPFA_NO_BUCKETS") &&
+    const bool bucketed = N >= kBucketMinWindows && small_units >= 32 && !tuning("IPFA_NO_BUCKETS") &&
                           pick_lattice_shape(small_units, halves * N, &s_small, "IPFA_ALPHA_SMALL_SHAPE", 6) &&
                           32 * s_small.WARPS * s_small.PER == small_units;
     if (!bucketed) {

@@ -595,7 +595,7 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
     // two length buckets when the batch is large and a half-width instance exists
     const int big_units = 32 * s.WARPS * s.PER, small_units = big_units / 2;
     LatticeShape s_small;
-    const bool bucketed = N >= kBucketMinWindows && small_units >= 32 && !getenv("IPFA_NO_BUCKETS") &&
+    const bool bucketed = N >= kBucketMinWindows && small_units >= 32 && !tuning("IPFA_NO_BUCKETS") &&
                           pick_lattice_shape(small_units, N, &s_small, "IPFA_VITERBI_SMALL_SHAPE", dense ? 3 : 6) &&
                           32 * s_small.WARPS * s_small.PER == small_units;
     if (!bucketed) {

@@ -1258,7 +1258,7 @@ static bool try_seg_fill_cluster(const SegFillParams &prm, SegShape s, cudaStrea
     // fill of one 2200-frame, 700-column window (tools/exp_sweep_floor.py).  With a dozen warps per
     // window the frame time is already the dependent-chain latency of one warp (~100 cycles), not
     // the issue rate of the SM, so a second SM has nothing to take over and the exchange only adds.
-    if (!getenv("IPFA_SEG_CLUSTER")) return false;
+    if (!tuning("IPFA_SEG_CLUSTER")) return false;
     if (!fast || prm.V > 32 || s.PER != 2) return false;
     if ((long long)prm.N * s.WARPS >= 148LL * 4 * 3) return false;  // enough warps without splitting
     switch (s.WARPS) {

@@ -186,7 +186,7 @@ inline PipeGeometry pipe_geometry(int U_panel, size_t budget_bytes) {
     size_t per_frame = (size_t)kStages * g.pitch * sizeof(float);
     int tc = (int)(budget_bytes / per_frame);
     if (tc > 32) tc = 32;
-    if (const char *e = getenv("IPFA_PIPE_TC")) {  // tuning override: frames per chunk
+    if (const char *e = tuning("IPFA_PIPE_TC")) {  // tuning override: frames per chunk
         const int v = atoi(e);
         if (v >= 2 && v < tc) tc = v;
     }

@@ -3,6 +3,8 @@
 // stream with a grow-only device arena).  See include/ipfa_b200.h.
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "ipfa_common.cuh"
 
@@ -10,37 +12,86 @@ namespace ipfa {
 cudaError_t g_last_cuda_error = cudaSuccess;
 uint64_t g_launch_count = 0;
 
+// ---- tuning switches: the IPFA_* environment variables are read ONCE, when the first entry point
+// needs one (or again on ipfa_tuning_reload()); the compute calls look them up in this table.
+namespace {
+const char *const kTuningNames[] = {
+    "IPFA_ALPHA_SHAPE", "IPFA_ALPHA_SMALL_SHAPE", "IPFA_ALPHA_LIN_SHAPE", "IPFA_ALPHA_LOG", "IPFA_NO_BUCKETS",
+    "IPFA_VITERBI_SHAPE", "IPFA_VITERBI_SMALL_SHAPE", "IPFA_SEG_SHAPE", "IPFA_SEG_CLUSTER", "IPFA_PIPE_TC",
+    "IPFA_ALPHA_F32", "IPFA_SEG_SKEW"};
+constexpr int kTuningCount = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
+struct TuningTable {
+    bool present[kTuningCount];
+    char value[kTuningCount][32];
+    void load() {
+        for (int i = 0; i < kTuningCount; ++i) {
+            const char *e = getenv(kTuningNames[i]);
+            present[i] = e != nullptr;
+            value[i][0] = 0;
+            if (e) { strncpy(value[i], e, sizeof(value[i]) - 1); value[i][sizeof(value[i]) - 1] = 0; }
+        }
+    }
+};
+std::mutex g_tuning_mu;
+TuningTable g_tuning;
+bool g_tuning_loaded = false;
+}  // namespace
+
+const char *tuning(const char *name) {
+    std::lock_guard<std::mutex> lock(g_tuning_mu);
+    if (!g_tuning_loaded) { g_tuning.load(); g_tuning_loaded = true; }
+    for (int i = 0; i < kTuningCount; ++i)
+        if (strcmp(name, kTuningNames[i]) == 0) return g_tuning.present[i] ? g_tuning.value[i] : nullptr;
+    return nullptr;
+}
+
 namespace {
 constexpr int kMaxChunks = 32;
+constexpr int kMaxDevices = 64;
 
+// One arena per CUDA device: a grow-only device buffer, a copy-in stream, a compute stream and the
+// events that order them.  A *_host call works on the arena of the device that is current when it
+// is entered and holds that arena's mutex for its duration, so calls on different devices run
+// concurrently and a process may switch devices between calls.
 struct Arena {
     std::mutex mu;
+    bool ready_ok = false;
     cudaStream_t stream = nullptr;    // copy-in stream (H2D)
     cudaStream_t compute = nullptr;   // kernels + D2H
     cudaEvent_t ready[kMaxChunks] = {};
     unsigned char *base = nullptr;
     size_t cap = 0, used = 0;
 
+    void teardown() {
+        for (int i = 0; i < kMaxChunks; ++i)
+            if (ready[i]) { cudaEventDestroy(ready[i]); ready[i] = nullptr; }
+        if (compute) { cudaStreamDestroy(compute); compute = nullptr; }
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+        ready_ok = false;
+    }
     int ensure(size_t bytes) {
-        if (!stream) {
+        if (!ready_ok) {
             cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-            if (e != cudaSuccess) { g_last_cuda_error = e; stream = nullptr; return IPFA_ERR_CUDA; }
-            e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking);
-            if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
-            for (int i = 0; i < kMaxChunks; ++i) {
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking);
+            for (int i = 0; i < kMaxChunks && e == cudaSuccess; ++i)
                 e = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming);
-                if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
-            }
+            if (e != cudaSuccess) { g_last_cuda_error = e; teardown(); return IPFA_ERR_CUDA; }
+            ready_ok = true;
         }
         if (bytes > cap) {
             if (base) { cudaStreamSynchronize(stream); cudaStreamSynchronize(compute); cudaFree(base); base = nullptr; cap = 0; }
             size_t want = bytes + (bytes >> 3) + (1 << 20);
             cudaError_t e = cudaMalloc(&base, want);
-            if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+            if (e != cudaSuccess) { g_last_cuda_error = e; base = nullptr; return IPFA_ERR_CUDA; }
             cap = want;
         }
         used = 0;
         return IPFA_OK;
+    }
+    // before ANY return that leaves copies in flight on the caller's buffers
+    void quiesce() {
+        if (stream) cudaStreamSynchronize(stream);
+        if (compute) cudaStreamSynchronize(compute);
     }
     template <typename T>
     T *take(size_t count) {
@@ -50,17 +101,34 @@ struct Arena {
         return p;
     }
 };
-Arena g_arena;
+Arena g_arenas[kMaxDevices];
+
+Arena *current_arena() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        g_last_cuda_error = (e != cudaSuccess) ? e : cudaErrorInvalidDevice;
+        return nullptr;
+    }
+    return &g_arenas[dev];
+}
 inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// inside a *_host function `A` is the locked arena: an error return first waits for the copies that
+// were already queued on the caller's host buffers
 #define IPFA_CUDA(call)                                              \
     do {                                                             \
         cudaError_t e__ = (call);                                    \
-        if (e__ != cudaSuccess) { g_last_cuda_error = e__; return IPFA_ERR_CUDA; } \
+        if (e__ != cudaSuccess) { g_last_cuda_error = e__; A.quiesce(); return IPFA_ERR_CUDA; } \
+    } while (0)
+#define IPFA_RC(expr)                                                \
+    do {                                                             \
+        int rc__ = (expr);                                           \
+        if (rc__) { A.quiesce(); return rc__; }                      \
     } while (0)
 
 // copy a [N, rows, V] fp32 host block (row pitch V) with batch stride stride_n
-int upload_lp(float *dst, const float *src, int64_t stride_n, int N, int64_t per_window, cudaStream_t st) {
+int upload_lp(Arena &A, float *dst, const float *src, int64_t stride_n, int N, int64_t per_window, cudaStream_t st) {
     if (stride_n == per_window || N == 1) {
         IPFA_CUDA(cudaMemcpyAsync(dst, src, (size_t)N * per_window * sizeof(float), cudaMemcpyHostToDevice, st));
     } else {
@@ -87,7 +155,7 @@ int windows_per_chunk(int N, int64_t per_window_floats) {
 
 using namespace ipfa;
 
-extern "C" int ipfa_version(void) { return 100; }
+extern "C" int ipfa_version(void) { return 200; }
 
 extern "C" const char *ipfa_status_string(int status) {
     switch (status) {
@@ -97,8 +165,15 @@ extern "C" const char *ipfa_status_string(int status) {
         case IPFA_ERR_WORKSPACE: return "workspace too small";
         case IPFA_ERR_CUDA: return "CUDA runtime error";
         case IPFA_ERR_AUDIO_SHORTER_THAN_TEXT: return "Audio is shorter than text!";
+        case IPFA_ERR_WINDOW: return "Maximum window size reached. Check data for large repetitions or noise.";
         default: return "unknown status";
     }
+}
+
+extern "C" void ipfa_tuning_reload(void) {
+    std::lock_guard<std::mutex> lock(g_tuning_mu);
+    g_tuning.load();
+    g_tuning_loaded = true;
 }
 
 extern "C" const char *ipfa_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda_error); }
@@ -117,20 +192,23 @@ extern "C" int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t st
     if (!lp || !in_len || !tgt_len || !nll_out || N < 0 || Tmax < 0 || stride_t != V ||
         (Lmax > 0 && !targets))
         return IPFA_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lock(g_arena.mu);
+    Arena *arena = current_arena();
+    if (!arena) return IPFA_ERR_CUDA;
+    Arena &A = *arena;
+    std::lock_guard<std::mutex> lock(A.mu);
     const int64_t per_window = (int64_t)Tmax * V;
     const size_t ws = ipfa_ctc_alpha_workspace_bytes(N, Tmax, Lmax, V);
     size_t need = pad256((size_t)N * per_window * 4) + pad256((size_t)N * (Lmax > 0 ? Lmax : 1) * 4) +
                   3 * pad256((size_t)N * 4) + pad256(ws) + 1024;
-    int rc = g_arena.ensure(need);
+    int rc = A.ensure(need);
     if (rc) return rc;
-    cudaStream_t st = g_arena.stream;
-    float *d_lp = g_arena.take<float>((size_t)N * per_window);
-    int32_t *d_tg = g_arena.take<int32_t>((size_t)N * (Lmax > 0 ? Lmax : 1));
-    int32_t *d_il = g_arena.take<int32_t>(N);
-    int32_t *d_tl = g_arena.take<int32_t>(N);
-    float *d_out = g_arena.take<float>(N);
-    void *d_ws = g_arena.take<unsigned char>(ws);
+    cudaStream_t st = A.stream;
+    float *d_lp = A.take<float>((size_t)N * per_window);
+    int32_t *d_tg = A.take<int32_t>((size_t)N * (Lmax > 0 ? Lmax : 1));
+    int32_t *d_il = A.take<int32_t>(N);
+    int32_t *d_tl = A.take<int32_t>(N);
+    float *d_out = A.take<float>(N);
+    void *d_ws = A.take<unsigned char>(ws);
     if (Lmax > 0) {
         if (tgt_stride == Lmax)
             IPFA_CUDA(cudaMemcpyAsync(d_tg, targets, (size_t)N * Lmax * 4, cudaMemcpyHostToDevice, st));
@@ -141,21 +219,21 @@ extern "C" int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t st
     IPFA_CUDA(cudaMemcpyAsync(d_il, in_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_tl, tgt_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     const int C = windows_per_chunk(N, per_window);
-    cudaStream_t cs = g_arena.compute;
+    cudaStream_t cs = A.compute;
     // every copy is queued before the first kernel launch, so the copy engine never waits for the host
     int n_chunks = 0;
     for (int w0 = 0; w0 < N; w0 += C, ++n_chunks) {
         const int n = (N - w0 < C) ? (N - w0) : C;
-        rc = upload_lp(d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
-        if (rc) return rc;
-        IPFA_CUDA(cudaEventRecord(g_arena.ready[n_chunks], st));
+        rc = upload_lp(A, d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
+        IPFA_RC(rc);
+        IPFA_CUDA(cudaEventRecord(A.ready[n_chunks], st));
     }
     for (int w0 = 0, ci = 0; w0 < N; w0 += C, ++ci) {
         const int n = (N - w0 < C) ? (N - w0) : C;
-        IPFA_CUDA(cudaStreamWaitEvent(cs, g_arena.ready[ci], 0));
+        IPFA_CUDA(cudaStreamWaitEvent(cs, A.ready[ci], 0));
         rc = ipfa_ctc_alpha_device(d_lp + (int64_t)w0 * per_window, per_window, V, d_tg + (int64_t)w0 * Lmax, Lmax,
                                    d_il + w0, d_tl + w0, n, Tmax, Lmax, V, blank, d_out + w0, d_ws, ws, cs);
-        if (rc) return rc;
+        IPFA_RC(rc);
     }
     IPFA_CUDA(cudaMemcpyAsync(nll_out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost, cs));
     IPFA_CUDA(cudaStreamSynchronize(cs));
@@ -172,7 +250,10 @@ extern "C" int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t 
     if (!lp || !in_len || !tgt_len || !paths_out || !status_out || N < 0 || Tmax < 0 || stride_t != V ||
         (Lmax > 0 && !targets) || ((tok_start == nullptr) != (tok_end == nullptr)))
         return IPFA_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lock(g_arena.mu);
+    Arena *arena = current_arena();
+    if (!arena) return IPFA_ERR_CUDA;
+    Arena &A = *arena;
+    std::lock_guard<std::mutex> lock(A.mu);
     const int64_t per_window = (int64_t)Tmax * V;
     size_t ws = ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V);
     {   // chunks may pick a lattice shape with a different backpointer pitch
@@ -186,21 +267,21 @@ extern "C" int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t 
     const size_t lcap = (size_t)(Lmax > 0 ? Lmax : 1);
     size_t need = pad256((size_t)N * per_window * 4) + pad256((size_t)N * lcap * 4) * 4 +
                   4 * pad256((size_t)N * 4) + 2 * pad256((size_t)N * Tmax * 4) + pad256(ws) + 4096;
-    int rc = g_arena.ensure(need);
+    int rc = A.ensure(need);
     if (rc) return rc;
-    cudaStream_t st = g_arena.stream;
-    float *d_lp = g_arena.take<float>((size_t)N * per_window);
-    int32_t *d_tg = g_arena.take<int32_t>((size_t)N * lcap);
-    int32_t *d_il = g_arena.take<int32_t>(N);
-    int32_t *d_tl = g_arena.take<int32_t>(N);
-    int32_t *d_paths = g_arena.take<int32_t>((size_t)N * Tmax);
-    float *d_scores = g_arena.take<float>((size_t)N * Tmax);
-    int32_t *d_ts = g_arena.take<int32_t>((size_t)N * lcap);
-    int32_t *d_te = g_arena.take<int32_t>((size_t)N * lcap);
-    float *d_tp = g_arena.take<float>((size_t)N * lcap);
-    float *d_total = g_arena.take<float>(N);
-    int32_t *d_status = g_arena.take<int32_t>(N);
-    void *d_ws = g_arena.take<unsigned char>(ws);
+    cudaStream_t st = A.stream;
+    float *d_lp = A.take<float>((size_t)N * per_window);
+    int32_t *d_tg = A.take<int32_t>((size_t)N * lcap);
+    int32_t *d_il = A.take<int32_t>(N);
+    int32_t *d_tl = A.take<int32_t>(N);
+    int32_t *d_paths = A.take<int32_t>((size_t)N * Tmax);
+    float *d_scores = A.take<float>((size_t)N * Tmax);
+    int32_t *d_ts = A.take<int32_t>((size_t)N * lcap);
+    int32_t *d_te = A.take<int32_t>((size_t)N * lcap);
+    float *d_tp = A.take<float>((size_t)N * lcap);
+    float *d_total = A.take<float>(N);
+    int32_t *d_status = A.take<int32_t>(N);
+    void *d_ws = A.take<unsigned char>(ws);
     if (Lmax > 0)
         IPFA_CUDA(cudaMemcpy2DAsync(d_tg, (size_t)Lmax * 4, targets, (size_t)tgt_stride * 4, (size_t)Lmax * 4,
                                     N, cudaMemcpyHostToDevice, st));
@@ -208,20 +289,20 @@ extern "C" int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t 
     IPFA_CUDA(cudaMemcpyAsync(d_tl, tgt_len, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     const bool tok = tok_start != nullptr && Lmax > 0;
     const int C = windows_per_chunk(N, per_window);
-    cudaStream_t cs = g_arena.compute;
+    cudaStream_t cs = A.compute;
     for (int w0 = 0, ci = 0; w0 < N; w0 += C, ++ci) {
         const int n = (N - w0 < C) ? (N - w0) : C;
         const int64_t ot = (int64_t)w0 * Tmax, ol = (int64_t)w0 * Lmax;
-        rc = upload_lp(d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
-        if (rc) return rc;
-        IPFA_CUDA(cudaEventRecord(g_arena.ready[ci], st));
-        IPFA_CUDA(cudaStreamWaitEvent(cs, g_arena.ready[ci], 0));
+        rc = upload_lp(A, d_lp + (int64_t)w0 * per_window, lp + (int64_t)w0 * stride_n, stride_n, n, per_window, st);
+        IPFA_RC(rc);
+        IPFA_CUDA(cudaEventRecord(A.ready[ci], st));
+        IPFA_CUDA(cudaStreamWaitEvent(cs, A.ready[ci], 0));
         rc = ipfa_ctc_viterbi_device(d_lp + (int64_t)w0 * per_window, per_window, V, d_tg + ol, Lmax, d_il + w0,
                                      d_tl + w0, n, Tmax, Lmax, V, blank, d_paths + ot,
                                      scores_out ? d_scores + ot : nullptr, tok ? d_ts + ol : nullptr,
                                      tok ? d_te + ol : nullptr, (tok && tok_score) ? d_tp + ol : nullptr,
                                      d_total + w0, d_status + w0, d_ws, ws, cs);
-        if (rc) return rc;
+        IPFA_RC(rc);
         IPFA_CUDA(cudaMemcpyAsync(paths_out + ot, d_paths + ot, (size_t)n * Tmax * 4, cudaMemcpyDeviceToHost, cs));
         if (scores_out)
             IPFA_CUDA(cudaMemcpyAsync(scores_out + ot, d_scores + ot, (size_t)n * Tmax * 4, cudaMemcpyDeviceToHost, cs));
@@ -248,12 +329,16 @@ extern "C" int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t strid
     if (!lp || !in_len || !gt || !n_cols || !utt_begin || !n_utts || !seg_out || !term_t_out || !status_out ||
         N < 0 || Tmax <= 0 || Cmax <= 0 || Kmax <= 0 || stride_t != V)
         return IPFA_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lock(g_arena.mu);
+    Arena *arena = current_arena();
+    if (!arena) return IPFA_ERR_CUDA;
+    Arena &A = *arena;
+    std::lock_guard<std::mutex> lock(A.mu);
     const int64_t per_window = (int64_t)Tmax * V;
     // audio longer than ctc-segmentation's min_window_size (8000 frames): windowed table mode, the
     // window doubled after IPFA_WIN_WINDOW_TOO_SMALL up to max_window_size (100000) like the
     // reference's `except IndexError` loop
     const bool windowed = Tmax > 8000;
+    bool window_exhausted = false;
     int window = 8000;
     size_t ws = windowed ? 0 : ipfa_ctcseg_workspace_bytes(N, Tmax, Cmax, Kmax, V);
     if (windowed)
@@ -267,24 +352,24 @@ extern "C" int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t strid
                   pad256((size_t)N * (Kmax + 1) * 4) + 4 * pad256((size_t)N * 4) + pad256(n_seg * 8) +
                   pad256((size_t)N * Kmax * 4) + pad256((size_t)N * Kmax * (size_t)Cmax * 4) +
                   2 * pad256((size_t)N * Kmax * (size_t)Tmax * 4) + pad256(ws) + 8192;
-    int rc = g_arena.ensure(need);
+    int rc = A.ensure(need);
     if (rc) return rc;
-    cudaStream_t st = g_arena.stream;
-    float *d_lp = g_arena.take<float>((size_t)N * per_window);
-    int32_t *d_gt = g_arena.take<int32_t>((size_t)N * Cmax);
-    int32_t *d_ub = g_arena.take<int32_t>((size_t)N * (Kmax + 1));
-    int32_t *d_il = g_arena.take<int32_t>(N);
-    int32_t *d_nc = g_arena.take<int32_t>(N);
-    int32_t *d_nu = g_arena.take<int32_t>(N);
-    int32_t *d_status = g_arena.take<int32_t>(N);
-    double *d_seg = g_arena.take<double>(n_seg);
-    int32_t *d_term = g_arena.take<int32_t>((size_t)N * Kmax);
-    int32_t *d_timing = timing_out ? g_arena.take<int32_t>((size_t)N * Kmax * Cmax) : nullptr;
-    float *d_cprob = char_prob_out ? g_arena.take<float>((size_t)N * Kmax * Tmax) : nullptr;
-    int32_t *d_state = state_out ? g_arena.take<int32_t>((size_t)N * Kmax * Tmax) : nullptr;
-    void *d_ws = g_arena.take<unsigned char>(ws);
-    rc = upload_lp(d_lp, lp, stride_n, N, per_window, st);
-    if (rc) return rc;
+    cudaStream_t st = A.stream;
+    float *d_lp = A.take<float>((size_t)N * per_window);
+    int32_t *d_gt = A.take<int32_t>((size_t)N * Cmax);
+    int32_t *d_ub = A.take<int32_t>((size_t)N * (Kmax + 1));
+    int32_t *d_il = A.take<int32_t>(N);
+    int32_t *d_nc = A.take<int32_t>(N);
+    int32_t *d_nu = A.take<int32_t>(N);
+    int32_t *d_status = A.take<int32_t>(N);
+    double *d_seg = A.take<double>(n_seg);
+    int32_t *d_term = A.take<int32_t>((size_t)N * Kmax);
+    int32_t *d_timing = timing_out ? A.take<int32_t>((size_t)N * Kmax * Cmax) : nullptr;
+    float *d_cprob = char_prob_out ? A.take<float>((size_t)N * Kmax * Tmax) : nullptr;
+    int32_t *d_state = state_out ? A.take<int32_t>((size_t)N * Kmax * Tmax) : nullptr;
+    void *d_ws = A.take<unsigned char>(ws);
+    rc = upload_lp(A, d_lp, lp, stride_n, N, per_window, st);
+    IPFA_RC(rc);
     IPFA_CUDA(cudaMemcpy2DAsync(d_gt, (size_t)Cmax * 4, gt, (size_t)gt_stride * 4, (size_t)Cmax * 4, N,
                                 cudaMemcpyHostToDevice, st));
     IPFA_CUDA(cudaMemcpyAsync(d_ub, utt_begin, (size_t)N * (Kmax + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -296,18 +381,20 @@ extern "C" int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t strid
         rc = ipfa_ctcseg_device(d_lp, per_window, V, d_il, d_gt, Cmax, d_nc, d_ub, d_nu, N, Tmax, Cmax, Kmax, V,
                                 blank, index_duration, score_len, flags, d_seg, d_term, d_timing, d_cprob, d_state,
                                 d_status, d_ws, ws, st);
-        if (rc) return rc;
+        IPFA_RC(rc);
     } else {
         while (true) {
             rc = ipfa_ctcseg_windowed_device(d_lp, nullptr, per_window, V, d_il, d_gt, Cmax, d_nc, d_ub, d_nu, N,
                                              Tmax, Cmax, Kmax, V, blank, index_duration, score_len, flags, window,
                                              1, d_seg, d_term, d_timing, d_cprob, d_state, d_status, d_ws, ws, st);
-            if (rc) return rc;
+            IPFA_RC(rc);
             IPFA_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
             IPFA_CUDA(cudaStreamSynchronize(st));
             bool too_small = false;
             for (int i = 0; i < N; ++i) too_small |= (status_out[i] & IPFA_WIN_WINDOW_TOO_SMALL) != 0;
-            if (!too_small || window >= Tmax || window * 2 >= 100000) break;
+            if (!too_small) break;
+            // the reference doubles the window and gives up with IndexError at max_window_size
+            if (window >= Tmax || window * 2 >= 100000) { window_exhausted = true; break; }
             window *= 2;
         }
     }
@@ -321,5 +408,5 @@ extern "C" int ipfa_ctcseg_host(const float *lp, int64_t stride_n, int64_t strid
         IPFA_CUDA(cudaMemcpyAsync(state_out, d_state, (size_t)N * Kmax * Tmax * 4, cudaMemcpyDeviceToHost, st));
     IPFA_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     IPFA_CUDA(cudaStreamSynchronize(st));
-    return IPFA_OK;
+    return window_exhausted ? IPFA_ERR_WINDOW : IPFA_OK;
 }

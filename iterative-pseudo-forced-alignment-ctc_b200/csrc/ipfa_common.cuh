@@ -7,6 +7,10 @@
 
 namespace ipfa {
 
+// Value of an IPFA_* tuning switch, or nullptr when it is not set.  The environment is read once per
+// process (host_api.cu; ipfa_tuning_reload() reads it again), never inside a compute call.
+const char *tuning(const char *name);
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 // Finite stand-in for log(0) in the log-sum-exp recursion: differences of two

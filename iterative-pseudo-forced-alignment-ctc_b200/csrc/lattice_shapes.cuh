@@ -42,7 +42,7 @@ inline bool shape_exists(int per, int warps, bool extra = false) {
 // target_warps: resident warps wanted on the whole GPU before widening PER.
 inline bool pick_lattice_shape(int units, int n_windows, LatticeShape *out, const char *env_name,
                                int warps_per_smsp = 3, bool extra = false) {
-    if (const char *e = getenv(env_name)) {  // tuning override "PER,WARPS"
+    if (const char *e = tuning(env_name)) {  // tuning override "PER,WARPS"
         int p = 0, w = 0;
         if (sscanf(e, "%d,%d", &p, &w) == 2 && shape_exists(p, w, extra) && 32 * w * p >= units) {
             out->PER = p; out->WARPS = w;

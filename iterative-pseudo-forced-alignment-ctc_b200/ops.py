@@ -15,7 +15,9 @@ Comparators these operators replace:
   anchor_select     the accept/shrink/revert state machine                     row A10
                     (/root/reference/src/iterative_utterance_alignment.py:221-379)
 """
+import contextlib
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -351,3 +353,26 @@ def text_round(x, decimals):
         rc = lib().ipfa_text_round_device(_ptr(x), x.numel(), int(decimals), _ptr(out), _stream(x.device))
     check(rc, "ipfa_text_round_device")
     return out
+
+
+@contextlib.contextmanager
+def tuning(**switches):
+    """``with tuning(IPFA_ALPHA_LOG="1"): ...`` -- set IPFA_* tuning switches for the block (tools and
+    tests; value ``None`` unsets).  The library reads the environment once per process, so the table
+    is re-read on entry and on exit (``ipfa_tuning_reload``)."""
+    old = {k: os.environ.get(k) for k in switches}
+    try:
+        for k, v in switches.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        lib().ipfa_tuning_reload()
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        lib().ipfa_tuning_reload()

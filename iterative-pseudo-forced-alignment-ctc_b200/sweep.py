@@ -19,7 +19,7 @@ from . import hostglue as hg
 from ._lib import check, lib
 
 ACTIVE, DONE, STOP_WINDOW, STOP_EXCEPTIONS, NEEDS_RECALC, CAPACITY, NO_AUDIO = range(7)
-STATUS_NAMES = ["active", "done", "window_to_stop", "exceptions_limit", "needs_recalc", "capacity"]
+STATUS_NAMES = ["active", "done", "window_to_stop", "exceptions_limit", "needs_recalc", "capacity", "no_audio"]
 
 _vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 

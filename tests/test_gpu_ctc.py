@@ -219,9 +219,8 @@ def test_viterbi_length_buckets(ipfa, monkeypatch):
     dev = [_dev(x) for x in (lp, tg, il, tl)]
     res = ipfa.ctc_forced_align(*dev)
     _check_viterbi(res, ref_paths, ref_scores, ref_status, il)
-    monkeypatch.setenv("IPFA_NO_BUCKETS", "1")
-    one = ipfa.ctc_forced_align(*dev)
-    monkeypatch.delenv("IPFA_NO_BUCKETS")
+    with ipfa.tuning(IPFA_NO_BUCKETS="1"):
+        one = ipfa.ctc_forced_align(*dev)
     for name in ("paths", "scores", "tok_start", "tok_end", "tok_score", "total", "status"):
         assert torch.equal(getattr(res, name), getattr(one, name)), name
     assert ((tl + 1 <= 32).sum() > 1000) and ((tl + 1 > 32).sum() > 300)
@@ -239,9 +238,8 @@ def test_alpha_length_buckets(ipfa, monkeypatch):
     dev = [_dev(x) for x in (lp, tg, il, tl)]
     nll = ipfa.ctc_alpha_nll(*dev)
     _check_nll(nll.cpu().numpy(), ref)
-    monkeypatch.setenv("IPFA_NO_BUCKETS", "1")
-    one = ipfa.ctc_alpha_nll(*dev)
-    monkeypatch.delenv("IPFA_NO_BUCKETS")
+    with ipfa.tuning(IPFA_NO_BUCKETS="1"):
+        one = ipfa.ctc_alpha_nll(*dev)
     _check_nll(one.cpu().numpy(), ref)
     # the two launch shapes associate the log-sum-exp differently: equal to fp32 rounding
     fin = torch.isfinite(one)
@@ -268,9 +266,8 @@ def test_alpha_linear_instance(ipfa, monkeypatch, shape, peaked):
     lin = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
     assert ipfa.ctc_alpha_redo_count(n) == 0
     _check_nll(lin, ref)
-    monkeypatch.setenv("IPFA_ALPHA_LOG", "1")
-    log = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
-    monkeypatch.delenv("IPFA_ALPHA_LOG")
+    with ipfa.tuning(IPFA_ALPHA_LOG="1"):
+        log = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
     _check_nll(log, ref)
     fin = np.isfinite(ref)
     np.testing.assert_allclose(lin[fin], log[fin], rtol=2e-5)
@@ -318,9 +315,8 @@ def test_alpha_linear_blank_in_target(ipfa, monkeypatch):
     dev = [_dev(x) for x in (lp, tg, il, tl)]
     lin = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
     assert ipfa.ctc_alpha_redo_count(16) == 6
-    monkeypatch.setenv("IPFA_ALPHA_LOG", "1")
-    log = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
-    monkeypatch.delenv("IPFA_ALPHA_LOG")
+    with ipfa.tuning(IPFA_ALPHA_LOG="1"):
+        log = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
     np.testing.assert_allclose(lin, log, rtol=1e-6)
 
 
@@ -348,8 +344,7 @@ def test_alpha_linear_instance_shapes(ipfa, monkeypatch, shape_env):
     l = min(32 * p * w - 1, 200)
     lp, tg, il, tl = ctc_case(50 + l, 12, 3 * l + 40, l, 32, ragged=True, repeats=True, peaked=(p == 2))
     ref = octc.ctc_alpha_nll(lp, tg, il, tl)
-    monkeypatch.setenv("IPFA_ALPHA_LIN_SHAPE", shape_env)
-    got = ipfa.ctc_alpha_nll(*[_dev(x) for x in (lp, tg, il, tl)]).cpu().numpy()
-    monkeypatch.delenv("IPFA_ALPHA_LIN_SHAPE")
+    with ipfa.tuning(IPFA_ALPHA_LIN_SHAPE=shape_env):
+        got = ipfa.ctc_alpha_nll(*[_dev(x) for x in (lp, tg, il, tl)]).cpu().numpy()
     assert ipfa.ctc_alpha_redo_count(12) == int(np.isinf(ref).sum())
     _check_nll(got, ref)

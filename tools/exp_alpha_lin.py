@@ -24,6 +24,7 @@ def run(lp, tg, il, tl, log):
         os.environ["IPFA_ALPHA_LOG"] = "1"
     else:
         os.environ.pop("IPFA_ALPHA_LOG", None)
+    ops.lib().ipfa_tuning_reload()  # the library reads its switches once per process
     out = ipfa.ctc_alpha_nll(torch.from_numpy(lp).to(dev), tg, il, tl).cpu().numpy()
     redo = 0 if log else ops.ctc_alpha_redo_count(len(il), dev)
     if redo and "--why" in sys.argv:
@@ -119,6 +120,7 @@ for label, env in [("log", {"IPFA_ALPHA_LOG": "1"}), ("lin 4,1", {"IPFA_ALPHA_LI
     os.environ.pop("IPFA_ALPHA_LOG", None)
     os.environ.pop("IPFA_ALPHA_LIN_SHAPE", None)
     os.environ.update(env)
+    ops.lib().ipfa_tuning_reload()
     for i in range(6):
         out = ipfa.ctc_alpha_nll(*sets[i % 3], il, tl)
     torch.cuda.synchronize()

@@ -1,6 +1,8 @@
-"""Randomised parity sweep on the GPU (not part of the test suite; run under gpurun):
-   python tools/fuzz_parity.py [seconds]
-Random shapes through every kernel family against the CPU oracle; prints and counts mismatches."""
+"""Randomised parity sweep on the GPU against the CPU oracle, every kernel family:
+
+    python tools/fuzz_parity.py [seconds] [alpha,viterbi,seg,windowed,sweep]     (under gpurun)
+
+``tests/test_gpu_fuzz.py`` runs a bounded, fixed-seed slice of it (``run_fuzz``) inside ``-m gpu``."""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,18 +13,13 @@ from oracle import ctc as octc
 from oracle import ctcseg as oseg
 from test_gpu_ctcseg import _pack
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
-only = sys.argv[2].split(",") if len(sys.argv) > 2 else None   # e.g. "alpha" or "alpha,viterbi"
-rng = np.random.default_rng(int(time.time()) % 100000)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-t_end = time.time() + budget
-n_cases = n_bad = 0
-counts = {}
-while time.time() < t_end:
-    kind = rng.choice(["alpha", "viterbi", "seg", "windowed", "sweep"], p=[0.3, 0.3, 0.2, 0.15, 0.05])
-    if only and kind not in only:
-        continue
-    counts[kind] = counts.get(kind, 0) + 1
+KINDS = ["alpha", "viterbi", "seg", "windowed", "sweep"]
+WEIGHTS = [0.3, 0.3, 0.2, 0.15, 0.05]
+
+
+def one_case(kind, rng, counts):
+    """One random case of ``kind``; returns (ok, description)."""
     seed = int(rng.integers(1 << 30))
     try:
         if kind in ("alpha", "viterbi"):
@@ -41,22 +38,20 @@ while time.time() < t_end:
                 ref = octc.ctc_alpha_nll(lp, tg, il, tl)
                 # the window scorer's instances: default choice, a forced linear-domain shape, log-domain alone
                 mode = rng.choice(["default", "shape", "log"], p=[0.5, 0.35, 0.15])
+                switches = {}
                 if mode == "shape":
-                    os.environ["IPFA_ALPHA_LIN_SHAPE"] = str(rng.choice(["1,1", "2,1", "4,1", "8,1", "1,2", "2,2", "4,2"]))
-                    desc += " lin_shape=" + os.environ["IPFA_ALPHA_LIN_SHAPE"]
+                    switches["IPFA_ALPHA_LIN_SHAPE"] = str(rng.choice(["1,1", "2,1", "4,1", "8,1", "1,2", "2,2", "4,2"]))
+                    desc += " lin_shape=" + switches["IPFA_ALPHA_LIN_SHAPE"]
                 elif mode == "log":
-                    os.environ["IPFA_ALPHA_LOG"] = "1"
+                    switches["IPFA_ALPHA_LOG"] = "1"
                     desc += " log"
                 if rng.random() < 0.2:   # sharper emissions: some windows go through the redo list
                     sc = float(rng.choice([4.0, 20.0, 60.0]))
                     lp = torch.from_numpy(lp * sc).log_softmax(-1).numpy()
                     ref = octc.ctc_alpha_nll(lp, tg, il, tl)
                     desc += f" sharp x{sc}"
-                try:
+                with ipfa.tuning(**switches):
                     got = ipfa.ctc_alpha_nll(dev(lp), dev(tg), dev(il), dev(tl)).cpu().numpy()
-                finally:
-                    os.environ.pop("IPFA_ALPHA_LIN_SHAPE", None)
-                    os.environ.pop("IPFA_ALPHA_LOG", None)
                 counts["alpha_redo"] = counts.get("alpha_redo", 0) + ipfa.ctc_alpha_redo_count(n)
                 fin = np.isfinite(ref)
                 ok = np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], ref[fin], rtol=1e-4, atol=1e-4)
@@ -136,9 +131,36 @@ while time.time() < t_end:
                 ok &= all(seg[u, 0] == segs[u][0] and seg[u, 1] == segs[u][1] and
                           np.isclose(seg[u, 2], segs[u][2], rtol=1e-12, atol=0) for u in range(k))
     except Exception as exc:  # noqa: BLE001
-        ok, desc = False, f"{kind} seed={seed}: {exc!r}"
-    n_cases += 1
-    if not ok:
-        n_bad += 1
-        print("MISMATCH", desc, "seed", seed, flush=True)
-print(f"{n_cases} random cases {counts}, {n_bad} mismatches")
+        ok, desc = False, f"{kind}: {exc!r}"
+    return ok, f"{desc} seed={seed}"
+
+
+def run_fuzz(seed, budget_s=None, cases_per_kind=None, only=None):
+    """Random cases until the time budget or the per-kind case count is used up.
+    Returns (number of cases, list of mismatch descriptions, counts per kind)."""
+    rng = np.random.default_rng(seed)
+    kinds = [k for k in KINDS if not only or k in only]
+    counts, bad, n_cases = {}, [], 0
+    t_end = time.time() + budget_s if budget_s else None
+    while True:
+        if t_end and time.time() >= t_end:
+            break
+        open_kinds = [k for k in kinds if cases_per_kind is None or counts.get(k, 0) < cases_per_kind[k]]
+        if not open_kinds:
+            break
+        w = np.array([WEIGHTS[KINDS.index(k)] for k in open_kinds])
+        kind = str(rng.choice(open_kinds, p=w / w.sum()))
+        counts[kind] = counts.get(kind, 0) + 1
+        ok, desc = one_case(kind, rng, counts)
+        n_cases += 1
+        if not ok:
+            bad.append(desc)
+            print("MISMATCH", desc, flush=True)
+    return n_cases, bad, counts
+
+
+if __name__ == "__main__":
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
+    n, bad, counts = run_fuzz(int(time.time()) % 100000, budget_s=budget, only=only)
+    print(f"{n} random cases {counts}, {len(bad)} mismatches")

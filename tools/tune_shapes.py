@@ -43,12 +43,14 @@ def main():
             wl.step(ipfa, sets[i[0] % len(sets)])
 
         os.environ.pop(env, None)
+        ipfa.ops.lib().ipfa_tuning_reload()  # the library reads its switches once per process
         base = time_fn(fn, 10)
         print(f"{name}: default shape {base:.3f} ms", flush=True)
         for p, w in SHAPES:
             if 32 * w * p < l + 1 or 32 * w * p > 8 * (l + 1) + 64:
                 continue
             os.environ[env] = f"{p},{w}"
+            ipfa.ops.lib().ipfa_tuning_reload()
             try:
                 ms = time_fn(fn, 10)
                 print(f"  {name} shape P={p} W={w}: {ms:.3f} ms", flush=True)
