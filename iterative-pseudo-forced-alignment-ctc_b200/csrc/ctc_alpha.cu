@@ -724,6 +724,12 @@ ctc_alpha_kernel(const AlphaParams prm) {
     }
 }
 
+}  // namespace ipfa
+
+#include "ctc_alpha_f32.cuh"
+
+namespace ipfa {
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -799,6 +805,42 @@ static int launch_alpha_lin(const AlphaParams &prm, int Lmax, int P, int W, cuda
 #undef IPFA_LIN
     return IPFA_ERR_UNSUPPORTED;
 }
+// fp32 tier (ctc_alpha_f32.cuh): one warp per half window, P pairs per lane, V <= 32
+template <int P>
+static int launch_alpha_f32_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
+    PipeGeometry g = pipe_geometry(32, 16 * 1024);
+    prm.pitch = g.pitch;
+    prm.tc = g.tc;
+    prm.u_cap = 0;
+    prm.l_cap = Lmax;
+    prm.group_smem = (g.ring_bytes + 16 + 32 + 15) & ~(size_t)15;
+    const size_t smem = prm.group_smem * 4;
+    auto kern = ctc_alpha_f32_kernel<P>;
+    static size_t smem_set[16] = {0};
+    int dev_id = 0;
+    cudaError_t e = cudaGetDevice(&dev_id);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    if (dev_id < 0 || dev_id >= 16 || smem > smem_set[dev_id]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+        if (dev_id >= 0 && dev_id < 16) smem_set[dev_id] = smem;
+    }
+    const int blocks = (prm.halves * prm.N + 3) / 4;
+    kern<<<blocks, 128, smem, stream>>>(prm);
+    ++g_launch_count;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
+static int launch_alpha_f32(const AlphaParams &prm, int Lmax, int P, cudaStream_t stream) {
+    switch (P) {
+        case 1: return launch_alpha_f32_p<1>(prm, Lmax, stream);
+        case 2: return launch_alpha_f32_p<2>(prm, Lmax, stream);
+        case 4: return launch_alpha_f32_p<4>(prm, Lmax, stream);
+        case 8: return launch_alpha_f32_p<8>(prm, Lmax, stream);
+    }
+    return IPFA_ERR_UNSUPPORTED;
+}
 constexpr int kLinMaxPairs = 256;
 // pairs per lane / warps per half window for `units` state pairs: one warp per half window.
 // The two-warp instances (fp64 exchange line + CTA barrier per frame, as in the log-domain
@@ -827,10 +869,10 @@ static inline size_t alpha_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 // arrival counters [N] + the two halves' state vectors at the cut [N][2][2][Lmax + 1]
 extern "C" size_t ipfa_ctc_alpha_workspace_bytes(int N, int, int Lmax, int) {
     const size_t n = (size_t)(N > 0 ? N : 1), l1 = (size_t)(Lmax > 0 ? Lmax : 0) + 1;
-    // arrival counters (+ the redo counter and its reason bits right behind them: one memset), join vectors,
-    // length-bucket lists [2][N] + their counters, redo list [N]
-    return alpha_pad256((n + 2) * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
-           alpha_pad256(n * 2 * sizeof(int32_t)) + 256 + alpha_pad256(n * sizeof(int32_t)) + 256;
+    // arrival counters (+ the two tiers' redo counters and reason bits right behind them: one memset),
+    // join vectors, length-bucket lists [2][N] + their counters, the two redo lists [N]
+    return alpha_pad256((n + 4) * sizeof(int32_t)) + alpha_pad256(n * 4 * l1 * sizeof(float)) +
+           alpha_pad256(n * 2 * sizeof(int32_t)) + 256 + 2 * alpha_pad256(n * sizeof(int32_t)) + 256;
 }
 
 extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
@@ -862,8 +904,8 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     prm.join_count = static_cast<int *>(workspace);
     prm.join_vec = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) +
-                                             alpha_pad256(((size_t)N + 2) * sizeof(int32_t)));
-    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, ((size_t)N + 2) * sizeof(int32_t), st);
+                                             alpha_pad256(((size_t)N + 4) * sizeof(int32_t)));
+    cudaError_t e = cudaMemsetAsync(prm.join_count, 0, ((size_t)N + 4) * sizeof(int32_t), st);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     // Dense panels whose lattice fits one warp: the linear-domain instance scores the windows and
     // lists the ones it cannot vouch for; the log-domain instance below then runs over that list.
@@ -874,28 +916,45 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     int32_t *count = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(order) +
                                                  alpha_pad256((size_t)N * 2 * sizeof(int32_t)));
     int32_t *redo = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(count) + 256);
+    int32_t *redo_f32 = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(redo) +
+                                                    alpha_pad256((size_t)N * sizeof(int32_t)));
     if (lin) {
-        prm.redo = redo;
-        prm.redo_count = prm.join_count + N;
         int P = 0, W = 0;
         lin_shape(Lmax + 1, (long long)halves * N, &P, &W);
-        if (N >= kBucketMinWindows && W == 1 && P >= 2 && !tuning("IPFA_NO_BUCKETS")) {
+        // Tiers: fp32 linear-domain (V <= 32) -> fp64 linear-domain over the windows the first could
+        // not vouch for -> log-domain over the windows the second could not vouch for.  The lists
+        // and their lengths stay on the device; a tier's groups beyond its list's length leave at once.
+        // (the fp32 tier is OFF unless IPFA_ALPHA_F32=1: on BASELINE configs[1] the states of one lane
+        // lie 100-150 binades apart, fp32 cannot hold that next to the growth between two re-scalings,
+        // 58 % of the windows are handed over and the step gets slower -- ctc_alpha_f32.cuh)
+        const bool f32 = V <= 32 && W == 1 && !tuning("IPFA_ALPHA_LIN_SHAPE") &&
+                         tuning("IPFA_ALPHA_F32") && tuning("IPFA_ALPHA_F32")[0] == '1';
+        const bool buckets = N >= kBucketMinWindows && W == 1 && P >= 2 && !tuning("IPFA_NO_BUCKETS");
+        if (buckets) {
             e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
             if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
             length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, 32 * P / 2, order, count);
             ++g_launch_count;
-            for (int cls = 0; cls < 2; ++cls) {
-                prm.order = order + (int64_t)cls * N;
-                prm.count = count + cls;
-                const int rc = launch_alpha_lin(prm, Lmax, cls == 0 ? P / 2 : P, 1, st);
-                if (rc) return rc;
-            }
-        } else {
-            const int rc = launch_alpha_lin(prm, Lmax, P, W, st);
+        }
+        // first tier over every window (in two length buckets when the batch is large)
+        prm.redo = f32 ? redo_f32 : redo;
+        prm.redo_count = prm.join_count + N + (f32 ? 2 : 0);
+        for (int cls = 0; cls < (buckets ? 2 : 1); ++cls) {
+            if (buckets) { prm.order = order + (int64_t)cls * N; prm.count = count + cls; }
+            const int Pc = (buckets && cls == 0) ? P / 2 : P;
+            const int rc = f32 ? launch_alpha_f32(prm, Lmax, Pc, st) : launch_alpha_lin(prm, Lmax, Pc, W, st);
+            if (rc) return rc;
+        }
+        if (f32) {  // second tier: the fp64 instance over the first tier's list
+            prm.order = redo_f32;
+            prm.count = prm.join_count + N + 2;
+            prm.redo = redo;
+            prm.redo_count = prm.join_count + N;
+            const int rc = launch_alpha_lin(prm, Lmax, P, 1, st);
             if (rc) return rc;
         }
         prm.order = redo;
-        prm.count = prm.redo_count;
+        prm.count = prm.join_count + N;
         prm.redo = nullptr;
         prm.redo_count = nullptr;
         if (dense) return dispatch_alpha<true>(prm, Lmax, s, st);

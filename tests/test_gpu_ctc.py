@@ -348,3 +348,22 @@ def test_alpha_linear_instance_shapes(ipfa, monkeypatch, shape_env):
         got = ipfa.ctc_alpha_nll(*[_dev(x) for x in (lp, tg, il, tl)]).cpu().numpy()
     assert ipfa.ctc_alpha_redo_count(12) == int(np.isinf(ref).sum())
     _check_nll(got, ref)
+
+
+def test_alpha_fp32_tier_is_exact_where_it_answers(ipfa):
+    """The optional fp32 tier (IPFA_ALPHA_F32=1) in front of the fp64 one: whatever it cannot vouch for
+    goes down the redo lists (fp32 -> fp64 -> log domain), so results do not depend on it."""
+    from oracle import ctc as octc
+    for seed, n, t, l, peaked in ((1, 48, 300, 100, False), (2, 24, 500, 100, True), (3, 40, 90, 50, False),
+                                  (6, 64, 40, 10, False), (8, 33, 200, 0, False)):
+        lp, tg, il, tl = ctc_case(seed, n, t, max(l, 1), 32, ragged=True, repeats=True, peaked=peaked)
+        if l == 0:
+            tl[:] = 0
+        ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+        dev = [_dev(x) for x in (lp, tg, il, tl)]
+        plain = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+        with ipfa.tuning(IPFA_ALPHA_F32="1"):
+            tiered = ipfa.ctc_alpha_nll(*dev).cpu().numpy()
+        _check_nll(tiered, ref)
+        fin = np.isfinite(ref)
+        np.testing.assert_allclose(tiered[fin], plain[fin], rtol=2e-5)
