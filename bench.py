@@ -137,8 +137,8 @@ class CtcWorkload:
         read = int((il * np.minimum(tl + 1, self.v) * 4 + tl * 4).sum())
         if self.kind == "alpha":
             write = 4 * len(il)
-        else:  # 2-bit backpointers written once and read once + paths + frame scores
-            write = int((2 * ((il * (2 * tl + 1) * 2 + 7) // 8) + il * 8).sum())
+        else:  # backpointer planes, 1.5 bits per state and frame, written once and read once + paths + frame scores
+            write = int((2 * ((il * (2 * tl + 1) * 3 + 15) // 16) + il * 8).sum())
         return cells, hours, read + write
 
     def step(self, ipfa, inputs):
@@ -256,8 +256,10 @@ class SegWorkload:
         cells = int(self.n) * self.t * self.cols
         hours = self.n * self.t * FRAME_SECONDS / 3600.0
         read = self.n * self.t * min(self.cols, self.v) * 4 + self.n * self.cols * 4
-        bp = 2 * ((self.n * self.t * self.cols + 7) // 8)  # 1-bit backpointers, written + read once
-        out = self.n * self.k * self.k * 24 + self.n * self.k * self.t * 4
+        # 1-bit transition marks written once; the backtrace hops from switch to switch and reads only the
+        # blocks it walks (profiles/r01_seg.txt: 191 MB of DRAM traffic per step), so its reads are not charged
+        bp = (self.n * self.t * self.cols + 7) // 8
+        out = self.n * self.k * self.k * 24 + self.n * self.k * 4
         return cells, hours, read + bp + out
 
     def step(self, ipfa, inputs):
@@ -394,25 +396,18 @@ def c5_reference_arm(args):
     return 0
 
 
-def c5_arm(args):
-    """A step = the whole anchor loop of this rank's files (state reset, run until every file stops)."""
+def c5_measure(hours_total, world, rank, dev, steps, warm, groups=32, use_graphs=True, capacity=None,
+               with_e2e=True):
+    """BASELINE configs[4] on this job's ranks: ONE corpus of `hours_total` hours, its files sharded over
+    the ranks (LPT by duration), every rank runs the whole anchor loop of its files.  A step = state
+    reset + run until every file stops.  Collective calls (all ranks must enter).  Returns a dict of
+    job-wide numbers (times are the max over ranks, counts the sums)."""
     import torch
     import torch.distributed as dist
-    import ipfa_b200 as ipfa
     import sweep_corpus
     from ipfa_b200 import sweep as sw_mod
     stub = __import__("importlib").import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    specs, minutes, mine = _c5_specs(args.hours, world, rank)
+    specs, minutes, mine = _c5_specs(hours_total, world, rank)
     files = [sw_mod.SweepFile(s.file_id, s.audio_path, sweep_corpus.emissions(s, dev, seed=i), s.n_samples, s.rows)
              for i, s in zip(mine, specs)]
     files = sw_mod.sort_longest_first(files)
@@ -420,8 +415,7 @@ def c5_arm(args):
     for f in files:
         f.lpz = None  # the corpus holds the only copy
     sweep = sw_mod.AnchorSweep(corpus, index_duration=FRAME_SECONDS, samples_to_frames_ratio=320.0,
-                               groups=args.groups, use_graphs=not args.no_graphs,
-                               capacity=[int(x) for x in args.capacity.split(',')] if args.capacity else None)
+                               groups=groups, use_graphs=use_graphs, capacity=capacity)
     hours_mine = sum(s.n_samples for s in specs) / 16000 / 3600.0
 
     def barrier():
@@ -434,12 +428,10 @@ def c5_arm(args):
         sweep.reset()
         return sweep.run(steps_per_poll=16)
 
-    steps = min(args.steps, 10)
-    warm = max(min(args.warmup, 3), 3)
     for _ in range(warm):   # also settles the launch capacity (CAPACITY round trips happen here)
         status = one_sweep()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     launches0 = sweep.kernel_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -455,74 +447,108 @@ def c5_arm(args):
     sampler.join()
     st = sweep.stats()
 
-    # end to end: emissions start in pinned host memory; corpus upload + sweep + result rows back
-    host_lp = corpus.lp.cpu().pin_memory()
-    out_seg_h = torch.empty(sweep.out_seg.shape, dtype=torch.float64).pin_memory()
-    out_info_h = torch.empty(sweep.out_info.shape, dtype=torch.int32).pin_memory()
-    e2e_steps = max(2, min(steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        corpus.lp.copy_(host_lp, non_blocking=True)
-        one_sweep()
-        out_seg_h.copy_(sweep.out_seg, non_blocking=True)
-        out_info_h.copy_(sweep.out_info, non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    e2e_ms, h2d_b, d2h_b = 0.0, 0.0, 0.0
+    if with_e2e:
+        # end to end: emissions start in pinned host memory; corpus upload + sweep + result rows back
+        host_lp = corpus.lp.cpu().pin_memory()
+        out_seg_h = torch.empty(sweep.out_seg.shape, dtype=torch.float64).pin_memory()
+        out_info_h = torch.empty(sweep.out_info.shape, dtype=torch.int32).pin_memory()
+        e2e_steps = max(2, min(steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            corpus.lp.copy_(host_lp, non_blocking=True)
+            one_sweep()
+            out_seg_h.copy_(sweep.out_seg, non_blocking=True)
+            out_info_h.copy_(sweep.out_info, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        h2d_b, d2h_b = float(host_lp.numel() * 4), float(out_seg_h.numel() * 8 + out_info_h.numel() * 4)
 
-    vals = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    vals = torch.tensor([elapsed_ms, e2e_ms, float(st["steps"]), float(len(files))], dtype=torch.float64, device=dev)
     sums = torch.tensor([hours_mine, float(st["cells"]), float(st["frames"]), float(st["windows"]),
-                         float(len(files)), float((status == sw_mod.DONE).sum()), float(launches),
-                         float(host_lp.numel() * 4), float(out_seg_h.numel() * 8 + out_info_h.numel() * 4)],
+                         float(len(files)), float((status == sw_mod.DONE).sum()), float(launches), h2d_b, d2h_b],
                         dtype=torch.float64, device=dev)
+    gathered = None
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         # the job's only collective on results: per-utterance rows to rank 0 (not timed)
         from ipfa_b200 import sharding
         gathered = sharding.gather_objects([len(r) for r in sweep.file_rows()])
-    elapsed_ms, e2e_ms = float(vals[0]), float(vals[1])
-    hours, cells, frames, windows, n_files, n_done, launches_all, h2d, d2h = (float(x) for x in sums)
+    out = dict(zip(("hours", "cells", "frames", "windows", "files", "files_done", "launches", "h2d", "d2h"),
+                   (float(x) for x in sums)))
+    out.update(elapsed_ms=float(vals[0]), e2e_ms=float(vals[1]), iterations_max=int(vals[2]),
+               files_per_rank_max=int(vals[3]), steps=steps, warm=warm, capacity=sweep.capacity,
+               iterations_rank0=st["steps"], clocks=sampler.result(), gathered=gathered,
+               longest_file_minutes=float(max(minutes)))
+    del sweep, corpus, files
+    torch.cuda.empty_cache()
+    return out
+
+
+def c5_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps = min(args.steps, 10)
+    warm = max(min(args.warmup, 3), 3)
+    m = c5_measure(args.hours, world, rank, dev, steps, warm, groups=args.groups, use_graphs=not args.no_graphs,
+                   capacity=[int(x) for x in args.capacity.split(',')] if args.capacity else None)
     if rank == 0:
         peak, peak_src = peaks()
-        ms_per_step = elapsed_ms / steps
-        alg_bytes = frames * 32 * 4 + 2 * cells / 8  # emission panel rows + 1-bit backpointers written and read
+        ms_per_step = m["elapsed_ms"] / steps
+        alg_bytes = m["frames"] * 32 * 4 + 2 * m["cells"] / 8  # emission panel rows + 1-bit backpointers written and read
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         legs = c5_cpu_leg(budget_s=20.0)
         best = legs["oracle_port"]
         line = {
-            "metric": "aligned_audio_hours_per_s", "value": hours / (ms_per_step * 1e-3), "unit": "audio-h/s",
+            "metric": "aligned_audio_hours_per_s", "value": m["hours"] / (ms_per_step * 1e-3), "unit": "audio-h/s",
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": C5_TEXT.format(h=args.hours), "kernel": "sweep",
-                       "l2": f"corpus emissions {h2d / 1e6:.0f} MB over all ranks, every window read once per sweep",
-                       "sharding": "files sharded by duration (LPT), no collective on the data path",
-                       "files": int(n_files), "files_done": int(n_done), "hours": hours,
-                       "iterations_rank0": st["steps"], "windows": int(windows),
-                       "capacity_T_C_K_rank0": sweep.capacity, "groups_per_gpu": args.groups, "cuda_graphs": not args.no_graphs, "V": 32},
-            "cells_per_s": cells / (ms_per_step * 1e-3),
+            "config": {"workload": C5_TEXT.format(h=args.hours), "kernel": "sweep"},
+            "run": {"l2": f"corpus emissions {m['h2d'] / 1e6:.0f} MB over all ranks, every window read once per sweep",
+                    "sharding": "files sharded by duration (LPT), no collective on the data path",
+                    "files": int(m["files"]), "files_done": int(m["files_done"]), "hours": m["hours"],
+                    "iterations_rank0": m["iterations_rank0"], "iterations_max": m["iterations_max"],
+                    "windows": int(m["windows"]), "capacity_T_C_K_rank0": m["capacity"],
+                    "groups_per_gpu": args.groups, "cuda_graphs": not args.no_graphs, "V": 32},
+            "cells_per_s": m["cells"] / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
-                         "kernels_per_step": launches_all / max(steps, 1) / world,
-                         "note": "lock-step iterations of T-serial kernels over <= files-in-flight windows: "
-                                 "latency bound, see DESIGN.md 5.6"},
+                         "kernels_per_step": m["launches"] / max(steps, 1) / world,
+                         "note": "lock-step iterations of T-serial kernels over <= files-in-flight windows; a window "
+                                 "lives on one SM, whose issue rate bounds the iteration: see DESIGN.md 5.6"},
             "cpu_baseline": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "cores": legs["cores"],
                              "kind": "port",
                              "sample": f"{best['files']} files of {best['minutes_per_file']:g} min, one per core, "
                                        "through oracle/sweep.py (C table fill + interpreted backtrace/loop)",
                              "oracle_port": best},
-            "e2e": {"value": hours / (e2e_ms * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "api": "ipfa_sweep_step_device"},
-            "gpu_launches": int(launches_all), "clocks": sampler.result(),
+            "e2e": {"value": m["hours"] / (m["e2e_ms"] * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": int(m["h2d"]),
+                    "d2h_bytes_per_step": int(m["d2h"]), "ms_per_step": m["e2e_ms"], "api": "ipfa_sweep_step_device"},
+            "gpu_launches": int(m["launches"]), "clocks": m["clocks"],
         }
         if world > 1:
-            line["final_gather"] = {"files": int(sum(len(g) for g in gathered)), "backend": "nccl"}
+            line["final_gather"] = {"files": int(sum(len(g) for g in m["gathered"])), "backend": "nccl"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def config_obj(wl):
+    """The `config` of a line: the workload and its shape, the same object in both arms."""
+    return dict({"workload": wl.text, "kernel": wl.kind}, **wl.shape)
 
 
 # ----------------------------------------------------------------------------- CPU legs
@@ -592,7 +618,7 @@ def reference_arm(args):
         "unit": "audio-h/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": best["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.text, "kernel": wl.kind},
+        "config": config_obj(wl),
         "cells_per_s": best["cells_per_s"], "cpu_baseline": cpu_baseline_obj(legs, what),
         "e2e": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -603,37 +629,26 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def gpu_arm(args):
+def _timed(fn, n, barrier, torch):
+    """n calls of fn(i) between two CUDA events on the current stream; returns ms."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    last = None
+    for i in range(n):
+        last = fn(i)
+    ev[1].record()
+    barrier()
+    return ev[0].elapsed_time(ev[1]), last
+
+
+def measure_resident(wl, ipfa, dev, rank, steps, warm, barrier, use_graphs, sustain_s=0.0):
+    """Device-resident throughput of one workload on this rank: rotating input sets (> L2), optional CUDA
+    graphs, K timed steps, then (sustain_s > 0) the same loop for at least that long."""
     import torch
-    import torch.distributed as dist
-    import ipfa_b200 as ipfa
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    wl = WORKLOADS[args.workload]
-    # rotate over several distinct input sets so no step finds its emissions in the 126 MB L2
     n_sets = max(3, min(8, int(np.ceil(3 * 126e6 / wl.set_bytes)))) if wl.set_bytes < 2e9 else 1
-    sets = [wl.make(1000 * rank + s, device=dev) for s in range(n_sets)]
+    sets = [wl.make(1000 * rank + s_, device=dev) for s_ in range(n_sets)]
     cells, hours, alg_bytes = wl.units(sets[0])
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # Window scoring is two short kernels per step: the step of every input set is captured once in
-    # a CUDA graph and replayed (no host launch gaps between the memset and the kernels);
-    # --no_graphs launches from the host instead.
-    use_graphs = wl.kind == "alpha" and not args.no_graphs
     graphs, graph_outs, launches_per_step = [], [], 0
     if use_graphs:
         side = torch.cuda.Stream()
@@ -656,26 +671,125 @@ def gpu_arm(args):
             return graph_outs[i % n_sets]
         return wl.step(ipfa, sets[i % n_sets])
 
-    warm = max(args.warmup, 3)
     for i in range(warm):
         do_step(i)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     launches0 = ipfa.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    barrier()
-    ev[0].record()
-    last = None
-    for i in range(args.steps):
-        last = do_step(i)
-    ev[1].record()
-    barrier()
-    elapsed_ms = ev[0].elapsed_time(ev[1])
-    # kernels executed in the timed region (a graph replay executes the kernels its capture launched)
-    launches = launches_per_step * args.steps if use_graphs else ipfa.launch_count() - launches0
+    elapsed_ms, last = _timed(do_step, steps, barrier, torch)
+    launches = launches_per_step * steps if use_graphs else ipfa.launch_count() - launches0
+    sustained = None
+    if sustain_s > 0:
+        n_sus = int(max(steps, min(2_000_000, sustain_s * 1e3 / max(elapsed_ms / steps, 1e-4))))
+        sus_ms, _ = _timed(do_step, n_sus, barrier, torch)
+        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus}
     sampler.stop_flag = True
     sampler.join()
+    # the dominant kernel alone, CUDA events on the launching stream around its launch (no graph)
+    torch.cuda.synchronize()
+    k = [0]
+
+    def one_plain():
+        k[0] += 1
+        wl.step(ipfa, sets[k[0] % n_sets])
+    kernel_ms = ipfa.ops.dominant_kernel_ms(one_plain, repeats=6)
+    return {"sets": sets, "n_sets": n_sets, "cells": cells, "hours": hours, "alg_bytes": alg_bytes,
+            "elapsed_ms": elapsed_ms, "steps": steps, "launches": launches, "last": last, "clocks": sampler.result(),
+            "sustained": sustained, "kernel_ms": kernel_ms, "use_graphs": use_graphs}
+
+
+def gpu_comparators(wl, sets, torch, budget_windows=64):
+    """The kernels this image already has for the same jobs, on the same
+    inputs: ATen's CUDA ctc_loss (whole batch, [T, N, C]) for the window scorer, torchaudio's CUDA
+    forced_align (one launch per frame, batch size 1: a sample of the windows) for Viterbi."""
+    lp, tg, il, tl = sets[0]
+    out = {}
+    try:
+        if wl.kind == "alpha":
+            n = lp.shape[0] if wl.set_bytes < 1e9 else min(lp.shape[0], budget_windows)
+            x = lp[:n].transpose(0, 1).contiguous()
+            tgt, a, b = tg[:n].long(), il[:n].long(), tl[:n].long()
+            fn = lambda: torch.nn.functional.ctc_loss(x, tgt, a, b, blank=0, reduction="none")
+            units = float(il[:n].sum()) * FRAME_SECONDS / 3600.0
+            name = "torch.nn.functional.ctc_loss (CUDA, reduction='none')"
+        else:
+            import torchaudio.functional as AF
+            n = min(lp.shape[0], budget_windows)
+            items = [(lp[i:i + 1, :int(il[i])].contiguous(), tg[i:i + 1, :int(tl[i])].long()) for i in range(n)]
+
+            def fn():
+                for e, t_ in items:
+                    AF.forced_align(e, t_, blank=0)
+            units = float(il[:n].sum()) * FRAME_SECONDS / 3600.0
+            name = "torchaudio.functional.forced_align (CUDA, one call per window)"
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 5 if wl.kind == "alpha" else 2
+        ev[0].record()
+        for _ in range(reps):
+            fn()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        out = {"name": name, "windows": int(n), "ms": ms, "audio_h_per_s": units / (ms * 1e-3)}
+    except Exception as exc:  # noqa: BLE001  (a comparator that does not run is reported, not fatal)
+        out = {"error": repr(exc)[:200]}
+    return out
+
+
+def raw_copy_ceiling(nbytes, barrier, torch, seconds=0.25):
+    """What the link gives this rank while every rank copies at once: one pinned buffer of the step's
+    size, cudaMemcpyAsync host-to-device in a loop (the e2e step cannot be faster than this)."""
+    host = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+    devb = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        devb.copy_(host, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        devb.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        n += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return nbytes * n / dt / 1e9
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import ipfa_b200 as ipfa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # Window scoring is a memset and two or three short kernels per step: the step of every input set
+    # is captured once in a CUDA graph and replayed (no host launch gaps); --no_graphs launches from the host.
+    use_graphs = wl.kind == "alpha" and not args.no_graphs
+    warm = max(args.warmup, 3)
+    m = measure_resident(wl, ipfa, dev, rank, args.steps, warm, barrier, use_graphs, sustain_s=args.sustain)
+    sets, n_sets, cells, hours, alg_bytes = m["sets"], m["n_sets"], m["cells"], m["hours"], m["alg_bytes"]
+    elapsed_ms, launches, last = m["elapsed_ms"], m["launches"], m["last"]
 
     # the only collective of the job: one gather of the per-window results (not timed)
     gathered = None
@@ -687,7 +801,7 @@ def gpu_arm(args):
         gathered = [int(full.shape[0]), bool(torch.isfinite(full).all())]
 
     # end-to-end through the host-buffer C ABI: pinned host buffers, H2D + D2H inside the timed region
-    host_sets = [wl.to_host(sets[s]) for s in range(min(n_sets, 2))]
+    host_sets = [wl.to_host(sets[s_]) for s_ in range(min(n_sets, 2))]
     e2e_steps = max(3, min(args.steps, 20))
     for i in range(3):
         wl.e2e_step(ipfa, *host_sets[i % len(host_sets)])
@@ -698,18 +812,48 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
     h2d, d2h = wl.traffic()
+    raw_gbs = raw_copy_ceiling(h2d, barrier, torch)
 
-    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    sus_ms = m["sustained"]["ms_per_step"] if m["sustained"] else 0.0
+    times = torch.tensor([elapsed_ms, e2e_ms, sus_ms, -raw_gbs], dtype=torch.float64, device=dev)
+    raw_sum = torch.tensor([raw_gbs], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+        dist.all_reduce(raw_sum, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, sus_ms, raw_min = float(times[0]), float(times[1]), float(times[2]), -float(times[3])
+
+    # BASELINE configs[4] on the same ranks (strong scaling of one corpus), and -- single GPU only -- short
+    # runs of the other configs; every rank enters c5_measure (it is collective)
+    extra = {}
+    if args.extras and args.workload == "c2":
+        del host_sets
+        c5 = c5_measure(args.hours, world, rank, dev, steps=2, warm=2, with_e2e=False)
+        ms5 = c5["elapsed_ms"] / c5["steps"]
+        extra["c5"] = {"workload": C5_TEXT.format(h=args.hours), "scaling": "strong", "ms_per_sweep": ms5,
+                       "audio_h_per_s": c5["hours"] / (ms5 * 1e-3), "files": int(c5["files"]),
+                       "files_per_rank_max": c5["files_per_rank_max"], "iterations_longest_chain": c5["iterations_max"],
+                       "longest_file_minutes": c5["longest_file_minutes"], "windows": int(c5["windows"]),
+                       "cells_per_s": c5["cells"] / (ms5 * 1e-3), "kernels_per_sweep": c5["launches"] / c5["steps"] / world}
+        if world == 1:
+            for name in ("c2v", "c3", "c4", "seg"):
+                w2 = WORKLOADS[name]
+                r2 = measure_resident(w2, ipfa, dev, rank, steps=5, warm=3, barrier=barrier, use_graphs=False)
+                ms2 = r2["elapsed_ms"] / r2["steps"]
+                extra[name] = {"workload": w2.text, "ms_per_step": ms2, "audio_h_per_s": r2["hours"] / (ms2 * 1e-3),
+                               "cells_per_s": r2["cells"] / (ms2 * 1e-3), "kernel_ms": r2["kernel_ms"],
+                               "roofline_frac": r2["alg_bytes"] / (ms2 * 1e-3) / 1e9 / peaks()[0],
+                               "algorithmic_bytes_per_step": r2["alg_bytes"]}
+                if w2.kind in ("alpha", "viterbi"):
+                    extra[name]["gpu_comparator"] = gpu_comparators(w2, r2["sets"], torch)
+                del r2
+                torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = peaks()
         ms_per_step = elapsed_ms / args.steps
-        # launches are issued ahead of execution (the GPU never idles inside the timed region), so
-        # the step's kernels average ms_per_step of device time per step
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        kernel_ms = m["kernel_ms"] if m["kernel_ms"] else ms_per_step
+        # roofline of the dominant kernel: its algorithmic bytes over its own event-timed duration
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         legs = cpu_leg(wl, budget_s=12.0)
         lin = wl.kind == "alpha" and wl.v <= 64 and wl.l + 1 <= 256 and not os.environ.get("IPFA_ALPHA_LOG")
         bound_note = {"alpha": ("T-serial recursion walked from both ends, states kept as scaled fp64 probabilities "
@@ -718,12 +862,12 @@ def gpu_arm(args):
                                ("T-serial log-sum-exp recursion walked from both ends: MUFU bound (4 MUFU per state "
                                 "pair and frame), not HBM bound -- DESIGN.md 5.1"),
                       "viterbi": "T-serial max-plus recursion + latency-bound backtrace: issue bound -- DESIGN.md 5.2",
-                      "seg": "T-serial max-plus recursion with a CTA barrier per frame -- DESIGN.md 5.3"}[wl.kind]
+                      "seg": "T-serial max-plus recursion, issue bound (13-15 instructions per cell) -- DESIGN.md 5.3"}[wl.kind]
         extra_roof = {}
         if wl.kind == "alpha" and wl.v <= 64:
             il = sets[0][2].cpu().numpy().astype(np.int64)
             tl = sets[0][3].cpu().numpy().astype(np.int64)
-            clk = (sampler.result().get("sm_mhz") or 1965.0) * 1e6
+            clk = (m["clocks"].get("sm_mhz") or 1965.0) * 1e6
             if lin:
                 # the pipes that bound the linear-domain instance: per frame and warp of
                 # 32 lanes x P pairs, 3P + 1 FP64 warp-instructions (2 cycles each per SM sub-partition,
@@ -734,36 +878,52 @@ def gpu_arm(args):
                 fp64_ms = frames * (3 * per_lane + 1) * 2 / (148 * 4) / clk * 1e3
                 issue_ms = frames * (9 * per_lane + 1) / (148 * 4) / clk * 1e3
                 extra_roof = {"fp64_pipe_floor_ms": fp64_ms, "issue_floor_ms": issue_ms,
-                              "frac_of_issue_floor": issue_ms / ms_per_step}
+                              "frac_of_issue_floor": issue_ms / kernel_ms}
             else:
-                # the bound that actually binds the log-domain instance: 4 MUFU
-                # warp-instructions per 32 state pairs and frame, 8 cycles each per SM sub-partition
-                # (profiles/microbench_r01.txt)
                 pair_warps = np.ceil((tl + 1) / 32.0)
                 mufu_cycles = float((il * pair_warps).sum()) * 4 * 8
                 floor_ms = mufu_cycles / (148 * 4) / clk * 1e3
-                extra_roof = {"mufu_floor_ms": floor_ms, "frac_of_mufu_floor": floor_ms / ms_per_step}
+                extra_roof = {"mufu_floor_ms": floor_ms, "frac_of_mufu_floor": floor_ms / kernel_ms}
         line = {
             "metric": "aligned_audio_hours_per_s", "value": world * hours / (ms_per_step * 1e-3),
             "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if lin else "f32", "data": "synthetic",
-            "config": dict({"workload": wl.text, "kernel": wl.kind,
-                            "l2": f"{n_sets} rotating input sets of {wl.set_bytes / 1e6:.0f} MB per GPU (> 126 MB L2)",
-                            "sharding": "independent windows per rank, no collective on the data path",
-                            "cuda_graphs": use_graphs}, **wl.shape),
+            "config": config_obj(wl),
+            "run": {"l2": f"{n_sets} rotating input sets of {wl.set_bytes / 1e6:.0f} MB per GPU (> 126 MB L2)",
+                    "sharding": "independent windows per rank, no collective on the data path",
+                    "cuda_graphs": use_graphs},
             "cells_per_s": world * cells / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(args.workload),
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                         "kernel_ms_how": ("CUDA events on the launching stream around the step's longest kernel, "
+                                           "mean of 6 launches outside the graph") if m["kernel_ms"] else "step time",
+                         "step_ms": ms_per_step, "kernel_share_of_step": kernel_ms / ms_per_step,
                          "kernels_per_step": launches / max(args.steps, 1), "note": bound_note, **extra_roof},
             "cpu_baseline": cpu_baseline_obj(legs, "same shapes, same generator"),
             "e2e": {"value": world * hours / (e2e_ms * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": wl.api},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": wl.api,
+                    "raw_h2d_copy_gbs": {"sum_over_ranks": float(raw_sum[0]), "slowest_rank": raw_min,
+                                         "how": "every rank copies one pinned buffer of h2d_bytes_per_step to its "
+                                                "GPU in a loop at the same time (cudaMemcpyAsync); the e2e step "
+                                                "moves the same bytes, so it cannot beat this"},
+                    "link_share": (h2d / (e2e_ms * 1e-3) / 1e9) / max(raw_min, 1e-9)},
             "gpu_launches": int(launches),
-            "clocks": sampler.result(),
+            "clocks": m["clocks"],
         }
+        if m["sustained"]:
+            line["sustained"] = {"value": world * hours / (sus_ms * 1e-3), "unit": "audio-h/s", "ms_per_step": sus_ms,
+                                 "steps": m["sustained"]["steps"], "seconds": m["sustained"]["seconds"],
+                                 "note": "same loop run for >= --sustain seconds right after the K timed steps; "
+                                         "`value` is the K-step (burst) figure, the clocks were sampled over both"}
+        if wl.kind in ("alpha", "viterbi"):
+            line["gpu_comparator"] = gpu_comparators(wl, sets, torch)
+            if "audio_h_per_s" in line["gpu_comparator"]:
+                line["gpu_comparator"]["ours_over_it"] = (hours / (ms_per_step * 1e-3)) / line["gpu_comparator"]["audio_h_per_s"]
+        if extra:
+            line["extra"] = extra
         if gathered is not None:
             line["final_gather"] = {"rows": gathered[0], "finite": gathered[1], "backend": "nccl"}
         print(json.dumps(line))
@@ -783,6 +943,9 @@ def main():
     ap.add_argument("--no_graphs", action="store_true", help="c5: launch every kernel from the host (no CUDA graph)")
     ap.add_argument("--groups", type=int, default=32, help="c5: independent file groups (streams) per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sustain", type=float, default=1.0, help="seconds of the sustained run after the K timed steps (0: none)")
+    ap.add_argument("--no_extras", dest="extras", action="store_false",
+                    help="c2 only: skip the extra.c5 / c2v / c3 / c4 / seg sub-results")
     args = ap.parse_args()
     if args.workload == "c5":
         return c5_reference_arm(args) if args.impl == "reference" else c5_arm(args)

@@ -61,6 +61,13 @@ const char *ipfa_last_cuda_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t ipfa_launch_count(void);
 int ipfa_device_count(void);
+/* Measurement aid (bench.py's roofline): with enable != 0 every launch of a lattice kernel (window
+ * scorer, Viterbi fill, segmentation fill) is bracketed by CUDA events on the launching stream, except
+ * while a graph is being captured; ipfa_profile_read_ms() waits for them and returns the longest bracket
+ * since the last read (the dominant kernel's own duration, in ms; < 0 when none was taken).  Not
+ * thread-safe; leave it off outside measurements. */
+void ipfa_profile_kernels(int enable);
+float ipfa_profile_read_ms(void);
 /* The IPFA_* tuning switches (kernel-instance overrides used by tools/ and the tests) are read from
  * the environment once per process, not inside compute calls; this reads them again. */
 void ipfa_tuning_reload(void);
@@ -75,13 +82,15 @@ void ipfa_tuning_reload(void);
  *   in_len    [N] int32 frames per window, tgt_len [N] int32 labels per window
  *   nll_out   [N] fp32: -log p(target | window); +inf when infeasible
  *   workspace caller-owned scratch of ipfa_ctc_alpha_workspace_bytes() bytes; its first
- *             N + 2 int32 words end a call as: [0, N) arrival counters, [N] number
+ *             N + 4 int32 words end a call as: [0, N) arrival counters, [N] number
  *             of windows the linear-domain (fp64) instance handed to the log-domain
  *             instance, [N + 1] OR of the reasons (1 target names the blank, 2 emission
  *             ratio outside fp32, 4 reachable state too small, 8 state too large,
- *             16 / 32 scale step / neighbouring scales too far apart).  Diagnostic
+ *             16 / 32 scale step / neighbouring scales too far apart), [N + 2] / [N + 3]
+ *             the same two words for the optional fp32 tier in front of it.  Diagnostic
  *             only: results are the same either way (csrc/ctc_alpha.cu).
- * Environment: IPFA_ALPHA_LOG=1 scores with the log-domain instance alone.
+ * Environment (read once per process): IPFA_ALPHA_LOG=1 scores with the log-domain instance alone;
+ * IPFA_ALPHA_F32=1 puts the fp32 linear-domain tier in front (csrc/ctc_alpha_f32.cuh).
  * ------------------------------------------------------------------------- */
 size_t ipfa_ctc_alpha_workspace_bytes(int N, int Tmax, int Lmax, int V);
 int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,

@@ -24,6 +24,8 @@ _SIGNATURES = {
     "ipfa_launch_count": (ctypes.c_uint64, []),
     "ipfa_device_count": (c_i, []),
     "ipfa_tuning_reload": (None, []),
+    "ipfa_profile_kernels": (None, [c_i]),
+    "ipfa_profile_read_ms": (ctypes.c_float, []),
     "ipfa_ctc_alpha_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "ipfa_ctc_alpha_device": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
                                     c_i, c_i, c_i, c_i, c_i, c_void, c_void, c_sz, c_void]),

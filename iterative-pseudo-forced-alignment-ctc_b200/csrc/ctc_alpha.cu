@@ -767,7 +767,9 @@ static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
     }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
     const int blocks = (prm.halves * prm.N + GROUPS - 1) / GROUPS;
+    const int prof_slot = profile_begin(stream);
     kern<<<blocks, threads, smem, stream>>>(prm);
+    profile_end(prof_slot, stream);
     ++g_launch_count;
     e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
@@ -826,7 +828,9 @@ static int launch_alpha_f32_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
         if (dev_id >= 0 && dev_id < 16) smem_set[dev_id] = smem;
     }
     const int blocks = (prm.halves * prm.N + 3) / 4;
+    const int prof_slot = profile_begin(stream);
     kern<<<blocks, 128, smem, stream>>>(prm);
+    profile_end(prof_slot, stream);
     ++g_launch_count;
     e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }

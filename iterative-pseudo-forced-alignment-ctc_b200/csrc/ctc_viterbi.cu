@@ -485,7 +485,9 @@ static int launch_fill_p(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     const int threads = (WARPS == 1) ? 128 : 32 * WARPS;
     const int blocks = (prm.N + GROUPS - 1) / GROUPS;
+    const int prof_slot = profile_begin(stream);
     kern<<<blocks, threads, smem, stream>>>(prm);
+    profile_end(prof_slot, stream);
     ++g_launch_count;
     e = cudaGetLastError();
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }

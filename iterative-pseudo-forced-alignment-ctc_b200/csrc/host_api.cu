@@ -45,6 +45,36 @@ const char *tuning(const char *name) {
     return nullptr;
 }
 
+// ---- per-kernel timing for bench.py's roofline: when switched on, the launch sites of the T-serial
+// lattice kernels bracket each launch with CUDA events on the launching stream (not while a graph is
+// being captured); ipfa_profile_read_ms() returns the longest bracket since the last read -- the
+// step's dominant kernel, timed alone instead of inferred from the step.
+namespace {
+constexpr int kProfileSlots = 16;
+struct ProfileState {
+    bool on = false;
+    int used = 0;
+    cudaEvent_t e0[kProfileSlots] = {}, e1[kProfileSlots] = {};
+};
+ProfileState g_profile;
+}  // namespace
+
+int profile_begin(cudaStream_t st) {
+    if (!g_profile.on || g_profile.used >= kProfileSlots) return -1;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return -1;
+    const int i = g_profile.used;
+    if (!g_profile.e0[i]) {
+        if (cudaEventCreate(&g_profile.e0[i]) != cudaSuccess || cudaEventCreate(&g_profile.e1[i]) != cudaSuccess) return -1;
+    }
+    if (cudaEventRecord(g_profile.e0[i], st) != cudaSuccess) return -1;
+    ++g_profile.used;
+    return i;
+}
+void profile_end(int slot, cudaStream_t st) {
+    if (slot >= 0) cudaEventRecord(g_profile.e1[slot], st);
+}
+
 namespace {
 constexpr int kMaxChunks = 32;
 constexpr int kMaxDevices = 64;
@@ -168,6 +198,22 @@ extern "C" const char *ipfa_status_string(int status) {
         case IPFA_ERR_WINDOW: return "Maximum window size reached. Check data for large repetitions or noise.";
         default: return "unknown status";
     }
+}
+
+extern "C" void ipfa_profile_kernels(int enable) {
+    g_profile.on = enable != 0;
+    g_profile.used = 0;
+}
+extern "C" float ipfa_profile_read_ms(void) {
+    float best = -1.0f;
+    for (int i = 0; i < g_profile.used; ++i) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(g_profile.e1[i]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, g_profile.e0[i], g_profile.e1[i]) == cudaSuccess && ms > best)
+            best = ms;
+    }
+    g_profile.used = 0;
+    return best;
 }
 
 extern "C" void ipfa_tuning_reload(void) {

@@ -11,6 +11,10 @@ namespace ipfa {
 // process (host_api.cu; ipfa_tuning_reload() reads it again), never inside a compute call.
 const char *tuning(const char *name);
 
+// bench.py's per-kernel timing (host_api.cu): event brackets around a launch, no-ops unless switched on
+int profile_begin(cudaStream_t st);
+void profile_end(int slot, cudaStream_t st);
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 // Finite stand-in for log(0) in the log-sum-exp recursion: differences of two

@@ -376,3 +376,21 @@ def tuning(**switches):
             else:
                 os.environ[k] = v
         lib().ipfa_tuning_reload()
+
+
+def dominant_kernel_ms(fn, repeats=5):
+    """Mean duration (ms) of the longest lattice kernel `fn()` launches, timed alone with CUDA events on
+    the launching stream (``ipfa_profile_kernels``); None when `fn` launched none outside a graph."""
+    L = lib()
+    total, n = 0.0, 0
+    try:
+        for _ in range(repeats):
+            L.ipfa_profile_kernels(1)
+            fn()
+            ms = float(L.ipfa_profile_read_ms())
+            if ms >= 0:
+                total += ms
+                n += 1
+    finally:
+        L.ipfa_profile_kernels(0)
+    return total / n if n else None

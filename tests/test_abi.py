@@ -73,11 +73,11 @@ def test_invalid_arguments_are_rejected(libmod):
 
 
 def test_alpha_workspace_holds_its_documented_parts(libmod):
-    """include/ipfa_b200.h: N + 2 counter words, the two halves' state vectors of every window
-    ([N][2][2][Lmax + 1] fp32), the two length-bucket lists and the redo list ([3][N] int32)."""
+    """include/ipfa_b200.h: N + 4 counter words, the two halves' state vectors of every window
+    ([N][2][2][Lmax + 1] fp32), the two length-bucket lists and the two tiers' redo lists ([4][N] int32)."""
     L = libmod.lib()
     for n, lmax in ((1, 0), (7, 1), (1024, 100), (4300, 40), (65536, 40)):
-        need = (n + 2) * 4 + n * 4 * (lmax + 1) * 4 + 3 * n * 4
+        need = (n + 4) * 4 + n * 4 * (lmax + 1) * 4 + 4 * n * 4
         got = L.ipfa_ctc_alpha_workspace_bytes(n, 1000, lmax, 32)
         assert need <= got <= need + 8 * 256, (n, lmax, got, need)
     # monotone in N (the host entry point sizes one workspace for all its chunks)
