@@ -68,6 +68,7 @@ extern "C" int ipfa_anchor_select_device(const double *seg, const int32_t *n_utt
     if (N == 0) return IPFA_OK;
     if (!seg || !n_utts || !text_len || !is_last || !decision_out || !anchor_out || N < 0 || Kmax <= 0)
         return IPFA_ERR_INVALID_ARG;
+    NvtxRange range("ipfa.anchor_select");
     const int threads = 128;
     anchor_select_kernel<<<(N + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         seg, n_utts, text_len, is_last, N, Kmax, threshold, short_len, decision_out, anchor_out);

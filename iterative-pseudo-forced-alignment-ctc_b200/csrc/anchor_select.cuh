@@ -51,7 +51,7 @@ __device__ __forceinline__ AnchorDecision anchor_select_one(const double *__rest
         double score = 0.0;
         for (int u = 0; u < k; ++u) {  // :221-260
             score = score_of(k, u);
-            if (score < threshold) {
+            if (!(score >= threshold)) {  // (a NaN score -- a prefix that was not aligned -- is never an anchor)
                 bad = true;
             } else {
                 bad = false;

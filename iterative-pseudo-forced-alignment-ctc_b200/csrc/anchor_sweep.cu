@@ -343,6 +343,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
     const ipfa_sweep_params p = *params;
     // the window of every file for the first iteration (idempotent: the tail of the previous call
     // already built it from the same state)
+    NvtxRange range("ipfa.sweep_step (build + n x {segmentation, tail})");
     sweep_build_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax);
     ++g_launch_count;
     for (int i = 0; i < n_steps; ++i) {
@@ -351,6 +352,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
                             p.seg_flags | IPFA_SEG_ALL_PREFIXES, w.seg, w.term_t, nullptr, nullptr, nullptr,
                             w.win_status, w.seg_ws, w.seg_ws_bytes, stream);
         if (rc) return rc;
+        NvtxRange range_tail("ipfa.sweep.tail (select + rows + next window)");
         sweep_tail_kernel<<<F, kBuildThreads, 0, st>>>(c, p, s, w, Tmax, Cmax, Kmax, out_seg, out_info);
         ++g_launch_count;
     }

@@ -885,6 +885,7 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
                                      int Lmax, int V, int blank, float *nll_out, void *workspace,
                                      size_t workspace_bytes, void *stream) {
     (void)Tmax;
+    NvtxRange range("ipfa.ctc_alpha (window scorer: tiers + redo lists)");
     if (N == 0) return IPFA_OK;
     if (!lp || !in_len || !tgt_len || !nll_out || N < 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V ||
         (Lmax > 0 && !targets))

@@ -601,11 +601,17 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
                           pick_lattice_shape(small_units, N, &s_small, "IPFA_VITERBI_SMALL_SHAPE", dense ? 3 : 6) &&
                           32 * s_small.WARPS * s_small.PER == small_units;
     if (!bucketed) {
-        int rc = dense ? dispatch_fill<true>(fp, Lmax, s, st) : dispatch_fill<false>(fp, Lmax, s, st);
+        int rc;
+        {
+            NvtxRange range("ipfa.viterbi.fill");
+            rc = dense ? dispatch_fill<true>(fp, Lmax, s, st) : dispatch_fill<false>(fp, Lmax, s, st);
+        }
         if (rc) return rc;
         bt.NT = 32 * s.WARPS;
+        NvtxRange range("ipfa.viterbi.backtrace");
         return launch_backtrace(bt, s.PER, st);
     }
+    NvtxRange range_b("ipfa.viterbi.length_buckets(fill+backtrace x2)");
     cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st);
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     length_bucket_kernel<<<(N + 255) / 256, 256, 0, st>>>(tgt_len, N, small_units, order, count);

@@ -689,6 +689,12 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_windowed_fill_kernel(const
     const int kslot = (PP > 1) ? prob - w * PP : max(0, min(prm.n_utts[w], prm.Kmax)) - 1;
     const int K = max(0, min(prm.n_utts[w], prm.Kmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+    // The window's status word is initialised HERE, by the fill of its first problem: the backtrace
+    // launch that follows only ORs IPFA_WIN_WINDOW_TOO_SMALL into it (a store there could overwrite the
+    // bit another prefix of the same window had already set).
+    if ((PP == 1 || kslot == 0) && threadIdx.x == 0)
+        prm.status_out[w] = (max(0, min(prm.n_cols[w], prm.Cmax)) > min(prm.in_len[w], prm.Tmax)) ? IPFA_WIN_TEXT_LONGER
+                                                                                                   : IPFA_WIN_OK;
     if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int T = min(prm.in_len[w], prm.Tmax);
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
@@ -844,7 +850,7 @@ __global__ void __launch_bounds__(128) ctcseg_windowed_backtrace_kernel(const Se
     const int T = min(prm.in_len[w], prm.Tmax);
     const int NCw = max(0, min(prm.n_cols[w], prm.Cmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
-    if ((PP == 1 || kslot == 0) && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    // (status_out[w] was initialised by the fill kernel; this launch only ORs into it)
     if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
@@ -945,6 +951,12 @@ __global__ void __launch_bounds__(kWinThreads) ctcseg_multi_fill_kernel(const Se
     const int kslot = (PP > 1) ? prob - w * PP : max(0, min(prm.n_utts[w], prm.Kmax)) - 1;
     const int K = max(0, min(prm.n_utts[w], prm.Kmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
+    // The window's status word is initialised HERE, by the fill of its first problem: the backtrace
+    // launch that follows only ORs IPFA_WIN_WINDOW_TOO_SMALL into it (a store there could overwrite the
+    // bit another prefix of the same window had already set).
+    if ((PP == 1 || kslot == 0) && threadIdx.x == 0)
+        prm.status_out[w] = (max(0, min(prm.n_cols[w], prm.Cmax)) > min(prm.in_len[w], prm.Tmax)) ? IPFA_WIN_TEXT_LONGER
+                                                                                                   : IPFA_WIN_OK;
     if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int T = min(prm.in_len[w], prm.Tmax);
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
@@ -1102,7 +1114,7 @@ __global__ void __launch_bounds__(128) ctcseg_multi_backtrace_kernel(const SegMu
     const int T = min(prm.in_len[w], prm.Tmax);
     const int NCw = max(0, min(prm.n_cols[w], prm.Cmax));
     const bool all_prefixes = prm.flags & IPFA_SEG_ALL_PREFIXES;
-    if ((PP == 1 || kslot == 0) && lane == 0) prm.status_out[w] = (NCw > T) ? IPFA_WIN_TEXT_LONGER : IPFA_WIN_OK;
+    // (status_out[w] was initialised by the fill kernel; this launch only ORs into it)
     if (kslot < 0 || kslot >= K || (!all_prefixes && kslot != K - 1)) return;
     const int32_t *ub = prm.utt_begin + (int64_t)w * (prm.Kmax + 1);
     const int32_t *gt = prm.gt + (int64_t)w * prm.gt_stride;
@@ -1344,9 +1356,13 @@ int ctcseg_run(const float *lp, const int64_t *win_off, int64_t stride_n, int64_
     fp.N = N; fp.Tmax = Tmax; fp.Cmax = Cmax; fp.V = V; fp.blank = blank; fp.flags = flags;
     fp.bp = bp; fp.words_per_window = wpw; fp.colarg = colarg;
     int rc = IPFA_OK;
-    if (!(use_dense_panel(V, Cmax) && try_seg_fill_cluster(fp, s, st, &rc)))
-        rc = use_dense_panel(V, Cmax) ? dispatch_seg_fill<true>(fp, s, st) : dispatch_seg_fill<false>(fp, s, st);
+    {
+        NvtxRange range("ipfa.ctcseg.fill");
+        if (!(use_dense_panel(V, Cmax) && try_seg_fill_cluster(fp, s, st, &rc)))
+            rc = use_dense_panel(V, Cmax) ? dispatch_seg_fill<true>(fp, s, st) : dispatch_seg_fill<false>(fp, s, st);
+    }
     if (rc) return rc;
+    NvtxRange range_bt("ipfa.ctcseg.backtrace+segments");
 
     SegBackParams bk{};
     bk.lp = lp; bk.win_off = win_off; bk.stride_n = stride_n; bk.stride_t = stride_t; bk.in_len = in_len;

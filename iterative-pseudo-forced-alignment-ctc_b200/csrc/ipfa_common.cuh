@@ -1,6 +1,7 @@
 // ipfa_common.cuh -- shared device helpers for the sm_100a alignment kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include "../../include/ipfa_b200.h"
@@ -10,6 +11,15 @@ namespace ipfa {
 // Value of an IPFA_* tuning switch, or nullptr when it is not set.  The environment is read once per
 // process (host_api.cu; ipfa_tuning_reload() reads it again), never inside a compute call.
 const char *tuning(const char *name);
+
+// NVTX range over the launches of one phase (fill / backtrace / select ...): what a timeline tool
+// groups the kernels by; a push / pop pair costs nothing measurable when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // bench.py's per-kernel timing (host_api.cu): event brackets around a launch, no-ops unless switched on
 int profile_begin(cudaStream_t st);
