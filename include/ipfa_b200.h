@@ -105,8 +105,9 @@ int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t stride_t,
                         int N, int Tmax, int Lmax, int V, int blank, float *nll_out);
 
 /* ------------------------------------------------------------------------- *
- * Kernel (2a): CTC Viterbi forced alignment on the 2L+1 lattice with 2-bit
- * packed backpointers in HBM, then a warp-parallel backtrace that also emits
+ * Kernel (2a): CTC Viterbi forced alignment on the 2L+1 lattice with backpointers
+ * as bit planes in HBM (3 words per state pair and 32-frame block: 1.5 bits per
+ * state and frame), then a warp-parallel backtrace that also emits
  * per-frame scores and per-token spans/confidences.  Replaces
  * torchaudio.functional.forced_align + merge_tokens.
  *   paths_out   [N, Tmax] int32 token id per frame (-1 beyond in_len / on error)

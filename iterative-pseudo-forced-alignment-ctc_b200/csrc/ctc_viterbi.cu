@@ -1,6 +1,6 @@
 // ctc_viterbi.cu -- kernel (2a): CTC Viterbi forced alignment on the 2L+1
-// lattice with 2-bit packed backpointers in HBM + warp-parallel backtrace with
-// per-frame scores and per-token spans / confidences.
+// lattice with backpointer bit planes in HBM (1.5 bits per state and frame) + warp-parallel
+// backtrace with per-frame scores and per-token spans / confidences.
 //
 // Replaces torchaudio.functional.forced_align (torchaudio/csrc/forced_align/cpu/
 // compute.cpp::forced_align_impl; Python surface functional/_alignment.py:11-73)
@@ -12,12 +12,12 @@
 //
 // Fill: same pair-per-thread register layout as ctc_alpha.cu (max-plus instead
 // of log-sum-exp; fp32 single-rounding adds so scores are bit-identical to the
-// CPU).  Every thread packs its 2P states x 2 bits per frame into 32-bit words
-// (8/P frames per word) and stores them lane-contiguous: bp[w][t / SPW][thread],
-// i.e. exactly 2 bits per (padded) lattice cell, written once, coalesced.
-// Backtrace: one warp per window; per 32-frame block the warp fetches the
-// 4P words x (8/P) thread-columns it can possibly touch with ONE coalesced
-// load, then walks the block through warp shuffles.
+// CPU).  Backpointers are bit PLANES: per state and 32-frame block one word whose bit f says
+// "entered from a lower state at frame f" (blank: from the label below; label: from its blank,
+// and a second plane for the skip transition) -- 3 words per state pair and block, stored
+// lane-contiguous, written once, coalesced.
+// Backtrace: one warp per window hops from move to move (find-leading-one on the planes of the
+// block, staged in shared memory one block ahead) instead of stepping frame by frame.
 #include "emission_pipe.cuh"
 #include "lattice_shapes.cuh"
 
