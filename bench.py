@@ -107,9 +107,10 @@ class ClockSampler(threading.Thread):
 class CtcWorkload:
     """kind 'alpha' (kernel 1) or 'viterbi' (kernel 2a) on the 2L+1 lattice."""
 
-    def __init__(self, name, kind, n, t, l, v, ragged, text):
+    def __init__(self, name, kind, n, t, l, v, ragged, text, vocab_major=False):
         self.name, self.kind, self.n, self.t, self.l, self.v, self.ragged, self.text = \
             name, kind, n, t, l, v, ragged, text
+        self.vocab_major = vocab_major  # emissions stored [N, V, T] (viewed as [N, T, V] with stride_v = T)
         self.api = "ipfa_ctc_alpha_host" if kind == "alpha" else "ipfa_ctc_viterbi_host"
         self.set_bytes = n * t * v * 4
         self.shape = {"windows_per_gpu": n, "T": t, "L": l, "V": v}
@@ -120,6 +121,8 @@ class CtcWorkload:
         dev = device or "cpu"
         g = torch.Generator(device=dev).manual_seed(seed)
         lp = torch.log_softmax(torch.randn(n, self.t, self.v, generator=g, device=dev), dim=-1)
+        if self.vocab_major:
+            lp = lp.transpose(1, 2).contiguous().transpose(1, 2)  # same values, vocabulary-major storage
         tg = torch.randint(1, self.v, (n, self.l), generator=g, device=dev, dtype=torch.int32)
         if self.ragged:
             il = torch.randint(self.t // 2, self.t + 1, (n,), generator=g, device=dev, dtype=torch.int32)
@@ -149,7 +152,8 @@ class CtcWorkload:
 
     def to_host(self, inputs):
         import torch
-        host = [x.cpu().pin_memory().numpy() for x in inputs]
+        # (the host-buffer entry point takes [N, T, V] rows; a vocabulary-major set is laid out that way for it)
+        host = [x.contiguous().cpu().pin_memory().numpy() for x in inputs]
         n, t = self.n, self.t
         if self.kind == "alpha":
             out = {"out": torch.empty(n, dtype=torch.float32).pin_memory().numpy()}
@@ -311,6 +315,10 @@ WORKLOADS = {
                       "BASELINE configs[2]: Viterbi forced align + backtrace, 65536 utterances, T<=500, L<=40, V=32"),
     "c4": CtcWorkload("c4", "alpha", 256, 3000, 400, 5000, False,
                       "BASELINE configs[3]: long-window large-vocab scoring, 256 windows x T=3000 x L=400, V=5000"),
+    "c4v": CtcWorkload("c4v", "alpha", 256, 3000, 400, 5000, False,
+                       "BASELINE configs[3] with vocabulary-major emissions ([N, V, T], stride_v = T): 256 windows x "
+                       "T=3000 x L=400, V=5000 -- the layout in which the window scorer reads only its own columns",
+                       vocab_major=True),
     "seg": SegWorkload("seg", 256, 3500, 6, 150, 32,
                        "BASELINE configs[4] unit: anchor-loop iteration for 256 files in flight, 70 s windows "
                        "(T=3500), 6 utterances x 150 chars, all prefixes + on-device selection, V=32"),
@@ -835,7 +843,7 @@ def gpu_arm(args):
                        "longest_file_minutes": c5["longest_file_minutes"], "windows": int(c5["windows"]),
                        "cells_per_s": c5["cells"] / (ms5 * 1e-3), "kernels_per_sweep": c5["launches"] / c5["steps"] / world}
         if world == 1:
-            for name in ("c2v", "c3", "c4", "seg"):
+            for name in ("c2v", "c3", "c4", "c4v", "seg"):
                 w2 = WORKLOADS[name]
                 r2 = measure_resident(w2, ipfa, dev, rank, steps=5, warm=3, barrier=barrier, use_graphs=False)
                 ms2 = r2["elapsed_ms"] / r2["steps"]

@@ -99,6 +99,18 @@ int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t stride_t,
                           int N, int Tmax, int Lmax, int V, int blank,
                           float *nll_out, void *workspace, size_t workspace_bytes,
                           void *stream);
+/* The same call for emissions whose VOCABULARY axis is not contiguous: element (n, t, v) lives at
+ * lp[n * stride_n + t * stride_t + v * stride_v].  With a vocabulary-major producer ([N, V, T]:
+ * stride_v = T, stride_t = 1) and a large vocabulary, the frames of each column a window needs are
+ * contiguous runs, so the kernel reads the algorithmic T * (L + 1) * 4 bytes instead of streaming the dense
+ * rows (BASELINE configs[3], V = 5000: 1.23 GB instead of 14.2 GB).  stride_v != 1 always takes the gather
+ * panel; stride_v == 1 is ipfa_ctc_alpha_device. */
+int ipfa_ctc_alpha_strided_device(const float *lp, int64_t stride_n, int64_t stride_t, int64_t stride_v,
+                                  const int32_t *targets, int64_t tgt_stride,
+                                  const int32_t *in_len, const int32_t *tgt_len,
+                                  int N, int Tmax, int Lmax, int V, int blank,
+                                  float *nll_out, void *workspace, size_t workspace_bytes,
+                                  void *stream);
 int ipfa_ctc_alpha_host(const float *lp, int64_t stride_n, int64_t stride_t,
                         const int32_t *targets, int64_t tgt_stride,
                         const int32_t *in_len, const int32_t *tgt_len,
@@ -127,6 +139,15 @@ int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_t stride_t,
                             int32_t *tok_start, int32_t *tok_end, float *tok_score,
                             float *total_out, int32_t *status_out,
                             void *workspace, size_t workspace_bytes, void *stream);
+/* ... and with a vocabulary stride, see ipfa_ctc_alpha_strided_device. */
+int ipfa_ctc_viterbi_strided_device(const float *lp, int64_t stride_n, int64_t stride_t, int64_t stride_v,
+                                    const int32_t *targets, int64_t tgt_stride,
+                                    const int32_t *in_len, const int32_t *tgt_len,
+                                    int N, int Tmax, int Lmax, int V, int blank,
+                                    int32_t *paths_out, float *scores_out,
+                                    int32_t *tok_start, int32_t *tok_end, float *tok_score,
+                                    float *total_out, int32_t *status_out,
+                                    void *workspace, size_t workspace_bytes, void *stream);
 int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
                           const int32_t *targets, int64_t tgt_stride,
                           const int32_t *in_len, const int32_t *tgt_len,

@@ -36,6 +36,12 @@ _SIGNATURES = {
                                       c_i, c_i, c_i, c_i, c_i,
                                       c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                                       c_void, c_sz, c_void]),
+    "ipfa_ctc_alpha_strided_device": (c_i, [c_void, c_i64, c_i64, c_i64, c_void, c_i64, c_void, c_void,
+                                            c_i, c_i, c_i, c_i, c_i, c_void, c_void, c_sz, c_void]),
+    "ipfa_ctc_viterbi_strided_device": (c_i, [c_void, c_i64, c_i64, c_i64, c_void, c_i64, c_void, c_void,
+                                              c_i, c_i, c_i, c_i, c_i,
+                                              c_void, c_void, c_void, c_void, c_void, c_void, c_void,
+                                              c_void, c_sz, c_void]),
     "ipfa_ctc_viterbi_host": (c_i, [c_void, c_i64, c_i64, c_void, c_i64, c_void, c_void,
                                     c_i, c_i, c_i, c_i, c_i,
                                     c_void, c_void, c_void, c_void, c_void, c_void, c_void]),

@@ -28,7 +28,7 @@ namespace ipfa {
 
 struct AlphaParams {
     const float *lp;
-    int64_t stride_n, stride_t;
+    int64_t stride_n, stride_t, stride_v;
     const int32_t *targets;
     int64_t tgt_stride;
     const int32_t *in_len;
@@ -217,7 +217,7 @@ ctc_alpha_kernel(const AlphaParams prm) {
 
     EmissionPipe<WARPS, DENSE> pipe;
     pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, U, prm.V, pitch,
-              prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid, t_lo, rev);
+              prm.tc, reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid, t_lo, rev, prm.stride_v);
     pipe.prologue(tid);
 
     // LIN: first frame (walk index) at which the lattice can have reached blank_p / label_p by the
@@ -549,6 +549,8 @@ ctc_alpha_kernel(const AlphaParams prm) {
                 v.z = fmaxf(v.z * kLog2e, kNegBig); v.w = fmaxf(v.w * kLog2e, kNegBig);
                 p4[q] = v;
             }
+            // (an odd pitch -- vocabulary-major gather -- can leave up to three elements behind the last float4)
+            for (int q = 4 * n4 + tid; q < rows * pitch; q += NT) panel[q] = fmaxf(panel[q] * kLog2e, kNegBig);
             group_sync<WARPS>();
         }
         const int first_row = rev ? rows - 1 : 0;  // the chunk's first frame in walking order
@@ -742,7 +744,7 @@ static int launch_alpha_p(AlphaParams prm, int Lmax, cudaStream_t stream) {
     const int U = PITCH ? PITCH : (DENSE ? prm.V : (Lmax + 1));
     // shared-memory budget per group for the emission ring
     const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
-    PipeGeometry g = pipe_geometry(U, budget);
+    PipeGeometry g = pipe_geometry(U, budget, !DENSE && prm.stride_v > prm.stride_t);
     prm.pitch = g.pitch;
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
@@ -884,11 +886,20 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
                                      const int32_t *in_len, const int32_t *tgt_len, int N, int Tmax,
                                      int Lmax, int V, int blank, float *nll_out, void *workspace,
                                      size_t workspace_bytes, void *stream) {
+    return ipfa_ctc_alpha_strided_device(lp, stride_n, stride_t, 1, targets, tgt_stride, in_len, tgt_len, N, Tmax,
+                                         Lmax, V, blank, nll_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ipfa_ctc_alpha_strided_device(const float *lp, int64_t stride_n, int64_t stride_t, int64_t stride_v,
+                                             const int32_t *targets, int64_t tgt_stride,
+                                             const int32_t *in_len, const int32_t *tgt_len, int N, int Tmax,
+                                             int Lmax, int V, int blank, float *nll_out, void *workspace,
+                                             size_t workspace_bytes, void *stream) {
     (void)Tmax;
     NvtxRange range("ipfa.ctc_alpha (window scorer: tiers + redo lists)");
     if (N == 0) return IPFA_OK;
     if (!lp || !in_len || !tgt_len || !nll_out || N < 0 || V <= 0 || Lmax < 0 || blank < 0 || blank >= V ||
-        (Lmax > 0 && !targets))
+        (Lmax > 0 && !targets) || stride_v < 1)
         return IPFA_ERR_INVALID_ARG;
     if (!workspace) return IPFA_ERR_INVALID_ARG;
     if (workspace_bytes < ipfa_ctc_alpha_workspace_bytes(N, Tmax, Lmax, V)) return IPFA_ERR_WORKSPACE;
@@ -896,13 +907,14 @@ extern "C" int ipfa_ctc_alpha_device(const float *lp, int64_t stride_n, int64_t 
     // MUFU pipe wants ~6 resident warp-chains per SM sub-partition more than it wants units per
     // thread.  The gather panel (large vocabularies) is bound by its loads, not by the chain:
     // one group per window.
-    const bool dense = use_dense_panel(V, Lmax);
+    // (rows that are not contiguous over the vocabulary -- stride_v != 1 -- always go through the gather panel)
+    const bool dense = stride_v == 1 && use_dense_panel(V, Lmax);
     const int halves = dense ? 2 : 1;
     LatticeShape s;
     if (!pick_lattice_shape(Lmax + 1, halves * N, &s, "IPFA_ALPHA_SHAPE", 6)) return IPFA_ERR_UNSUPPORTED;
     AlphaParams prm{};
     prm.halves = halves;
-    prm.lp = lp; prm.stride_n = stride_n; prm.stride_t = stride_t;
+    prm.lp = lp; prm.stride_n = stride_n; prm.stride_t = stride_t; prm.stride_v = stride_v;
     prm.targets = targets; prm.tgt_stride = tgt_stride;
     prm.in_len = in_len; prm.tgt_len = tgt_len; prm.order = nullptr; prm.count = nullptr;
     prm.N = N; prm.V = V; prm.blank = blank; prm.nll_out = nll_out;

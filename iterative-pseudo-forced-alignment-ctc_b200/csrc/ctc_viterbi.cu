@@ -29,7 +29,7 @@ bool use_dense_panel(int V, int Lmax);
 
 struct ViterbiParams {
     const float *lp;
-    int64_t stride_n, stride_t;
+    int64_t stride_n, stride_t, stride_v;
     const int32_t *targets;
     int64_t tgt_stride;
     const int32_t *in_len;
@@ -132,7 +132,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
 
     EmissionPipe<WARPS, DENSE> pipe;
     pipe.init(ring, cols, prm.lp + (int64_t)w * prm.stride_n, prm.stride_t, T, U, prm.V, pitch, prm.tc,
-              reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid);
+              reinterpret_cast<uint64_t *>(gsm + prm.group_smem - 32), tid, 0, false, prm.stride_v);
     pipe.prologue(tid);
 
     float ab[P], al[P];
@@ -291,7 +291,7 @@ ctc_viterbi_fill_kernel(const ViterbiParams prm) {
 
 struct BacktraceParams {
     const float *lp;
-    int64_t stride_n, stride_t;
+    int64_t stride_n, stride_t, stride_v;
     const int32_t *targets;
     int64_t tgt_stride;
     const int32_t *in_len;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
         const int c_cur = c_base;
         c_base = s >> LOG2SPT;
         if (blk > 0) request(blk - 1, c_base);  // in flight during this block's walk
-        if (pend_t >= 0 && scores) pend_sc = lp[(int64_t)pend_t * prm.stride_t + pend_lab];
+        if (pend_t >= 0 && scores) pend_sc = lp[(int64_t)pend_t * prm.stride_t + (int64_t)pend_lab * prm.stride_v];
         // moves of this block as two 32-bit masks (bit = frame - t_lo)
         uint32_t S_mv = 0, S_b2 = 0;
         const int s_top = s;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
     }
     if (pend_t >= 0) {
         paths[pend_t] = pend_lab;
-        if (scores) scores[pend_t] = lp[(int64_t)pend_t * prm.stride_t + pend_lab];
+        if (scores) scores[pend_t] = lp[(int64_t)pend_t * prm.stride_t + (int64_t)pend_lab * prm.stride_v];
     }
     if (want_tok && tok_p) {
         __syncwarp();
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(128) ctc_viterbi_backtrace_kernel(const Backtr
             if (a >= 0 && b > a) {
                 const int lab = tg_s[l];
                 float acc = 0.0f;
-                for (int t = a; t < b; ++t) acc += lp[(int64_t)t * prm.stride_t + lab];
+                for (int t = a; t < b; ++t) acc += lp[(int64_t)t * prm.stride_t + (int64_t)lab * prm.stride_v];
                 tok_p[l] = acc / (float)(b - a);
             }
         }
@@ -470,7 +470,7 @@ static int launch_fill_p(ViterbiParams prm, int Lmax, cudaStream_t stream) {
     constexpr int GROUPS = (WARPS == 1) ? 4 : 1;
     const int U = PITCH ? PITCH : (DENSE ? prm.V : (Lmax + 1));
     const size_t budget = (WARPS == 1) ? (16 * 1024) : (160 * 1024);
-    PipeGeometry g = pipe_geometry(U, budget);
+    PipeGeometry g = pipe_geometry(U, budget, !DENSE && prm.stride_v > prm.stride_t);
     prm.pitch = g.pitch;
     prm.tc = g.tc;
     prm.u_cap = DENSE ? 0 : ((Lmax + 1 + 3) & ~3);
@@ -546,9 +546,14 @@ static inline size_t vit_pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 extern "C" size_t ipfa_ctc_viterbi_workspace_bytes(int N, int Tmax, int Lmax, int V) {
     (void)V;
-    LatticeShape s;
+    LatticeShape s, s6;
     if (N <= 0 || Tmax < 0 || Lmax < 0 || !pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return 256;
-    const size_t bp = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s) * sizeof(uint32_t);
+    size_t bp = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s) * sizeof(uint32_t);
+    // (a strided call, stride_v != 1, always takes the gather panel's shape: size for the wider of the two)
+    if (pick_lattice_shape(Lmax + 1, N, &s6, "IPFA_VITERBI_SHAPE", 6)) {
+        const size_t bp6 = (size_t)N * (size_t)viterbi_words_per_window(Tmax, s6) * sizeof(uint32_t);
+        if (bp6 > bp) bp = bp6;
+    }
     // planes, final states, bucket lists [2][N] + counters
     return vit_pad256(bp) + vit_pad256((size_t)N * 4) + vit_pad256((size_t)N * 8) + 256 + 256;
 }
@@ -560,13 +565,28 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
                                        int32_t *tok_start, int32_t *tok_end, float *tok_score,
                                        float *total_out, int32_t *status_out, void *workspace,
                                        size_t workspace_bytes, void *stream) {
+    return ipfa_ctc_viterbi_strided_device(lp, stride_n, stride_t, 1, targets, tgt_stride, in_len, tgt_len, N, Tmax,
+                                           Lmax, V, blank, paths_out, scores_out, tok_start, tok_end, tok_score,
+                                           total_out, status_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ipfa_ctc_viterbi_strided_device(const float *lp, int64_t stride_n, int64_t stride_t, int64_t stride_v,
+                                               const int32_t *targets, int64_t tgt_stride,
+                                               const int32_t *in_len, const int32_t *tgt_len, int N, int Tmax,
+                                               int Lmax, int V, int blank, int32_t *paths_out, float *scores_out,
+                                               int32_t *tok_start, int32_t *tok_end, float *tok_score,
+                                               float *total_out, int32_t *status_out, void *workspace,
+                                               size_t workspace_bytes, void *stream) {
     if (N == 0) return IPFA_OK;
+    if (stride_v < 1) return IPFA_ERR_INVALID_ARG;
     if (!lp || !in_len || !tgt_len || !paths_out || !status_out || N < 0 || Tmax < 0 || V <= 0 ||
         Lmax < 0 || blank < 0 || blank >= V || (Lmax > 0 && !targets) || !workspace ||
         ((tok_start == nullptr) != (tok_end == nullptr)))
         return IPFA_ERR_INVALID_ARG;
     LatticeShape s;
-    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE", use_dense_panel(V, Lmax) ? 3 : 6)) return IPFA_ERR_UNSUPPORTED;
+    // (rows that are not contiguous over the vocabulary -- stride_v != 1 -- always go through the gather panel)
+    const bool dense = stride_v == 1 && use_dense_panel(V, Lmax);
+    if (!pick_lattice_shape(Lmax + 1, N, &s, "IPFA_VITERBI_SHAPE", dense ? 3 : 6)) return IPFA_ERR_UNSUPPORTED;
     if (workspace_bytes < ipfa_ctc_viterbi_workspace_bytes(N, Tmax, Lmax, V)) return IPFA_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t wpw = viterbi_words_per_window(Tmax, s);
@@ -580,19 +600,18 @@ extern "C" int ipfa_ctc_viterbi_device(const float *lp, int64_t stride_n, int64_
                                                  vit_pad256((size_t)N * 8));
 
     ViterbiParams fp{};
-    fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t;
+    fp.lp = lp; fp.stride_n = stride_n; fp.stride_t = stride_t; fp.stride_v = stride_v;
     fp.targets = targets; fp.tgt_stride = tgt_stride; fp.in_len = in_len; fp.tgt_len = tgt_len;
     fp.N = N; fp.Tmax = Tmax; fp.V = V; fp.blank = blank;
     fp.bp = bp; fp.words_per_window = wpw; fp.final_state = final_state;
     fp.total_out = total_out; fp.status_out = status_out;
     BacktraceParams bt{};
-    bt.lp = lp; bt.stride_n = stride_n; bt.stride_t = stride_t;
+    bt.lp = lp; bt.stride_n = stride_n; bt.stride_t = stride_t; bt.stride_v = stride_v;
     bt.targets = targets; bt.tgt_stride = tgt_stride; bt.in_len = in_len; bt.tgt_len = tgt_len;
     bt.N = N; bt.Tmax = Tmax; bt.Lmax = Lmax; bt.V = V; bt.blank = blank;
     bt.bp = bp; bt.words_per_window = wpw; bt.final_state = final_state;
     bt.paths_out = paths_out; bt.scores_out = scores_out;
     bt.tok_start = tok_start; bt.tok_end = tok_end; bt.tok_score = tok_score;
-    const bool dense = use_dense_panel(V, Lmax);
 
     // two length buckets when the batch is large and a half-width instance exists
     const int big_units = 32 * s.WARPS * s.PER, small_units = big_units / 2;

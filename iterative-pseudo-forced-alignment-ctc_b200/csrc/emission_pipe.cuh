@@ -71,6 +71,7 @@ struct EmissionPipe {
     const int *cols;      // smem column list (gather mode)
     const float *base;    // &lp[w, 0, 0]
     int64_t stride_t;
+    int64_t stride_v;     // gather mode: elements between two vocabulary entries of one frame (1: rows contiguous)
     int T, U, V, pitch, tc, nchunks;
     int t_lo;             // first frame of the range this pipe walks
     bool rev;             // chunks (and the caller's rows) run from the last frame down
@@ -80,9 +81,10 @@ struct EmissionPipe {
     // All threads of the group call init(); it ends with a group barrier.
     __device__ __forceinline__ void init(float *ring_, const int *cols_, const float *base_,
                                          int64_t stride_t_, int T_, int U_, int V_, int pitch_, int tc_,
-                                         uint64_t *bars_, int tid, int t_lo_ = 0, bool rev_ = false) {
+                                         uint64_t *bars_, int tid, int t_lo_ = 0, bool rev_ = false,
+                                         int64_t stride_v_ = 1) {
         // T_ frames starting at t_lo_; rev_: logical chunk 0 holds the LAST tc frames of the range
-        ring = ring_; cols = cols_; base = base_; stride_t = stride_t_;
+        ring = ring_; cols = cols_; base = base_; stride_t = stride_t_; stride_v = stride_v_;
         T = T_; U = U_; V = V_; pitch = pitch_; tc = tc_; bars = bars_; t_lo = t_lo_; rev = rev_;
         nchunks = (T + tc - 1) / tc;
         vec16 = DENSE && (V % 4 == 0) && (stride_t % 4 == 0) &&
@@ -136,11 +138,20 @@ struct EmissionPipe {
                         cp_async_4(dst + r * pitch + c, base + (int64_t)(t0 + r) * stride_t + c);
                     }
                 }
+            } else if (stride_v > stride_t) {
+                // vocabulary-major emissions ([V, T] per window): the frames of one column are contiguous,
+                // so the lanes of a warp walk TIME -- one 128-byte run per (column, chunk) -- and the
+                // panel (frame-major, odd pitch: conflict-free) is filled column by column
+                const int lane = tid & 31;
+                for (int j = tid >> 5; j < U; j += WARPS) {
+                    const float *src = base + (int64_t)cols[j] * stride_v + (int64_t)t0 * stride_t;
+                    for (int r = lane; r < rows; r += 32) cp_async_4(dst + r * pitch + j, src + (int64_t)r * stride_t);
+                }
             } else {
                 for (int r = 0; r < rows; ++r) {
                     const float *src = base + (int64_t)(t0 + r) * stride_t;
                     float *d = dst + r * pitch;
-                    for (int j = tid; j < U; j += NT) cp_async_4(d + j, src + cols[j]);
+                    for (int j = tid; j < U; j += NT) cp_async_4(d + j, src + (int64_t)cols[j] * stride_v);
                 }
             }
         }
@@ -180,9 +191,9 @@ struct PipeGeometry {
     size_t ring_bytes;
 };
 
-inline PipeGeometry pipe_geometry(int U_panel, size_t budget_bytes) {
+inline PipeGeometry pipe_geometry(int U_panel, size_t budget_bytes, bool odd_pitch = false) {
     PipeGeometry g;
-    g.pitch = (U_panel + 3) & ~3;
+    g.pitch = odd_pitch ? (U_panel | 1) : ((U_panel + 3) & ~3);  // odd: column-wise fills hit distinct banks
     size_t per_frame = (size_t)kStages * g.pitch * sizeof(float);
     int tc = (int)(budget_bytes / per_frame);
     if (tc > 32) tc = 32;

@@ -57,11 +57,14 @@ def _i32(t, device):
 
 
 def _lp_strides(lp, batch_first):
+    """(tensor, N, T, V, stride_n, stride_t, stride_v) in elements.  Any strided view is taken as it is --
+    [N, T, V], [T, N, V] (batch_first=False) and vocabulary-major storage ([N, V, T] viewed through
+    ``.transpose(1, 2)``: stride_v = T) all work without a copy."""
     if lp.dim() != 3:
         raise ValueError("lp must be [N, T, V] (or [T, N, V] with batch_first=False)")
     if lp.dtype != torch.float32:
         raise ValueError("lp must be float32 log-probabilities")
-    if lp.stride(2) != 1:
+    if min(lp.stride()) < 1:
         lp = lp.contiguous()
     if batch_first:
         n, t, v = lp.shape
@@ -69,7 +72,7 @@ def _lp_strides(lp, batch_first):
     else:
         t, n, v = lp.shape
         st, sn = lp.stride(0), lp.stride(1)
-    return lp, n, t, v, sn, st
+    return lp, n, t, v, sn, st, lp.stride(2)
 
 
 _ws_cache = {}
@@ -88,7 +91,7 @@ def _workspace(nbytes, device):
 def ctc_alpha_nll(lp, targets, in_len, tgt_len, blank=0, batch_first=True):
     """Negative log-likelihood of every window, fp32 [N] (inf when infeasible)."""
     _need_cuda(lp, "lp")
-    lp, n, t, v, sn, st = _lp_strides(lp, batch_first)
+    lp, n, t, v, sn, st, sv = _lp_strides(lp, batch_first)
     dev = lp.device
     targets = _i32(targets, dev)
     if targets.dim() == 1:
@@ -100,10 +103,10 @@ def ctc_alpha_nll(lp, targets, in_len, tgt_len, blank=0, batch_first=True):
     with torch.cuda.device(dev):
         ws_bytes = L.ipfa_ctc_alpha_workspace_bytes(n, t, lmax, v)
         ws = _workspace(ws_bytes, dev)
-        rc = L.ipfa_ctc_alpha_device(_ptr(lp), sn, st, _ptr(targets), targets.stride(0) if lmax else 0,
-                                     _ptr(in_len), _ptr(tgt_len), n, t, lmax, v, blank, _ptr(out),
-                                     _ptr(ws), ws.numel(), _stream(dev))
-    check(rc, "ipfa_ctc_alpha_device")
+        rc = L.ipfa_ctc_alpha_strided_device(_ptr(lp), sn, st, sv, _ptr(targets), targets.stride(0) if lmax else 0,
+                                             _ptr(in_len), _ptr(tgt_len), n, t, lmax, v, blank, _ptr(out),
+                                             _ptr(ws), ws.numel(), _stream(dev))
+    check(rc, "ipfa_ctc_alpha_strided_device")
     return out
 
 
@@ -169,7 +172,7 @@ class ForcedAlignment:
 
 def ctc_forced_align(lp, targets, in_len, tgt_len, blank=0, batch_first=True, tokens=True):
     _need_cuda(lp, "lp")
-    lp, n, t, v, sn, st = _lp_strides(lp, batch_first)
+    lp, n, t, v, sn, st, sv = _lp_strides(lp, batch_first)
     dev = lp.device
     targets = _i32(targets, dev)
     if targets.dim() == 1:
@@ -190,12 +193,12 @@ def ctc_forced_align(lp, targets, in_len, tgt_len, blank=0, batch_first=True, to
     with torch.cuda.device(dev):
         ws_bytes = L.ipfa_ctc_viterbi_workspace_bytes(n, t, lmax, v)
         ws = _workspace(ws_bytes, dev)
-        rc = L.ipfa_ctc_viterbi_device(_ptr(lp), sn, st, _ptr(targets), targets.stride(0) if lmax else 0,
-                                       _ptr(in_len), _ptr(tgt_len), n, t, lmax, v, blank,
-                                       _ptr(paths), _ptr(scores), _ptr(tok_start), _ptr(tok_end),
-                                       _ptr(tok_score), _ptr(total), _ptr(status),
-                                       _ptr(ws), ws.numel(), _stream(dev))
-    check(rc, "ipfa_ctc_viterbi_device")
+        rc = L.ipfa_ctc_viterbi_strided_device(_ptr(lp), sn, st, sv, _ptr(targets), targets.stride(0) if lmax else 0,
+                                               _ptr(in_len), _ptr(tgt_len), n, t, lmax, v, blank,
+                                               _ptr(paths), _ptr(scores), _ptr(tok_start), _ptr(tok_end),
+                                               _ptr(tok_score), _ptr(total), _ptr(status),
+                                               _ptr(ws), ws.numel(), _stream(dev))
+    check(rc, "ipfa_ctc_viterbi_strided_device")
     return ForcedAlignment(paths, scores, tok_start, tok_end, tok_score, total, status)
 
 
@@ -247,7 +250,9 @@ def ctcseg_align(lp, in_len, gt, n_cols, utt_begin, n_utts, index_duration, blan
     ``None`` = full-table kernels (T <= 8000 frames).  In windowed mode ``status`` carries bit 8
     (``WIN_WINDOW_TOO_SMALL``) where the reference would raise IndexError and double the window."""
     _need_cuda(lp, "lp")
-    lp, n, t, v, sn, st = _lp_strides(lp, batch_first)
+    if lp.dim() == 3 and lp.stride(2) != 1:  # the segmentation kernels read whole rows
+        lp = lp.contiguous()
+    lp, n, t, v, sn, st, sv = _lp_strides(lp, batch_first)
     dev = lp.device
     gt = _i32(gt, dev)
     utt_begin = _i32(utt_begin, dev)

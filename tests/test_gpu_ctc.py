@@ -367,3 +367,28 @@ def test_alpha_fp32_tier_is_exact_where_it_answers(ipfa):
         _check_nll(tiered, ref)
         fin = np.isfinite(ref)
         np.testing.assert_allclose(tiered[fin], plain[fin], rtol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(3, 150, 60, 5000), (2, 400, 130, 700), (4, 300, 100, 32), (2, 95, 40, 33)])
+def test_vocabulary_major_emissions(ipfa, shape):
+    """Emissions stored [N, V, T] (stride_v = T, stride_t = 1) through the strided entry points: the
+    window scorer and Viterbi read runs of frames per column instead of rows; results do not depend on
+    the storage order."""
+    import torch
+    from oracle import ctc as octc
+    n, t, l, v = shape
+    lp, tg, il, tl = ctc_case(21, n, t, l, v, ragged=True, repeats=True, peaked=True)
+    ref = octc.ctc_alpha_nll(lp, tg, il, tl)
+    paths, scores, status = octc.ctc_viterbi(lp, tg, il, tl)
+    rows = _dev(lp)
+    cols = rows.transpose(1, 2).contiguous().transpose(1, 2)  # [N, T, V] view of [N, V, T] storage
+    assert cols.stride(2) == t and cols.stride(1) == 1 and torch.equal(cols, rows)
+    a = [_dev(x) for x in (tg, il, tl)]
+    nll = ipfa.ctc_alpha_nll(cols, *a).cpu().numpy()
+    _check_nll(nll, ref)
+    res = ipfa.ctc_forced_align(cols, *a)
+    _check_viterbi(res, paths, scores, status, il)
+    # and a non-unit stride on a row-major tensor (every other column of a wider matrix)
+    wide = torch.zeros((n, t, 2 * v), device="cuda")
+    wide[:, :, ::2] = rows
+    _check_nll(ipfa.ctc_alpha_nll(wide[:, :, ::2], *a).cpu().numpy(), ref)
