@@ -199,6 +199,11 @@ int ipfa_ctc_viterbi_host(const float *lp, int64_t stride_n, int64_t stride_t,
  *   cur_offset[s+1] = cur_offset[s] + offset runs in ascending order  /  as a shift (multi-column gt). */
 #define IPFA_SEG_WINDOW_STEP_CEIL 16
 #define IPFA_SEG_OFFSET_SHIFT 32
+/* Launch policy of the full-table fill, results unaffected: spread the columns of every window over a
+ * thread-block cluster of 2 / 4 SMs, boundary values handed over a chunk at a time through distributed
+ * shared memory.  Opt-in: on the anchor sweep's windows it measured no faster than one SM. */
+#define IPFA_SEG_SPREAD_2 64
+#define IPFA_SEG_SPREAD_4 128
 
 size_t ipfa_ctcseg_workspace_bytes(int N, int Tmax, int Cmax, int Kmax, int V);
 int ipfa_ctcseg_device(const float *lp, int64_t stride_n, int64_t stride_t,

@@ -62,15 +62,23 @@ struct SegFillParams {
 // backpointer word address the panel with immediate offsets.
 // FAST: the reference's default flags (blank_transition_cost_zero = False,
 // preamble_transition_cost_zero = True) compiled in, so neither costs an instruction per cell.
-// CL > 1 (experiment, see try_seg_fill_cluster): a window is spread over a thread-block CLUSTER of CL
-// CTAs (CTA `rank` owns the columns of threads rank*NT ...), for batches too small to fill the GPU: the per-frame instruction stream of
-// a window then issues on CL SMs.  The one value per frame that crosses the CTA boundary (last
-// column of rank r -> first column of rank r+1) travels through distributed shared memory: the
-// producer stores (value, frame) as one 8-byte remote store into a ring in the consumer's smem,
-// the consumer spins on its OWN smem until the tag is the frame it needs, and reports its progress
-// back with a remote store so the producer never laps the ring.  No cluster barrier per frame: the
-// CTAs of a window run skewed by the store latency, like pipeline stages.
-constexpr int kClusterRing = 64;
+// CL > 1: a window's columns are spread over a thread-block CLUSTER of CL CTAs (CTA `rank` owns the
+// columns of threads rank*NT ...), for launches that leave SMs idle: the fill is issue bound and a
+// window otherwise lives on ONE SM, so CL SMs issue its frames CL times as fast.  The one
+// value per frame that crosses a CTA boundary (last column of rank r -> first column of rank r+1) is
+// handed over a CHUNK at a time: the producer collects the 32 boundary values of an emission chunk in
+// its own shared memory and, at the end of the chunk, sends them into a 4-slot ring in the consumer's
+// shared memory as asynchronous remote stores (st.async, distributed shared memory) that complete an
+// mbarrier over there -- no fence, nothing to wait for on the producer's side; the consumer waits on
+// that mbarrier once per chunk and then reads the values locally, frame by frame.  The CTAs of a window
+// therefore run one chunk (plus the hand-over latency) behind each other, like pipeline stages, and
+// nothing is exchanged per frame (round 1's per-frame remote ring was slower than no split at all).
+// Inside a frame the value the right neighbour waits for is published first and the emissions are
+// fetched a frame ahead (see frame()), which is what the few warps of such a CTA are bound by.
+// Back-pressure: the consumer reports the chunks it has finished; the producer never runs more than
+// two chunks ahead of that, so a ring slot is not rewritten while its last value is still needed.
+constexpr int kSpreadSlots = 4;   // ring of chunk-sized boundary buffers (a chunk = 32 frames)
+constexpr int kSpreadBytes = kSpreadSlots * 32 * 4 + kSpreadSlots * 8 + 32 * 4 + 16;
 
 template <int KC, int WARPS, bool DENSE, int PITCH, bool FAST, int CL = 1>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
@@ -93,7 +101,7 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     unsigned char *gsm = smem_raw + (size_t)group * prm.group_smem;
     float *ring = reinterpret_cast<float *>(gsm);
     float *xline = ring + (size_t)kStages * prm.tc * pitch;     // [2][NT + 1] neighbour exchange
-    int *cols = reinterpret_cast<int *>(xline + 2 * (NT + 1));    // [u_cap]
+    int *cols = reinterpret_cast<int *>(xline + (CL > 1 ? 3 : 2) * (NT + 1));    // [u_cap]
 
     const int T = min(prm.in_len[w], prm.Tmax);
     const int NC = max(0, min(prm.n_cols[w], prm.Cmax));
@@ -145,19 +153,29 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     }
     const bool warp_tracks = __any_sync(0xffffffffu, track);
     if constexpr (WARPS > 1) {
-        if (ltid < 2) xline[ltid * (NT + 1)] = 0.0f;  // z(t) = table[t, 0]; table[0, 0] = 0
+        if (ltid < (CL > 1 ? 3 : 2)) xline[ltid * (NT + 1)] = 0.0f;  // z(t) = table[t, 0]; table[0, 0] = 0
     }
-    // cluster exchange: ring of (value bits, frame tag) written by the left neighbour, progress word
-    // written by the right neighbour
-    uint2 *xring = reinterpret_cast<uint2 *>(gsm + prm.group_smem - 32 - (kClusterRing + 2) * sizeof(uint2));
-    volatile int *progress = reinterpret_cast<volatile int *>(xring + kClusterRing);
-    uint32_t ring_next = 0, progress_prev = 0;  // remote addresses
+    // cluster hand-over (CL > 1): [kSpreadSlots][32] incoming boundary values, their flags, the outgoing
+    // staging line, the right neighbour's progress word
+    float *sp_in = reinterpret_cast<float *>(gsm + prm.group_smem - 32 - kSpreadBytes);
+    uint64_t *sp_bar = reinterpret_cast<uint64_t *>(sp_in + kSpreadSlots * 32);   // one mbarrier per slot
+    float *sp_out = reinterpret_cast<float *>(sp_bar + kSpreadSlots);
+    volatile uint32_t *sp_progress = reinterpret_cast<volatile uint32_t *>(sp_out + 32);
+    uint32_t sp_in_next = 0, sp_bar_next = 0, sp_progress_prev = 0;  // remote (shared::cluster) addresses
     if constexpr (CL > 1) {
-        for (int i = ltid; i < kClusterRing; i += NT)
-            xring[i] = make_uint2(__float_as_uint(kProbMax), i == 0 ? 0u : 0xffffffffu);  // frame 0: prob_max
-        if (ltid == 0) *progress = 0;
-        if (rank + 1 < CL) ring_next = cluster_map(xring, rank + 1);
-        if (rank > 0) progress_prev = cluster_map(const_cast<int *>(progress), rank - 1);
+        if (ltid == 0) {
+            *sp_progress = 0;
+            for (int i = 0; i < kSpreadSlots; ++i) mbar_init(&sp_bar[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // every slot is armed for one chunk of 32 values: the producer's asynchronous stores complete it
+            for (int i = 0; i < kSpreadSlots; ++i) mbar_expect_tx(&sp_bar[i], 128);
+        }
+        if (ltid == NT - 1) sp_out[0] = kProbMax;  // table[0, c] = prob_max for every column c >= 1
+        if (rank + 1 < CL) {
+            sp_in_next = cluster_map(sp_in, rank + 1);
+            sp_bar_next = cluster_map(sp_bar, rank + 1);
+        }
+        if (rank > 0) sp_progress_prev = cluster_map(const_cast<uint32_t *>(sp_progress), rank - 1);
         cluster_sync_all();  // every ring is initialised before any neighbour stores into it
     }
     group_sync<WARPS>();
@@ -173,43 +191,74 @@ ctcseg_fill_kernel(const SegFillParams prm) {
 #pragma unroll
     for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = kNegInf; carg[k] = -1; }
     float z = 0.0f;  // column 0 at the previous frame
-    float next_prev = 0.0f;    // cluster exchange: value fetched ahead for the next frame
-    bool have_next = false;
-    int seen_progress = 0;     // cluster exchange: cached progress of the right neighbour
     uint32_t word = 0;
     int shift = 0;
     uint32_t *bp_ptr = prm.bp + (int64_t)w * prm.words_per_window + tid;
     int t = 0;
 
     // one frame; returns this thread's KC decision bits
-    auto frame = [&](const float *row, const float *rd, float *wr) -> uint32_t {
-        const float eb = row[colb];
-        float ec[KC];
+    int li = 0;  // CL > 1: exchange line of the frame being written (three lines, frame t -> line t % 3)
+    // CL > 1: the emissions of a frame are fetched one frame ahead (eb_n / ec_n), so that no shared-memory
+    // load latency sits between the barrier and the values the neighbours wait for
+    float eb_n = 0.0f, ec_n[KC];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
+    for (int k = 0; k < KC; ++k) ec_n[k] = 0.0f;
+    auto prefetch = [&](const float *row) {
+        eb_n = row[colb];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) ec_n[k] = row[col[k]];
+    };
+    auto frame = [&](const float *row, const float *rd, float *wr) -> uint32_t {
+        float eb, ec[KC];
+        if constexpr (CL > 1) {
+            eb = eb_n;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) ec[k] = ec_n[k];
+            prefetch(row + pitch);  // (past the chunk's last row: stale rows of the ring, re-fetched at the chunk start)
+        } else {
+            eb = row[colb];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
+        }
+        float left_[KC], up_[KC], stayp_[KC];
+        const int t_now = t;
+        if constexpr (CL > 1) {
+            // Publish first.  The value the right neighbour waits for -- this thread's LAST column -- depends
+            // only on this thread's own values of the previous frame, so it is computed, stored and the CTA
+            // barrier is passed BEFORE the left neighbour's value (one shared-memory load later) is needed for
+            // the first column: with the few warps a CTA of a spread window has, the frame time is this
+            // dependent chain, not the issue rate.  The loads after the barrier read the line the previous
+            // frame wrote while faster neighbours may already write the next one: three lines.
+            static_assert(KC >= 2, "spread windows keep at least two columns per thread");
+            float *lw = xline + li * (NT + 1);
+            const float *lr = xline + (li == 0 ? 2 : li - 1) * (NT + 1);
+            li = (li == 2) ? 0 : li + 1;
+            {
+                constexpr int k = KC - 1;
+                const float left = val[k - 1], up = val[k];
+                const float stay_p = fmaxf(eb, ec[k]);
+                left_[k] = left; up_[k] = up; stayp_[k] = stay_p;
+                val[k] = fmaxf(__fadd_rn(left, ec[k]), __fadd_rn(up, stay_p));
+            }
+            lw[ltid + 1] = val[KC - 1];
+            if (rank + 1 < CL && ltid == NT - 1) sp_out[t & 31] = val[KC - 1];
+            __syncthreads();
+            float prev = lr[ltid];
+            // table[t-1] of the left neighbour's last column: delivered with the chunk of frame t-1
+            if (rank > 0 && ltid == 0) prev = sp_in[(((t - 1) >> 5) & (kSpreadSlots - 1)) * 32 + ((t - 1) & 31)];
+#pragma unroll
+            for (int k = KC - 2; k >= 0; --k) {
+                const float left = (k == 0) ? prev : val[k - 1];
+                const float up = val[k];
+                const float stay_p = fmaxf(eb, ec[k]);
+                left_[k] = left; up_[k] = up; stayp_[k] = stay_p;
+                val[k] = fmaxf(__fadd_rn(left, ec[k]), __fadd_rn(up, stay_p));
+            }
+            ++t;
+        } else {
         float prev;
         if constexpr (WARPS > 1) {
             prev = rd[ltid];
-            if constexpr (CL > 1) {
-                if (rank > 0 && ltid == 0) {  // table[t-1] of the left neighbour's last column
-                    if (have_next) {          // fetched during the previous frame
-                        prev = next_prev;
-                    } else {
-                        const volatile uint2 *slot = xring + ((t - 1) & (kClusterRing - 1));
-                        uint2 v;
-                        do { v.x = slot->x; v.y = slot->y; } while (v.y != (uint32_t)(t - 1));
-                        v.x = slot->x;  // (value and tag arrive as one 8-byte store; re-read after the tag matched)
-                        prev = __uint_as_float(v.x);
-                    }
-                    // look ahead: the neighbour usually leads by a few frames, so the value for the
-                    // NEXT frame is normally there already and its load hides behind this frame's work
-                    const volatile uint2 *nslot = xring + (t & (kClusterRing - 1));
-                    const uint32_t ntag = nslot->y;
-                    next_prev = __uint_as_float(nslot->x);
-                    have_next = (ntag == (uint32_t)t);
-                    if (have_next) next_prev = __uint_as_float(nslot->x);
-                }
-            }
         } else {
             prev = __shfl_up_sync(0xffffffffu, val[KC - 1], 1);
             if (ltid == 0) prev = z;
@@ -218,7 +267,6 @@ ctcseg_fill_kernel(const SegFillParams prm) {
         // through the exchange line and the CTA barrier) waits for; the transition test and the
         // arg-max bookkeeping of this frame are computed AFTER the barrier, in the shadow of the next
         // frame's shared-memory loads.
-        float left_[KC], up_[KC], stayp_[KC];
 #pragma unroll
         for (int k = KC - 1; k >= 0; --k) {
             const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
@@ -229,23 +277,13 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             left_[k] = left; up_[k] = up; stayp_[k] = stay_p;
             val[k] = fmaxf(sw, st);
         }
-        const int t_now = t;
-        if constexpr (CL > 1) {
-            if (rank + 1 < CL && ltid == NT - 1) {
-                // slot t % R still holds frame t - R: wait until the neighbour has consumed it (the
-                // progress word is re-read only when the cached value says the ring could be full)
-                while (t - seen_progress > kClusterRing - 2) seen_progress = *progress;
-                st_cluster_v2(ring_next + (uint32_t)((t & (kClusterRing - 1)) * sizeof(uint2)),
-                              __float_as_uint(val[KC - 1]), (uint32_t)t);
-            }
-            if (rank > 0 && ltid == 0) st_cluster_u32(progress_prev, (uint32_t)t);  // consumed frame t - 1
-        }
         ++t;
         if (!preamble_cost_zero) z = fmaxf(kProbMax, __fadd_rn(z, eb));
         if constexpr (WARPS > 1) {
             wr[ltid + 1] = val[KC - 1];
             if (!preamble_cost_zero && ltid == 0) wr[0] = z;
             __syncthreads();
+        }
         }
         uint32_t bits = 0;
 #pragma unroll
@@ -279,6 +317,12 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     for (int chunk = 0; chunk < pipe.nchunks; ++chunk) {
         const float *panel = pipe.acquire(chunk, ltid);
         const int rows = min(pipe.tc, T - chunk * pipe.tc);
+        if constexpr (CL > 1) {
+            // frames 32c+1 .. 32c+32 read the neighbour's values of frames 32c .. 32c+31: chunk c's buffer
+            // (the first frame of the chunk reads the last value of chunk c-1, delivered before)
+            if (rank > 0 && ltid == 0)
+                mbar_wait(&sp_bar[chunk & (kSpreadSlots - 1)], (uint32_t)(chunk / kSpreadSlots) & 1u);
+        }
         int r = 0;
         if (chunk == 0) {
             // t = 0: every column c >= 1 is max(switch = prob_max, stay = prob_max)
@@ -289,12 +333,14 @@ ctcseg_fill_kernel(const SegFillParams prm) {
             push_bits(0);
             t = 1;
             if constexpr (WARPS > 1) {
-                line0[ltid + 1] = kProbMax;
+                line0[ltid + 1] = kProbMax;  // (CL > 1: line 0 = the line of frame 0)
                 __syncthreads();
+                li = 1;
             }
             r = 1;
         }
         const float *row = panel + r * pitch;
+        if constexpr (CL > 1) prefetch(row);
         // frame t reads line[(t-1)&1], writes line[t&1]; tc is even so r has t's parity
         while (r < rows) {
             if (shift == 0 && !(r & 1) && r + SPW <= rows) {
@@ -312,6 +358,23 @@ ctcseg_fill_kernel(const SegFillParams prm) {
                 push_bits((r & 1) ? frame(row, line0, line1) : frame(row, line1, line0));
                 row += pitch;
                 ++r;
+            }
+        }
+        if constexpr (CL > 1) {
+            // (every frame ended with a CTA barrier: sp_out holds the whole chunk.)  The 32 values go to the
+            // neighbour as asynchronous remote stores that complete the slot's mbarrier there: no fence,
+            // nothing for this CTA to wait for.
+            if (rank + 1 < CL && ltid < 32) {
+                if (ltid == 0) {  // never more than two chunks ahead of what the neighbour has finished
+                    while ((int)((uint32_t)chunk - *sp_progress) > 2) {}
+                }
+                __syncwarp();
+                const uint32_t slot = (uint32_t)(chunk & (kSpreadSlots - 1));
+                st_async_u32(sp_in_next + (slot * 32 + ltid) * 4, __float_as_uint(sp_out[ltid]), sp_bar_next + slot * 8);
+            }
+            if (rank > 0 && ltid == 0) {  // done with the slot: arm it for chunk + kSpreadSlots, then say so
+                mbar_expect_tx(&sp_bar[chunk & (kSpreadSlots - 1)], 128);
+                st_cluster_u32(sp_progress_prev, (uint32_t)(chunk + 1));
             }
         }
     }
@@ -1239,7 +1302,7 @@ static int launch_seg_fill_cluster(SegFillParams prm, cudaStream_t stream) {
     prm.pitch = g.pitch;
     prm.tc = g.tc;
     prm.u_cap = 0;
-    size_t group_smem = g.ring_bytes + 2 * (32 * WARPS + 1) * sizeof(float) + (kClusterRing + 2) * sizeof(uint2) + 40;
+    size_t group_smem = g.ring_bytes + 3 * (32 * WARPS + 1) * sizeof(float) + kSpreadBytes + 40;
     group_smem = (group_smem + 15) & ~(size_t)15;
     prm.group_smem = group_smem;
     auto kern = ctcseg_fill_kernel<KC, WARPS, true, 32, true, CL>;
@@ -1263,24 +1326,25 @@ static int launch_seg_fill_cluster(SegFillParams prm, cudaStream_t stream) {
     return IPFA_OK;
 }
 
-// Experiment switch: true and launched when asked for, the batch is too small to fill the GPU and a
-// 2-CTA instance exists for this width (2 columns per thread, 8 / 12 / 16 warps per window)
+// Spread the columns of every window over CL SMs (cluster launch).  OPT-IN (IPFA_SEG_SPREAD_2 / _4 in
+// `flags`): measured on the anchor sweep's windows it does not pay -- 88 us per fill of a 1700-frame,
+// 700-column window on one SM, 94 us over two, 89 us over four (profiles/r02_fill_spread.txt) -- because
+// with a handful of warps per CTA the frame time is the dependent chain LDS(neighbour) -> FADD -> FMNMX ->
+// STS -> BAR (~100 cycles), which is as long as the 132 issue cycles the unsplit window needs.
+// Instances: dense 32-symbol panel, default flags, 2 columns per thread (the anchor loop's configuration).
 static bool try_seg_fill_cluster(const SegFillParams &prm, SegShape s, cudaStream_t stream, int *rc) {
     const bool fast = (prm.flags & (IPFA_SEG_BLANK_COST_ZERO | IPFA_SEG_PREAMBLE_COST_ZERO)) ==
                       IPFA_SEG_PREAMBLE_COST_ZERO;
-    // Opt-in (IPFA_SEG_CLUSTER=1): measured on the anchor sweep it LOSES -- 177 us against 115 us per
-    // fill of one 2200-frame, 700-column window (tools/exp_sweep_floor.py).  With a dozen warps per
-    // window the frame time is already the dependent-chain latency of one warp (~100 cycles), not
-    // the issue rate of the SM, so a second SM has nothing to take over and the exchange only adds.
-    if (!tuning("IPFA_SEG_CLUSTER")) return false;
     if (!fast || prm.V > 32 || s.PER != 2) return false;
-    if ((long long)prm.N * s.WARPS >= 148LL * 4 * 3) return false;  // enough warps without splitting
-    switch (s.WARPS) {
-#define IPFA_C(W_) case W_: *rc = launch_seg_fill_cluster<2, W_ / 2, 2>(prm, stream); return true;
-        IPFA_C(8) IPFA_C(12) IPFA_C(16)
+    int cl = (prm.flags & IPFA_SEG_SPREAD_4) ? 4 : (prm.flags & IPFA_SEG_SPREAD_2) ? 2 : 1;
+    if (cl == 4 && (s.WARPS % 4 != 0 || s.WARPS < 8)) cl = 2;
+    if (cl == 2 && (s.WARPS % 2 != 0 || s.WARPS < 4)) cl = 1;
+    if (cl == 1) return false;
+#define IPFA_C(CL_, W_) if (cl == CL_ && s.WARPS == CL_ * W_) { *rc = launch_seg_fill_cluster<2, W_, CL_>(prm, stream); return true; }
+    IPFA_C(2, 2) IPFA_C(2, 3) IPFA_C(2, 4) IPFA_C(2, 5) IPFA_C(2, 6) IPFA_C(2, 8) IPFA_C(2, 10) IPFA_C(2, 12)
+    IPFA_C(4, 2) IPFA_C(4, 3) IPFA_C(4, 4) IPFA_C(4, 5) IPFA_C(4, 6)
 #undef IPFA_C
-        default: return false;
-    }
+    return false;
 }
 
 template <int KC, int WARPS, bool DENSE>

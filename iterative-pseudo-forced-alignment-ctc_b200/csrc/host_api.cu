@@ -17,7 +17,7 @@ uint64_t g_launch_count = 0;
 namespace {
 const char *const kTuningNames[] = {
     "IPFA_ALPHA_SHAPE", "IPFA_ALPHA_SMALL_SHAPE", "IPFA_ALPHA_LIN_SHAPE", "IPFA_ALPHA_LOG", "IPFA_NO_BUCKETS",
-    "IPFA_VITERBI_SHAPE", "IPFA_VITERBI_SMALL_SHAPE", "IPFA_SEG_SHAPE", "IPFA_SEG_CLUSTER", "IPFA_PIPE_TC",
+    "IPFA_VITERBI_SHAPE", "IPFA_VITERBI_SMALL_SHAPE", "IPFA_SEG_SHAPE", "IPFA_PIPE_TC",
     "IPFA_ALPHA_F32", "IPFA_SEG_SKEW"};
 constexpr int kTuningCount = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 struct TuningTable {

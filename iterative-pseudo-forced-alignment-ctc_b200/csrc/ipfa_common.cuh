@@ -125,6 +125,15 @@ __device__ __forceinline__ uint32_t cluster_map(const void *smem_ptr, uint32_t r
 __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+// asynchronous 4-byte store into another CTA's shared memory that completes 4 bytes of an mbarrier there
+__device__ __forceinline__ void st_async_u32(uint32_t addr, uint32_t v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(addr), "r"(v),
+                 "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_cluster() {  // orders this thread's accesses at cluster scope (release / acquire)
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t a) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }

@@ -30,6 +30,7 @@ SEG_ROUND_NEAREST = 4
 SEG_ALL_PREFIXES = 8
 SEG_WINDOW_STEP_CEIL = 16
 SEG_OFFSET_SHIFT = 32
+SEG_SPREAD_2, SEG_SPREAD_4 = 64, 128
 WIN_WINDOW_TOO_SMALL = 8
 
 

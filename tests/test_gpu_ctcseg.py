@@ -480,3 +480,28 @@ def test_host_entry_point_long_audio(ipfa):
     res = ipfa.ctcseg_align_host(lp, in_len, gt, n_cols, ubs, n_utts, 0.02, flags=2)
     assert int(res.status[0]) == 0
     _compare_window(cfg, res, 0, int(n_utts[0]), lp[0, :in_len[0]], utts[0], lambda x: x)
+
+
+@pytest.mark.parametrize("spread", [64, 128])
+def test_window_columns_spread_over_a_cluster(ipfa, spread):
+    """IPFA_SEG_SPREAD_2 / _4: a window's columns over 2 / 4 SMs (thread-block cluster, boundary values handed
+    over a chunk at a time through distributed shared memory) -- same bits as one SM."""
+    import torch
+    from oracle import ctcseg as oseg
+    cfg = oseg.CtcSegmentationParameters(index_duration=0.02)
+    for shape in ((3, 900, 32, 6, 20, 40), (2, 1500, 32, 8, 40, 60), (2, 2500, 32, 8, 80, 120), (5, 400, 32, 6, 8, 16)):
+        n, t, v, k_utts, lo, hi = shape
+        lp, in_len, utts = seg_case(43, n, t, v, k_utts, lo, hi)
+        gt, ubs, n_cols, n_utts = _pack(cfg, utts)
+        dev = torch.from_numpy(lp).cuda()
+        one = ipfa.ctcseg_align(dev, in_len, gt, n_cols, ubs, n_utts, 0.02, flags=cfg.flags | 8)
+        many = ipfa.ctcseg_align(dev, in_len, gt, n_cols, ubs, n_utts, 0.02, flags=cfg.flags | 8 | spread)
+        for i in range(n):
+            for k in range(1, int(n_utts[i]) + 1):
+                for name in ("timing", "char_prob", "state"):
+                    a, b = getattr(one, name)[i, k - 1], getattr(many, name)[i, k - 1]
+                    m = int(in_len[i]) if name != "timing" else int(ubs[i, k]) + 1
+                    assert torch.equal(a[:m], b[:m]), (shape, name, i, k)
+                assert torch.equal(one.seg[i, k - 1, :k], many.seg[i, k - 1, :k])
+                assert int(one.term_t[i, k - 1]) == int(many.term_t[i, k - 1])
+        _compare_window(cfg, many, 0, int(n_utts[0]), lp[0, :in_len[0]], utts[0], lambda x: x.cpu().numpy())
