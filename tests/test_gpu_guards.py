@@ -118,7 +118,8 @@ def test_viterbi_writes_inside_its_buffers(guarded, shape):
 
 
 SEG_SHAPES = [(6, 60, 8, 2, 2, 4, None), (4, 400, 32, 6, 8, 16, None), (2, 1500, 40, 8, 40, 60, None),
-              (2, 600, 3000, 4, 10, 40, None), (2, 700, 32, 3, 10, 20, 256)]
+              (2, 600, 3000, 4, 10, 40, None), (2, 700, 32, 3, 10, 20, 256), (2, 1500, 32, 8, 40, 60, "spread2"),
+              (2, 2500, 32, 8, 80, 120, "spread4")]
 
 
 @pytest.mark.parametrize("shape", SEG_SHAPES)
@@ -129,7 +130,9 @@ def test_segmentation_writes_inside_its_buffers(guarded, shape):
     n, t, v, k_utts, lo, hi, window = shape
     lp, in_len, utts = seg_case(9, n, t, v, k_utts, lo, hi)
     gt, ubs, n_cols, n_utts = _pack(oseg.CtcSegmentationParameters(), utts)
-    res = ipfa.ops.ctcseg_align(_dev(lp), in_len, gt, n_cols, ubs, n_utts, 0.02, flags=2 | 8, window=window)
+    spread = {"spread2": 64, "spread4": 128}.get(window, 0)  # columns over a 2- / 4-CTA cluster
+    res = ipfa.ops.ctcseg_align(_dev(lp), in_len, gt, n_cols, ubs, n_utts, 0.02, flags=2 | 8 | spread,
+                                window=None if spread else window)
     res.status.sum().item()
     dec, anchor = ipfa.ops.anchor_select(res.seg, n_utts, np.full((n, res.seg.shape[1]), 40, np.int32),
                                          np.zeros(n, np.int32))

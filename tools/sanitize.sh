@@ -2,7 +2,7 @@
 # compute-sanitizer over a small-shape subset of the GPU tests (run under gpurun):
 #   memcheck   out-of-bounds / misaligned accesses, incl. the bulk-copy (cp.async.bulk + mbarrier) pipe
 #   racecheck  shared-memory hazards: the emission ring refilled after the in-place conversion
-#              (ctc_alpha.cu, LIN overlap path), the exchange lines, the DSMEM ring (IPFA_SEG_CLUSTER=1)
+#              (ctc_alpha.cu, LIN overlap path), the exchange lines, the cluster hand-over of the segmentation fill (IPFA_SEG_SPREAD_2 / _4)
 #   synccheck  barrier / mbarrier misuse
 # Summaries land in gpurun_out/sanitize_<tool>.txt; the last lines of each are what profiles/ keeps.
 mkdir -p gpurun_out
@@ -14,9 +14,9 @@ for tool in memcheck racecheck synccheck; do
         python -m pytest $SUBSET -m gpu -q -x -p no:cacheprovider >> gpurun_out/sanitize_$tool.txt 2>&1
     echo "exit code $?" >> gpurun_out/sanitize_$tool.txt
 done
-# the cluster experiment of the segmentation fill (distributed shared memory ring)
-echo "== racecheck, IPFA_SEG_CLUSTER=1" > gpurun_out/sanitize_cluster.txt
-IPFA_SEG_CLUSTER=1 timeout ${SAN_TIMEOUT:-900} $SAN --tool racecheck --print-limit 20 --error-exitcode 99 \
-    python -m pytest "tests/test_gpu_ctcseg.py::test_all_prefixes_vs_oracle" -m gpu -q -x -p no:cacheprovider >> gpurun_out/sanitize_cluster.txt 2>&1
+# the cluster variant of the segmentation fill (st.async hand-over through distributed shared memory)
+echo "== racecheck, segmentation fill spread over a cluster" > gpurun_out/sanitize_cluster.txt
+timeout ${SAN_TIMEOUT:-900} $SAN --tool racecheck --print-limit 20 --error-exitcode 99 \
+    python -m pytest "tests/test_gpu_ctcseg.py::test_window_columns_spread_over_a_cluster" -m gpu -q -x -p no:cacheprovider >> gpurun_out/sanitize_cluster.txt 2>&1
 echo "exit code $?" >> gpurun_out/sanitize_cluster.txt
 for f in gpurun_out/sanitize_*.txt; do echo "---- $f"; tail -8 $f; done
