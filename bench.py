@@ -228,8 +228,9 @@ class SegWorkload:
     kind = "seg"
     api = "ipfa_ctcseg_host"
 
-    def __init__(self, name, n, t, k, tokens, v, text):
+    def __init__(self, name, n, t, k, tokens, v, text, all_prefixes=True):
         self.name, self.n, self.t, self.k, self.tokens, self.v, self.text = name, n, t, k, tokens, v, text
+        self.all_prefixes = all_prefixes  # False: only the full text is aligned (word level / search on speech)
         self.set_bytes = n * t * v * 4
         self.cols = 2 + k * (tokens + 1)
         self.shape = {"windows_per_gpu": n, "T": t, "K": k, "columns": self.cols, "V": v}
@@ -268,6 +269,8 @@ class SegWorkload:
 
     def step(self, ipfa, inputs):
         lp, il, gt, nc, ub, nu, tlen, last = inputs
+        if not self.all_prefixes:
+            return ipfa.ctcseg_align(lp, il, gt, nc, ub, nu, FRAME_SECONDS, flags=2, details=False).seg
         res = ipfa.ctcseg_align(lp, il, gt, nc, ub, nu, FRAME_SECONDS, flags=2 | 8, details=False)
         dec, anchor = ipfa.anchor_select(res.seg, nu, tlen, last)
         return dec
@@ -278,7 +281,8 @@ class SegWorkload:
 
     def e2e_step(self, ipfa, host, out):
         lp, il, gt, nc, ub, nu = host
-        return ipfa.ctcseg_align_host(lp, il, gt, nc, ub, nu, FRAME_SECONDS, flags=2 | 8, details=False)
+        return ipfa.ctcseg_align_host(lp, il, gt, nc, ub, nu, FRAME_SECONDS, flags=2 | (8 if self.all_prefixes else 0),
+                                      details=False)
 
     def traffic(self):
         return int(self.set_bytes + self.n * (self.cols + self.k + 4) * 4), int(self.n * self.k * self.k * 24 +
@@ -322,6 +326,11 @@ WORKLOADS = {
     "seg": SegWorkload("seg", 256, 3500, 6, 150, 32,
                        "BASELINE configs[4] unit: anchor-loop iteration for 256 files in flight, 70 s windows "
                        "(T=3500), 6 utterances x 150 chars, all prefixes + on-device selection, V=32"),
+    "c3seg": SegWorkload("c3seg", 65536, 500, 6, 6, 32,
+                         "BASELINE configs[2] through the reference's own aligner call: 65536 word-level windows "
+                         "(word_level_alignment.py:69-103: [pre, sep, WORD, sep, post, sep]), T=500, 6 utterances x 6 "
+                         "tokens (44 columns), CTC segmentation + backtrace + scoring of the full text, V=32",
+                         all_prefixes=False),
 }
 
 
@@ -843,7 +852,7 @@ def gpu_arm(args):
                        "longest_file_minutes": c5["longest_file_minutes"], "windows": int(c5["windows"]),
                        "cells_per_s": c5["cells"] / (ms5 * 1e-3), "kernels_per_sweep": c5["launches"] / c5["steps"] / world}
         if world == 1:
-            for name in ("c2v", "c3", "c4", "c4v", "seg"):
+            for name in ("c2v", "c3", "c3seg", "c4", "c4v", "seg"):
                 w2 = WORKLOADS[name]
                 r2 = measure_resident(w2, ipfa, dev, rank, steps=5, warm=3, barrier=barrier, use_graphs=False)
                 ms2 = r2["elapsed_ms"] / r2["steps"]
