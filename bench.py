@@ -414,7 +414,7 @@ def c5_reference_arm(args):
 
 
 def c5_measure(hours_total, world, rank, dev, steps, warm, groups=32, use_graphs=True, capacity=None,
-               with_e2e=True):
+               with_e2e=True, mode=None):
     """BASELINE configs[4] on this job's ranks: ONE corpus of `hours_total` hours, its files sharded over
     the ranks (LPT by duration), every rank runs the whole anchor loop of its files.  A step = state
     reset + run until every file stops.  Collective calls (all ranks must enter).  Returns a dict of
@@ -432,7 +432,7 @@ def c5_measure(hours_total, world, rank, dev, steps, warm, groups=32, use_graphs
     for f in files:
         f.lpz = None  # the corpus holds the only copy
     sweep = sw_mod.AnchorSweep(corpus, index_duration=FRAME_SECONDS, samples_to_frames_ratio=320.0,
-                               groups=groups, use_graphs=use_graphs, capacity=capacity)
+                               groups=groups, use_graphs=use_graphs, capacity=capacity, mode=mode)
     hours_mine = sum(s.n_samples for s in specs) / 16000 / 3600.0
 
     def barrier():
@@ -497,7 +497,7 @@ def c5_measure(hours_total, world, rank, dev, steps, warm, groups=32, use_graphs
                    (float(x) for x in sums)))
     out.update(elapsed_ms=float(vals[0]), e2e_ms=float(vals[1]), iterations_max=int(vals[2]),
                files_per_rank_max=int(vals[3]), steps=steps, warm=warm, capacity=sweep.capacity,
-               iterations_rank0=st["steps"], clocks=sampler.result(), gathered=gathered,
+               iterations_rank0=st["steps"], clocks=sampler.result(), gathered=gathered, mode=sweep.mode,
                longest_file_minutes=float(max(minutes)))
     del sweep, corpus, files
     torch.cuda.empty_cache()
@@ -519,7 +519,8 @@ def c5_arm(args):
     steps = min(args.steps, 10)
     warm = max(min(args.warmup, 3), 3)
     m = c5_measure(args.hours, world, rank, dev, steps, warm, groups=args.groups, use_graphs=not args.no_graphs,
-                   capacity=[int(x) for x in args.capacity.split(',')] if args.capacity else None)
+                   capacity=[int(x) for x in args.capacity.split(',')] if args.capacity else None,
+                   mode=args.sweep_mode)
     if rank == 0:
         peak, peak_src = peaks()
         ms_per_step = m["elapsed_ms"] / steps
@@ -538,21 +539,25 @@ def c5_arm(args):
                     "files": int(m["files"]), "files_done": int(m["files_done"]), "hours": m["hours"],
                     "iterations_rank0": m["iterations_rank0"], "iterations_max": m["iterations_max"],
                     "windows": int(m["windows"]), "capacity_T_C_K_rank0": m["capacity"],
-                    "groups_per_gpu": args.groups, "cuda_graphs": not args.no_graphs, "V": 32},
+                    "sweep_mode": m["mode"],
+                    "groups_per_gpu": args.groups if m["mode"] == "lockstep" else None,
+                    "cuda_graphs": (not args.no_graphs) if m["mode"] == "lockstep" else None, "V": 32},
             "cells_per_s": m["cells"] / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
                          "kernels_per_step": m["launches"] / max(steps, 1) / world,
-                         "note": "lock-step iterations of T-serial kernels over <= files-in-flight windows; a window "
-                                 "lives on one SM, whose issue rate bounds the iteration: see DESIGN.md 5.6"},
+                         "note": "a file's windows are a serial chain of T-serial fills, each on one SM (resident mode: "
+                                 "one persistent launch, a CTA per file; lock step: three launches per iteration); the "
+                                 "longest file's chain bounds the sweep: see DESIGN.md 5.6"},
             "cpu_baseline": {"value": best["audio_h_per_s"], "unit": "audio-h/s", "cores": legs["cores"],
                              "kind": "port",
                              "sample": f"{best['files']} files of {best['minutes_per_file']:g} min, one per core, "
                                        "through oracle/sweep.py (C table fill + interpreted backtrace/loop)",
                              "oracle_port": best},
             "e2e": {"value": m["hours"] / (m["e2e_ms"] * 1e-3), "unit": "audio-h/s", "h2d_bytes_per_step": int(m["h2d"]),
-                    "d2h_bytes_per_step": int(m["d2h"]), "ms_per_step": m["e2e_ms"], "api": "ipfa_sweep_step_device"},
+                    "d2h_bytes_per_step": int(m["d2h"]), "ms_per_step": m["e2e_ms"],
+                    "api": "ipfa_sweep_resident_device" if m["mode"] == "resident" else "ipfa_sweep_step_device"},
             "gpu_launches": int(m["launches"]), "clocks": m["clocks"],
         }
         if world > 1:
@@ -850,7 +855,8 @@ def gpu_arm(args):
                        "audio_h_per_s": c5["hours"] / (ms5 * 1e-3), "files": int(c5["files"]),
                        "files_per_rank_max": c5["files_per_rank_max"], "iterations_longest_chain": c5["iterations_max"],
                        "longest_file_minutes": c5["longest_file_minutes"], "windows": int(c5["windows"]),
-                       "cells_per_s": c5["cells"] / (ms5 * 1e-3), "kernels_per_sweep": c5["launches"] / c5["steps"] / world}
+                       "cells_per_s": c5["cells"] / (ms5 * 1e-3), "kernels_per_sweep": c5["launches"] / c5["steps"] / world,
+                       "sweep_mode": c5["mode"]}
         if world == 1:
             for name in ("c2v", "c3", "c3seg", "c4", "c4v", "seg"):
                 w2 = WORKLOADS[name]
@@ -958,6 +964,8 @@ def main():
     ap.add_argument("--hours", type=float, default=100.0, help="c5: hours of audio in the corpus (all ranks)")
     ap.add_argument("--capacity", default="", help="c5: initial launch capacity T,C,K (default: from the rows)")
     ap.add_argument("--no_graphs", action="store_true", help="c5: launch every kernel from the host (no CUDA graph)")
+    ap.add_argument("--sweep_mode", default="auto", choices=["auto", "resident", "lockstep"],
+                    help="c5: one persistent launch with a CTA per file, or lock-step iterations")
     ap.add_argument("--groups", type=int, default=32, help="c5: independent file groups (streams) per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sustain", type=float, default=1.0, help="seconds of the sustained run after the K timed steps (0: none)")

@@ -402,6 +402,25 @@ int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipfa_sweep_par
                            int first_step, int n_steps, int Tmax, int Cmax, int Kmax,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* File-resident sweep: the same loop (same corpus / state / params / outputs, same rows, status words and
+ * counters) in ONE persistent launch.  A CTA takes a file from a ticket counter -- files in index order, so
+ * the caller lists the longest files first -- and runs that file's whole anchor loop on its SM: window
+ * construction, table fill, backtrace of every prefix, decision, next window, until the file leaves
+ * IPFA_SWEEP_ACTIVE; then it takes the next file.  No launch boundary and no other file sits on a file's
+ * serial chain of windows (/root/reference/src/iterative_utterance_alignment.py:67-402 is that chain), and
+ * the SMs are balanced by the queue.  Every file that is ACTIVE on entry has left ACTIVE when the launch
+ * completes (DONE, or one of the host-policy states above: handle it, set ACTIVE, call again).
+ * Covers dense emissions one bulk copy per 32-frame chunk can move (stride_t == V, V % 4 == 0, lp 16-byte
+ * aligned), the reference's default table flags (IPFA_SEG_PREAMBLE_COST_ZERO set, IPFA_SEG_BLANK_COST_ZERO
+ * clear), Cmax <= 4097, Tmax <= 8000; otherwise ipfa_sweep_resident_workspace_bytes returns 0 and the call
+ * IPFA_ERR_UNSUPPORTED: use ipfa_sweep_step_device. */
+size_t ipfa_sweep_resident_workspace_bytes(const ipfa_sweep_corpus *corpus, const ipfa_sweep_params *params,
+                                           int Tmax, int Cmax, int Kmax);
+int ipfa_sweep_resident_device(const ipfa_sweep_corpus *corpus, const ipfa_sweep_params *params,
+                               const ipfa_sweep_state *state, double *out_seg, int32_t *out_info,
+                               int Tmax, int Cmax, int Kmax, void *workspace, size_t workspace_bytes,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

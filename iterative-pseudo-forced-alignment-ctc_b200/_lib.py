@@ -68,6 +68,9 @@ _SIGNATURES = {
     "ipfa_sweep_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
     "ipfa_sweep_step_device": (c_i, [c_void, c_void, c_void, c_void, c_void, c_i, c_i, c_i, c_i, c_i,
                                      c_void, c_sz, c_void]),
+    "ipfa_sweep_resident_workspace_bytes": (c_sz, [c_void, c_void, c_i, c_i, c_i]),
+    "ipfa_sweep_resident_device": (c_i, [c_void, c_void, c_void, c_void, c_void, c_i, c_i, c_i,
+                                         c_void, c_sz, c_void]),
 }
 
 
@@ -78,7 +81,7 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(ipfa_[a-z0-9_]+)\s*\(", text)))
 
 
-ABI_VERSION = 200  # ipfa_version(): bumped whenever a signature or struct in include/ipfa_b200.h changes
+ABI_VERSION = 201  # ipfa_version(): bumped whenever a signature or struct in include/ipfa_b200.h changes
 _lib = None
 
 

@@ -30,8 +30,8 @@ struct AnchorDecision {
 };
 
 // seg_w: [Kmax][Kmax][3] segments of every prefix of one window; tl: [Kmax] text lengths.
-__device__ __forceinline__ AnchorDecision anchor_select_one(const double *__restrict__ seg_w,
-                                                            const int32_t *__restrict__ tl, int K, int Kmax,
+__device__ __forceinline__ AnchorDecision anchor_select_one(const double *seg_w,
+                                                            const int32_t *tl, int K, int Kmax,
                                                             bool is_last_window, double threshold,
                                                             int short_len) {
     const double penalty = __dmul_rn(2.0, threshold);

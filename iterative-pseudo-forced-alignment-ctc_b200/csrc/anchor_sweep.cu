@@ -35,6 +35,7 @@
 // of the file's token stream `blank, tokens(u0), blank, tokens(u1), ..., blank` behind a
 // leading -1 (prepare_token_list).
 #include "anchor_select.cuh"
+#include "ctcseg_walk.cuh"
 
 namespace ipfa {
 extern cudaError_t g_last_cuda_error;
@@ -108,14 +109,24 @@ __device__ __forceinline__ double text_to_audio(long long text_length, int sampl
 
 constexpr int kBuildThreads = 128;
 
+// CTA barrier that is safe when a warp arrives in pieces.  Thread 0 walks long single-thread policy paths
+// (with loops the compiler cannot bound) in these kernels.  ptxas does not always reconverge the warp behind
+// such a region, and __syncthreads() is the ALIGNED barrier: in the file-resident kernel lanes 1..31 of warp 0
+// reached it without lane 0, the hardware counted the warp as arrived, and lane 0 ran one barrier behind
+// everybody else from then on until the CTA deadlocked (an explicit __syncwarp() in front was elided).  The
+// non-aligned barrier.sync (this intrinsic) makes the compiler converge the warp first whenever it may be split.
+__device__ __forceinline__ void cta_sync() { __barrier_sync(0); }
+
 // :67-192 + :390-402 for file f: find the file's next window (or its terminal state) and write the
 // window descriptor.  Called by all threads of a CTA; thread 0 walks the policy, all threads copy
 // the ground-truth column.
+// `slot`: where the descriptor goes (the lock-step kernels keep one per file: slot == f; the file-resident
+// kernel one per CTA).
 __device__ __forceinline__ void build_window(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p,
-                                             const ipfa_sweep_state &s, const SweepWindows &w, int f, int Tmax,
-                                             int Cmax, int Kmax) {
+                                             const ipfa_sweep_state &s, const SweepWindows &w, int f, int slot,
+                                             int Tmax, int Cmax, int Kmax) {
     __shared__ int sh_active, sh_u0, sh_K, sh_ncols;
-    __syncthreads();
+    cta_sync();
     if (threadIdx.x == 0) {
         int active = 0, u0 = 0, K = 0, n_cols = 0, T = 0, is_last = 0;
         long long f0 = 0;
@@ -232,32 +243,70 @@ __device__ __forceinline__ void build_window(const ipfa_sweep_corpus &c, const i
             s.status[f] = status;
         }
         sh_active = active; sh_u0 = u0; sh_K = K; sh_ncols = n_cols;
-        w.in_len[f] = active ? T : 0;
-        w.n_cols[f] = active ? n_cols : 0;
-        w.n_utts[f] = active ? K : 0;
-        w.is_last[f] = is_last;
-        w.clip_start[f] = clip_start;
-        w.win_off[f] = active ? (c.file_frame0[f] + f0) * c.stride_t : 0;
+        w.in_len[slot] = active ? T : 0;
+        w.n_cols[slot] = active ? n_cols : 0;
+        w.n_utts[slot] = active ? K : 0;
+        w.is_last[slot] = is_last;
+        w.clip_start[slot] = clip_start;
+        w.win_off[slot] = active ? (c.file_frame0[f] + f0) * c.stride_t : 0;
     }
-    __syncthreads();
+    cta_sync();
     if (!sh_active) return;
     const int u0 = sh_u0, K = sh_K, n_cols = sh_ncols;
     const int slot0 = c.utt_first[f] + u0;
     const int col0 = c.utt_col[slot0];
     const int32_t *tok = c.tokens + c.file_tok0[f] + col0;
-    int32_t *gt = w.gt + (int64_t)f * Cmax;
-    for (int i = threadIdx.x; i < n_cols; i += kBuildThreads) gt[i] = (i == 0) ? -1 : tok[i - 1];
-    int32_t *ub = w.utt_begin + (int64_t)f * (Kmax + 1);
-    for (int k = threadIdx.x; k <= Kmax; k += kBuildThreads)
+    int32_t *gt = w.gt + (int64_t)slot * Cmax;
+    for (int i = threadIdx.x; i < n_cols; i += blockDim.x) gt[i] = (i == 0) ? -1 : tok[i - 1];
+    int32_t *ub = w.utt_begin + (int64_t)slot * (Kmax + 1);
+    for (int k = threadIdx.x; k <= Kmax; k += blockDim.x)
         ub[k] = 1 + c.utt_col[slot0 + min(k, K)] - col0;
-    int32_t *tl = w.text_len + (int64_t)f * Kmax;
-    for (int k = threadIdx.x; k < Kmax; k += kBuildThreads) tl[k] = (k < K) ? c.utt_chars[slot0 + k] : 0;
+    int32_t *tl = w.text_len + (int64_t)slot * Kmax;
+    for (int k = threadIdx.x; k < Kmax; k += blockDim.x) tl[k] = (k < K) ? c.utt_chars[slot0 + k] : 0;
 }
 
 __global__ void __launch_bounds__(kBuildThreads)
 sweep_build_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ipfa_sweep_state s,
                    const SweepWindows w, int Tmax, int Cmax, int Kmax) {
-    build_window(c, p, s, w, blockIdx.x, Tmax, Cmax, Kmax);
+    build_window(c, p, s, w, blockIdx.x, blockIdx.x, Tmax, Cmax, Kmax);
+}
+
+// The decision of one window and what follows from it (:221-379, :231-260, :388), one thread: accepted rows
+// -> output slots, new anchor, pending utterances, next row.  seg_w: [Kmax][Kmax][3] segments of every prefix.
+__device__ __forceinline__ void apply_decision(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p,
+                                               const ipfa_sweep_state &s, const SweepWindows &w, int f, int slot,
+                                               int K, int Kmax, const double *seg_w, double *out_seg,
+                                               int32_t *out_info) {
+    const AnchorDecision d = anchor_select_one(seg_w, w.text_len + (int64_t)slot * Kmax, min(K, Kmax), Kmax,
+                                               w.is_last[slot] != 0, p.threshold, p.short_len);
+    const int k = d.accepted;
+    const int u0 = s.utt[f];
+    const int64_t slot0 = c.utt_first[f] + u0;
+    const double clip_start = w.clip_start[slot];
+    const double penalty = __dmul_rn(2.0, p.threshold);
+    const double *seg = seg_w + (int64_t)max(k - 1, 0) * Kmax * 3;
+    const int row = s.row[f];
+    for (int u = 0; u < k; ++u) {
+        double score = round_decimals(seg[u * 3 + 2], 1.0e4);
+        if (c.utt_chars[slot0 + u] < p.short_len) score = __dadd_rn(score, penalty);  // :241
+        double *o = out_seg + (slot0 + u) * 4;
+        o[0] = clip_start;
+        o[1] = round_decimals(seg[u * 3 + 0], 100.0);
+        o[2] = round_decimals(seg[u * 3 + 1], 100.0);
+        o[3] = score;
+        out_info[(slot0 + u) * 2] = s.n_windows[f];  // ordinal of this window in its file
+        out_info[(slot0 + u) * 2 + 1] = row;
+    }
+    if (d.anchor_u == -1) s.anchor[f] = clip_start;                              // :277, :329
+    else if (d.anchor_u >= 0) s.anchor[f] = __dadd_rn(clip_start, d.anchor);     // :249
+    s.utt[f] = u0 + k;
+    s.exc[f] = 0;  // :388
+    s.row[f] = row + 1;
+    s.n_windows[f] += 1;
+    s.cells[f] += (int64_t)w.in_len[slot] * w.n_cols[slot];
+    s.frames[f] += w.in_len[slot];
+    w.decision[slot * 4 + 0] = d.accepted; w.decision[slot * 4 + 1] = d.n_iter;
+    w.decision[slot * 4 + 2] = d.outcome;  w.decision[slot * 4 + 3] = d.anchor_u;
 }
 
 // The tail of an iteration, one CTA per file: the accept / shrink / revert decision (:221-379,
@@ -269,40 +318,306 @@ sweep_tail_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ip
                   int32_t *__restrict__ out_info) {
     const int f = blockIdx.x;
     const int K = w.n_utts[f];
-    if (K > 0 && threadIdx.x == 0) {  // the file had a window this iteration
-        const double *seg_w = w.seg + (int64_t)f * Kmax * Kmax * 3;
-        const AnchorDecision d = anchor_select_one(seg_w, w.text_len + (int64_t)f * Kmax, min(K, Kmax), Kmax,
-                                                   w.is_last[f] != 0, p.threshold, p.short_len);
-        const int k = d.accepted;
-        const int u0 = s.utt[f];
-        const int64_t slot0 = c.utt_first[f] + u0;
-        const double clip_start = w.clip_start[f];
-        const double penalty = __dmul_rn(2.0, p.threshold);
-        const double *seg = seg_w + (int64_t)max(k - 1, 0) * Kmax * 3;
-        const int row = s.row[f];
-        for (int u = 0; u < k; ++u) {
-            double score = round_decimals(seg[u * 3 + 2], 1.0e4);
-            if (c.utt_chars[slot0 + u] < p.short_len) score = __dadd_rn(score, penalty);  // :241
-            double *o = out_seg + (slot0 + u) * 4;
-            o[0] = clip_start;
-            o[1] = round_decimals(seg[u * 3 + 0], 100.0);
-            o[2] = round_decimals(seg[u * 3 + 1], 100.0);
-            o[3] = score;
-            out_info[(slot0 + u) * 2] = s.n_windows[f];  // ordinal of this window in its file
-            out_info[(slot0 + u) * 2 + 1] = row;
-        }
-        if (d.anchor_u == -1) s.anchor[f] = clip_start;                              // :277, :329
-        else if (d.anchor_u >= 0) s.anchor[f] = __dadd_rn(clip_start, d.anchor);     // :249
-        s.utt[f] = u0 + k;
-        s.exc[f] = 0;  // :388
-        s.row[f] = row + 1;
-        s.n_windows[f] += 1;
-        s.cells[f] += (int64_t)w.in_len[f] * w.n_cols[f];
-        s.frames[f] += w.in_len[f];
-        w.decision[f * 4 + 0] = d.accepted; w.decision[f * 4 + 1] = d.n_iter;
-        w.decision[f * 4 + 2] = d.outcome;  w.decision[f * 4 + 3] = d.anchor_u;
+    if (K > 0 && threadIdx.x == 0)  // the file had a window this iteration
+        apply_decision(c, p, s, w, f, f, K, Kmax, w.seg + (int64_t)f * Kmax * Kmax * 3, out_seg, out_info);
+    build_window(c, p, s, w, f, f, Tmax, Cmax, Kmax);
+}
+
+
+// ===========================================================================
+// File-resident sweep: ONE persistent launch, one CTA per SM, a CTA owns a FILE.
+//
+// The lock-step kernels above pay, per iteration, three dependent launches and the longest window of
+// the group; a file's anchor loop is a serial chain of windows (the next window starts where the last
+// one was anchored), so the sweep's duration is (longest chain) x (latency of an iteration), and on top
+// of it whatever the lock step adds.  Here a CTA takes a file from a ticket counter (files longest
+// first) and runs the file's whole loop by itself -- build window -> table fill -> backtrace of every
+// prefix -> decision -> next window -- without leaving the SM: no launch boundary and no other file on
+// the chain, the window's ground truth, utterance boundaries and per-prefix segments stay in shared
+// memory, and a CTA that finishes its file takes the next one, so the SMs are balanced by a work queue
+// instead of by groups of streams.  The arithmetic is the lock-step path's: the same frame recursion and
+// transition test as ctcseg_fill_kernel (2 or 4 columns per thread, dense panel, the reference's default
+// flags), the same walk and scoring (ctcseg_walk.cuh), the same policy functions (build_window,
+// apply_decision) -- rows, state and counters are identical (tests/test_gpu_sweep.py).
+//
+// A window uses the first ceil((columns - 1) / (32 KC)) warps of the CTA for its fill (named barrier 1 over
+// exactly those warps); emission chunks of 32 frames arrive as 16-byte cp.async pieces on a ring of three stages.
+struct ResidentParams {
+    ipfa_sweep_corpus c;
+    ipfa_sweep_params p;
+    ipfa_sweep_state s;
+    SweepWindows w;          // descriptors, one slot per CTA
+    int Tmax, Cmax, Kmax, pitch;
+    uint32_t *bp;            // [slots][words_per_slot] backpointer words
+    int64_t words_per_slot;
+    int32_t *timing;         // [slots][Kmax][Cmax]
+    float *cprob;            // [slots][Kmax][Tmax]
+    int *ticket;
+    double *out_seg;
+    int32_t *out_info;
+};
+
+constexpr int kResChunk = 32;  // frames per emission chunk
+
+// Barrier `id` over the first `threads` threads of the CTA, once per frame of the fill: the ALIGNED form (one
+// BAR.SYNC, no divergence check; the non-aligned intrinsic costs a slow path per frame once a warp has ever
+// split -- measured 38 -> 50 ms on the 100 h sweep).  Its callers are warp-uniform code; resident_fill converges
+// every warp explicitly (__syncwarp) at the top of each emission chunk.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Table fill of one window by the first NTA threads of the CTA (all of them call this).
+template <int KC, int PITCH>
+__device__ __forceinline__ void resident_fill(const float *lp_win, int T, int NC, int V, int pitch_rt, int blank,
+                                              const int32_t *gt_s, const int32_t *ub_s, int K, float *ring,
+                                              float *xline, int line_len, int NTA,
+                                              uint32_t *bp, int32_t *colarg_s, int tid) {
+    constexpr int SPW = 32 / KC;
+    constexpr float kNegInf = -__builtin_huge_valf();
+    constexpr float kProbMax = -1000000000.0f;  // cdef float prob_max = -1000000000
+    const int pitch = PITCH ? PITCH : pitch_rt;
+    int col[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = 1 + tid * KC + k;
+        col[k] = (c < NC) ? gt_s[c] : blank;
     }
-    build_window(c, p, s, w, f, Tmax, Cmax, Kmax);
+    bool track = false;
+    {
+        const int c0 = 1 + tid * KC;
+        for (int u = 1; u <= K; ++u) {
+            const int c = ub_s[u];
+            track |= (c >= c0 && c < c0 + KC);
+        }
+    }
+    const bool warp_tracks = __any_sync(0xffffffffu, track);
+    const int nchunks = (T + kResChunk - 1) / kResChunk;
+    // Emission chunks (32 frames x V floats, contiguous) come in as 16-byte cp.async pieces issued by ALL the
+    // window's threads, three stages deep.  (Not the elected-thread bulk copy + mbarrier of the other kernels:
+    // in this kernel the lanes of warp 0 that polled the mbarrier were seen to keep lane 0 from ever issuing
+    // the copy -- a spin wait inside a diverged warp; cp.async.wait_group blocks in hardware instead.)
+    const int v4 = V >> 2;
+    auto issue = [&](int chunk) {
+        if (chunk < nchunks) {
+            const int rows = min(kResChunk, T - chunk * kResChunk);
+            float *dst = ring + (size_t)(chunk % 3) * kResChunk * pitch;
+            const float *src = lp_win + (int64_t)chunk * kResChunk * V;
+            const int pieces = rows * v4;
+            for (int q = tid; q < pieces; q += NTA) cp_async_16(dst + q * 4, src + q * 4);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    float val[KC], cmax[KC];
+    int carg[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) { val[k] = kProbMax; cmax[k] = kNegInf; carg[k] = -1; }
+    uint32_t word = 0;
+    int shift = 0;
+    uint32_t *bp_ptr = bp + tid;
+    int t = 0;
+    // one frame (the arithmetic of ctcseg_fill_kernel's FAST instance); returns this thread's KC decision bits
+    auto frame = [&](const float *row, const float *rd, float *wr) -> uint32_t {
+        const float eb = row[blank];
+        float ec[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) ec[k] = row[col[k]];
+        float left_[KC], up_[KC], stayp_[KC];
+        const int t_now = t;
+        const float prev = rd[tid];
+#pragma unroll
+        for (int k = KC - 1; k >= 0; --k) {
+            const float left = (k == 0) ? prev : val[k - 1];  // table[t-1, c-1]
+            const float up = val[k];                          // table[t-1, c]
+            const float sw = __fadd_rn(left, ec[k]);
+            const float stay_p = fmaxf(eb, ec[k]);
+            const float st = __fadd_rn(up, stay_p);
+            left_[k] = left; up_[k] = up; stayp_[k] = stay_p;
+            val[k] = fmaxf(sw, st);
+        }
+        ++t;
+        wr[tid + 1] = val[KC - 1];
+        named_bar_sync(1, NTA);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            // the reference backtrace's transition test, on the same fp32 values
+            const float v = val[k];
+            const float d_sw = fabsf(__fsub_rn(ec[k], __fsub_rn(v, left_[k])));
+            const float d_st = fabsf(__fsub_rn(stayp_[k], __fsub_rn(v, up_[k])));
+            bits |= (d_st > d_sw) ? (1u << k) : 0u;
+        }
+        if (warp_tracks) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (cmax[k] < val[k]) { cmax[k] = val[k]; carg[k] = t_now; }
+            }
+        }
+        return bits;
+    };
+    auto push_bits = [&](uint32_t bits) {
+        word |= bits << shift;
+        shift += KC;
+        if (shift == 32) {
+            *bp_ptr = word;
+            bp_ptr += NTA;
+            word = 0;
+            shift = 0;
+        }
+    };
+    float *line0 = xline, *line1 = xline + line_len;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        __syncwarp();              // (the per-frame barrier below is the aligned one)
+        cp_async_wait<1>();        // this thread's pieces of chunk `chunk` have landed ...
+        named_bar_sync(1, NTA);    // ... everybody's have, and everybody is done with the stage refilled next
+        issue(chunk + 2);
+        const float *panel = ring + (size_t)(chunk % 3) * kResChunk * pitch;
+        const int rows = min(kResChunk, T - chunk * kResChunk);
+        int r = 0;
+        if (chunk == 0) {
+            // t = 0: every column c >= 1 is max(switch = prob_max, stay = prob_max)
+            if (warp_tracks) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) { cmax[k] = kProbMax; carg[k] = 0; }
+            }
+            push_bits(0);
+            t = 1;
+            line0[tid + 1] = kProbMax;
+            named_bar_sync(1, NTA);
+            r = 1;
+        }
+        const float *row = panel + r * pitch;
+        // frame t reads line[(t-1)&1], writes line[t&1]; chunks are 32 frames so r has t's parity
+        while (r < rows) {
+            if (shift == 0 && !(r & 1) && r + SPW <= rows) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int f = 0; f < SPW; ++f)
+                    acc |= frame(row + f * pitch, (f & 1) ? line0 : line1, (f & 1) ? line1 : line0) << (f * KC);
+                *bp_ptr = acc;
+                bp_ptr += NTA;
+                row += SPW * pitch;
+                r += SPW;
+            } else {
+                push_bits((r & 1) ? frame(row, line0, line1) : frame(row, line1, line0));
+                row += pitch;
+                ++r;
+            }
+        }
+    }
+    if (shift != 0) *bp_ptr = word;
+    if (track) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int c = 1 + tid * KC + k;
+            for (int u = 1; u <= K; ++u)
+                if (ub_s[u] == c) colarg_s[u] = carg[k];
+        }
+    }
+    cp_async_wait<0>();
+}
+
+struct ResidentSmem {
+    size_t ring, xline, gt, walk, seg, ub, colarg, total;
+};
+template <int KC>
+__host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, int Cmax, int Kmax) {
+    ResidentSmem m;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    m.ring = take((size_t)3 * kResChunk * pitch * 4);
+    m.seg = take((size_t)Kmax * Kmax * 3 * 8);
+    m.xline = take((size_t)2 * (threads + 1) * 4);
+    m.gt = take((size_t)Cmax * 4);
+    m.walk = take((size_t)(threads / 32) * seg_walk_smem_words<KC>() * 4);
+    m.ub = take((size_t)(Kmax + 1) * 4);
+    m.colarg = take((size_t)(Kmax + 1) * 4);
+    m.total = off;
+    return m;
+}
+
+template <int KC, int PITCH, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) sweep_resident_kernel(const ResidentParams P) {
+    extern __shared__ __align__(128) unsigned char rs_smem[];
+    __shared__ int sh_file;
+    const ipfa_sweep_corpus &c = P.c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int slot = blockIdx.x;
+    const int Tmax = P.Tmax, Cmax = P.Cmax, Kmax = P.Kmax;
+    const ResidentSmem m = resident_smem<KC>(PITCH ? PITCH : P.pitch, blockDim.x, Cmax, Kmax);
+    float *ring = reinterpret_cast<float *>(rs_smem + m.ring);
+    double *seg_s = reinterpret_cast<double *>(rs_smem + m.seg);
+    float *xline = reinterpret_cast<float *>(rs_smem + m.xline);
+    int32_t *gt_s = reinterpret_cast<int32_t *>(rs_smem + m.gt);
+    uint32_t *walk_s = reinterpret_cast<uint32_t *>(rs_smem + m.walk) + (size_t)warp * seg_walk_smem_words<KC>();
+    int32_t *ub_s = reinterpret_cast<int32_t *>(rs_smem + m.ub);
+    int32_t *colarg_s = reinterpret_cast<int32_t *>(rs_smem + m.colarg);
+    const int line_len = blockDim.x + 1;
+    if (tid == 0) {
+        xline[0] = 0.0f;          // z(t) = table[t, 0] = 0 (preamble_transition_cost_zero)
+        xline[line_len] = 0.0f;
+    }
+    uint32_t *bp = P.bp + (int64_t)slot * P.words_per_slot;
+    const bool round_nearest = (P.p.seg_flags & IPFA_SEG_ROUND_NEAREST) != 0;
+    while (true) {
+        cta_sync();
+        if (tid == 0) sh_file = atomicAdd(P.ticket, 1);
+        cta_sync();
+        const int f = sh_file;
+        if (f >= c.n_files) break;
+        build_window(c, P.p, P.s, P.w, f, slot, Tmax, Cmax, Kmax);
+        while (true) {
+            cta_sync();
+            const int K = P.w.n_utts[slot];
+            if (K <= 0) break;  // the file is finished or waits for host policy (status word)
+            const int T = P.w.in_len[slot], NC = P.w.n_cols[slot];
+            const float *lp_win = c.lp + P.w.win_off[slot];
+            {
+                const int32_t *gt = P.w.gt + (int64_t)slot * Cmax;
+                for (int i = tid; i < NC; i += blockDim.x) {
+                    int g = gt[i];
+                    if (g < 0 || g >= c.V) g = c.blank;
+                    gt_s[i] = g;
+                }
+                const int32_t *ub = P.w.utt_begin + (int64_t)slot * (Kmax + 1);
+                for (int u = tid; u <= K; u += blockDim.x) { ub_s[u] = ub[u]; colarg_s[u] = -1; }
+            }
+            cta_sync();
+            const int nact = (NC - 1 + 32 * KC - 1) / (32 * KC);  // warps that own a column
+            if (warp < nact)
+                resident_fill<KC, PITCH>(lp_win, T, NC, c.V, P.pitch, c.blank, gt_s, ub_s, K, ring,
+                                         xline, line_len, 32 * nact, bp, colarg_s, tid);
+            cta_sync();
+            // every prefix of the window: one warp each (ctc_segmentation() backtrace + determine_utterance_segments)
+            for (int kslot = warp; kslot < K; kslot += nwarps) {
+                int32_t *timing = P.timing + ((int64_t)slot * Kmax + kslot) * Cmax;
+                float *cprob = P.cprob + ((int64_t)slot * Kmax + kslot) * Tmax;
+                double *seg = seg_s + (int64_t)kslot * Kmax * 3;
+                for (int t = lane; t < T; t += 32) cprob[t] = 0.0f;
+                for (int cc = lane; cc < NC; cc += 32) timing[cc] = -1;
+                const int c_end = ub_s[kslot + 1];
+                const bool feasible = T > 0 && c_end >= 1 && c_end < NC && c_end + 1 <= T;
+                const int t_term = feasible ? colarg_s[kslot + 1] : -1;
+                if (!feasible || t_term < 0) {
+                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                    for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+                    continue;
+                }
+                __syncwarp();
+                SegWalkArgs a;
+                a.lp = lp_win; a.stride_t = c.stride_t; a.T = T; a.Cmax = Cmax; a.blank = c.blank; a.NT = 32 * nact;
+                a.score_len = P.p.score_len; a.round_nearest = round_nearest; a.index_duration = P.p.index_duration;
+                a.bp_w = bp; a.ub = ub_s; a.gt_s = gt_s; a.timing = timing; a.cprob = cprob; a.state = nullptr;
+                a.seg = seg; a.raw = walk_s;
+                seg_walk_prefix<KC, true>(a, kslot, t_term, c_end, lane);
+            }
+            cta_sync();
+            if (tid == 0) apply_decision(c, P.p, P.s, P.w, f, slot, K, Kmax, seg_s, P.out_seg, P.out_info);
+            build_window(c, P.p, P.s, P.w, f, slot, Tmax, Cmax, Kmax);
+        }
+    }
 }
 
 }  // namespace
@@ -357,6 +672,145 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
         ++g_launch_count;
     }
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
+    return IPFA_OK;
+}
+
+namespace {
+struct ResidentPlan {
+    int kc, threads, pitch, slots;
+    bool fixed_pitch;
+    size_t smem;
+};
+// The file-resident kernel covers the anchor loop's own configuration: dense rows that one bulk copy per
+// chunk can move (stride_t == V, V a multiple of 4), the reference's default table flags, windows of at most
+// 4096 columns; anything else runs on the lock-step path (ipfa_sweep_step_device).
+bool resident_plan(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p, int Tmax, int Cmax, int Kmax,
+                   ResidentPlan *pl) {
+    const int table_flags = p.seg_flags & (IPFA_SEG_BLANK_COST_ZERO | IPFA_SEG_PREAMBLE_COST_ZERO);
+    if (table_flags != IPFA_SEG_PREAMBLE_COST_ZERO) return false;
+    if (c.V % 4 != 0 || c.V > 256 || c.stride_t != c.V || (reinterpret_cast<uintptr_t>(c.lp) & 15) != 0) return false;
+    if (Tmax > 8000 || Cmax - 1 > 4096) return false;
+    pl->kc = (Cmax - 1 <= 2048) ? 2 : 4;
+    const int warps = (Cmax - 1 + 32 * pl->kc - 1) / (32 * pl->kc);
+    pl->threads = 32 * (warps < 4 ? 4 : warps);
+    pl->pitch = c.V;
+    pl->fixed_pitch = (c.V == 32);
+    const ResidentSmem m = pl->kc == 2 ? resident_smem<2>(pl->pitch, pl->threads, Cmax, Kmax)
+                                       : resident_smem<4>(pl->pitch, pl->threads, Cmax, Kmax);
+    pl->smem = m.total;
+    if (pl->smem > 200 * 1024) return false;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        return false;
+    pl->slots = c.n_files < sms ? c.n_files : sms;
+    return true;
+}
+
+struct ResidentCarve {
+    SweepWindows w;
+    uint32_t *bp;
+    int64_t words_per_slot;
+    int32_t *timing;
+    float *cprob;
+    int *ticket;
+};
+size_t carve_resident(ResidentCarve *r, unsigned char *base, const ResidentPlan &pl, int Tmax, int Cmax, int Kmax) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char *q = base ? base + off : nullptr;
+        off += pad256(bytes);
+        return q;
+    };
+    const int S = pl.slots;
+    SweepWindows &w = r->w;
+    w.win_off = reinterpret_cast<int64_t *>(take((size_t)S * 8));
+    w.clip_start = reinterpret_cast<double *>(take((size_t)S * 8));
+    w.anchor_rel = nullptr;
+    w.seg = nullptr;
+    w.in_len = reinterpret_cast<int32_t *>(take((size_t)S * 4));
+    w.gt = reinterpret_cast<int32_t *>(take((size_t)S * Cmax * 4));
+    w.n_cols = reinterpret_cast<int32_t *>(take((size_t)S * 4));
+    w.utt_begin = reinterpret_cast<int32_t *>(take((size_t)S * (Kmax + 1) * 4));
+    w.n_utts = reinterpret_cast<int32_t *>(take((size_t)S * 4));
+    w.text_len = reinterpret_cast<int32_t *>(take((size_t)S * Kmax * 4));
+    w.is_last = reinterpret_cast<int32_t *>(take((size_t)S * 4));
+    w.term_t = nullptr;
+    w.win_status = nullptr;
+    w.decision = reinterpret_cast<int32_t *>(take((size_t)S * 4 * 4));
+    w.seg_ws = nullptr;
+    w.seg_ws_bytes = 0;
+    const int spw = 32 / pl.kc;
+    r->words_per_slot = (int64_t)((Tmax + spw - 1) / spw) * pl.threads;
+    r->bp = reinterpret_cast<uint32_t *>(take((size_t)S * (size_t)r->words_per_slot * 4));
+    r->timing = reinterpret_cast<int32_t *>(take((size_t)S * Kmax * (size_t)Cmax * 4));
+    r->cprob = reinterpret_cast<float *>(take((size_t)S * Kmax * (size_t)Tmax * 4));
+    r->ticket = reinterpret_cast<int *>(take(256));
+    return off;
+}
+
+template <int KC, int PITCH, int MAXT>
+cudaError_t launch_resident(const ResidentParams &P, const ResidentPlan &pl, cudaStream_t st) {
+    auto kern = sweep_resident_kernel<KC, PITCH, MAXT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<pl.slots, pl.threads, pl.smem, st>>>(P);
+    return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" size_t ipfa_sweep_resident_workspace_bytes(const ipfa_sweep_corpus *corpus, const ipfa_sweep_params *params,
+                                                      int Tmax, int Cmax, int Kmax) {
+    ResidentPlan pl;
+    if (!corpus || !params || Tmax <= 0 || Cmax <= 1 || Kmax <= 0 || corpus->n_files <= 0 ||
+        !resident_plan(*corpus, *params, Tmax, Cmax, Kmax, &pl))
+        return 0;
+    ResidentCarve r;
+    return carve_resident(&r, nullptr, pl, Tmax, Cmax, Kmax) + 256;
+}
+
+extern "C" int ipfa_sweep_resident_device(const ipfa_sweep_corpus *corpus, const ipfa_sweep_params *params,
+                                          const ipfa_sweep_state *state, double *out_seg, int32_t *out_info,
+                                          int Tmax, int Cmax, int Kmax, void *workspace, size_t workspace_bytes,
+                                          void *stream) {
+    if (!corpus || !params || !state || !out_seg || !out_info || !workspace || Tmax <= 0 || Cmax <= 1 || Kmax <= 0)
+        return IPFA_ERR_INVALID_ARG;
+    const ipfa_sweep_corpus &c = *corpus;
+    const ipfa_sweep_state &s = *state;
+    if (c.n_files == 0) return IPFA_OK;
+    if (c.n_files < 0 || !c.lp || c.V <= 0 || c.blank < 0 || c.blank >= c.V || c.stride_t < c.V || !c.file_frame0 ||
+        !c.file_frames || !c.file_samples || !c.row_first || !c.row_type || !c.row_start || !c.row_end ||
+        !c.row_utt_end || !c.utt_first || !c.utt_col || !c.utt_chars || !c.file_tok0 || !c.tokens ||
+        !s.row || !s.utt || !s.anchor || !s.prop || !s.next_ns || !s.follow_start || !s.exc || !s.status ||
+        !s.need || !s.recalc_row || !s.n_windows || !s.cells || !s.frames || !s.clip || params->sample_rate <= 0 ||
+        params->frame_shift <= 0 || !(params->samples_to_frames_ratio > 0.0) || !(params->index_duration > 0.0) ||
+        params->score_len <= 0)
+        return IPFA_ERR_INVALID_ARG;
+    ResidentPlan pl;
+    if (!resident_plan(c, *params, Tmax, Cmax, Kmax, &pl)) return IPFA_ERR_UNSUPPORTED;
+    ResidentCarve r;
+    if (workspace_bytes < carve_resident(&r, nullptr, pl, Tmax, Cmax, Kmax) + 256) return IPFA_ERR_WORKSPACE;
+    carve_resident(&r, static_cast<unsigned char *>(workspace), pl, Tmax, Cmax, Kmax);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ResidentParams P;
+    P.c = c; P.p = *params; P.s = s; P.w = r.w;
+    P.Tmax = Tmax; P.Cmax = Cmax; P.Kmax = Kmax; P.pitch = pl.pitch;
+    P.bp = r.bp; P.words_per_slot = r.words_per_slot; P.timing = r.timing; P.cprob = r.cprob; P.ticket = r.ticket;
+    P.out_seg = out_seg; P.out_info = out_info;
+    NvtxRange range("ipfa.sweep_resident (one persistent launch: files x {window, fill, backtrace, decision})");
+    cudaError_t e = cudaMemsetAsync(r.ticket, 0, 4, st);
+    if (e == cudaSuccess) {
+        const int prof_slot = profile_begin(st);
+        if (pl.kc == 2 && pl.fixed_pitch && pl.threads <= 512) e = launch_resident<2, 32, 512>(P, pl, st);
+        else if (pl.kc == 2 && pl.fixed_pitch) e = launch_resident<2, 32, 1024>(P, pl, st);
+        else if (pl.kc == 2 && pl.threads <= 512) e = launch_resident<2, 0, 512>(P, pl, st);
+        else if (pl.kc == 2) e = launch_resident<2, 0, 1024>(P, pl, st);
+        else if (pl.fixed_pitch) e = launch_resident<4, 32, 1024>(P, pl, st);
+        else e = launch_resident<4, 0, 1024>(P, pl, st);
+        profile_end(prof_slot, st);
+        ++g_launch_count;
+    }
     if (e != cudaSuccess) { g_last_cuda_error = e; return IPFA_ERR_CUDA; }
     return IPFA_OK;
 }

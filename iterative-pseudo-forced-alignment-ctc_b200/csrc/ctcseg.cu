@@ -26,6 +26,7 @@
 //    backtraced from (argmax_t table[:, utt_begin[k]], utt_begin[k]).
 // Full-table mode only (T <= min_window_size = 8000 frames); the windowed
 // variant is SURVEY.md section 8(f) rank 2.
+#include "ctcseg_walk.cuh"
 #include "emission_pipe.cuh"
 #include "lattice_shapes.cuh"
 
@@ -389,124 +390,6 @@ ctcseg_fill_kernel(const SegFillParams prm) {
     }
 }
 
-// --- numpy-order float64 sums ------------------------------------------------
-// np.ndarray.mean on a contiguous float64 vector = pairwise sum (8 accumulators
-// for n <= 128, recursive halving above) / n.  char_probs is float64 holding
-// fp32 values; mirroring the order keeps the score bit-identical.
-__device__ __forceinline__ double np_sum_upto128(const float *__restrict__ a, int n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
-        return res;
-    }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = (double)a[j];
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], (double)a[i + j]);
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, (double)a[i]);
-    return res;
-}
-__device__ __noinline__ double np_pairwise_sum_rec(const float *a, int n) {
-    if (n <= 128) return np_sum_upto128(a, n);
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(np_pairwise_sum_rec(a, n2), np_pairwise_sum_rec(a + n2, n - n2));
-}
-// the scoring windows are score_len (30) frames: the common case stays inline, register-only
-__device__ __forceinline__ double np_pairwise_sum(const float *a, int n) {
-    return (n <= 128) ? np_sum_upto128(a, n) : np_pairwise_sum_rec(a, n);
-}
-
-// determine_utterance_segments for utterances 0..n_utt-1 of one
-// alignment, one warp: start/end from the column timings, score = min over the windowed means
-// of char_probs (numpy summation order, fp64).
-__device__ __forceinline__ void score_segments(const int32_t *__restrict__ ub, const int32_t *timing,
-                                               const float *cprob, int n_utt, int T, int Cmax, double dur,
-                                               int n, bool round_nearest, int lane, double *seg) {
-    auto tm = [&](int cc) -> double {
-        if (cc < 0 || cc >= Cmax) return 0.0;
-        const int f = timing[cc];
-        return f < 0 ? 0.0 : __dmul_rn((double)f, dur);
-    };
-    for (int u = 0; u < n_utt; ++u) {
-        const int b = ub[u], e = ub[u + 1];
-        const double mid_b = __ddiv_rn(__dadd_rn(tm(b), tm(b - 1)), 2.0);
-        const double start = fmax(__dadd_rn(tm(b + 1), -0.5), mid_b);
-        const double mid_e = __ddiv_rn(__dadd_rn(tm(e), tm(e - 1)), 2.0);
-        const double end = fmin(__dadd_rn(tm(e - 1), 0.5), mid_e);
-        const double qs = __ddiv_rn(start, dur), qe = __ddiv_rn(end, dur);
-        const long long s_t = (long long)(round_nearest ? rint(qs) : floor(qs));
-        const long long e_t = (long long)(round_nearest ? rint(qe) : floor(qe));
-        double score;
-        if (e_t <= s_t) {
-            score = -10000000000.0;
-        } else if (e_t - s_t <= n) {
-            const int lo = (int)max(0LL, min(s_t, (long long)T));
-            const int hi = (int)max(0LL, min(e_t, (long long)T));
-            const int cnt = hi - lo;
-            score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
-                              : __longlong_as_double(0x7ff8000000000000LL);
-        } else {
-            // min over t of mean(char_probs[t : t + n]).  x -> x / n is monotone, so for the windows of
-            // full length the minimum of the means is the minimum of the sums divided once (the fp64
-            // division is a long instruction sequence); windows clipped by the end of the audio keep
-            // their own division.
-            double best = 0.0, best_sum = __longlong_as_double(0x7ff0000000000000LL);
-            for (long long t = s_t + lane; t < e_t - n; t += 32) {
-                const int lo = (int)max(0LL, min(t, (long long)T));
-                const int hi = (int)max(0LL, min(t + n, (long long)T));
-                const int cnt = hi - lo;
-                if (cnt <= 0) continue;
-                const double sum = np_pairwise_sum(cprob + lo, cnt);
-                if (cnt == n) best_sum = fmin(best_sum, sum);
-                else best = fmin(best, __ddiv_rn(sum, (double)cnt));
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
-                best_sum = fmin(best_sum, __shfl_xor_sync(0xffffffffu, best_sum, off));
-            }
-            if (best_sum < __longlong_as_double(0x7ff0000000000000LL))
-                best = fmin(best, __ddiv_rn(best_sum, (double)n));
-            score = best;
-        }
-        if (lane == 0) {
-            seg[u * 3] = start;
-            seg[u * 3 + 1] = end;
-            seg[u * 3 + 2] = score;
-        }
-    }
-}
-
-// Bits 0, KC, 2KC, ... of x packed into the low 32 / KC bits.
-template <int KC>
-__device__ __forceinline__ uint32_t compress_stride(uint32_t x) {
-    if constexpr (KC == 1) {
-        return x;
-    } else if constexpr (KC == 2) {
-        x &= 0x55555555u;
-        x = (x | (x >> 1)) & 0x33333333u;
-        x = (x | (x >> 2)) & 0x0f0f0f0fu;
-        x = (x | (x >> 4)) & 0x00ff00ffu;
-        return (x | (x >> 8)) & 0x0000ffffu;
-    } else if constexpr (KC == 4) {
-        x &= 0x11111111u;
-        x = (x | (x >> 3)) & 0x03030303u;
-        x = (x | (x >> 6)) & 0x000f000fu;
-        return (x | (x >> 12)) & 0x000000ffu;
-    } else {
-        x &= 0x01010101u;
-        x = (x | (x >> 7)) & 0x00030003u;
-        return (x | (x >> 14)) & 0x0000000fu;
-    }
-}
-
 struct SegBackParams {
     const float *lp;
     const int64_t *win_off;
@@ -533,14 +416,7 @@ struct SegBackParams {
 // One warp per (window, prefix).
 template <int KC>
 __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackParams prm) {
-    constexpr int SPW = 32 / KC;        // frames per word
-    constexpr int NW = KC;              // word-rows per 32-frame block
-    constexpr int NCW = 31 / KC + 2;    // thread-columns reachable inside one block
-    // staged one block ahead, before the walk of the current block is known: the start column
-    // can drop by up to 32 more columns (one switch per frame) -> 32 / KC + 1 more thread-columns
-    constexpr int NCW2 = NCW + 32 / KC + 1;
-    constexpr int NWORDS2 = NCW2 * NW;
-    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: raw[NWORDS2] + col32[NCW2*KC] + gt[Cmax]
+    extern __shared__ __align__(16) unsigned char bt_smem[];  // per warp: seg_walk_smem_words<KC>() + gt[Cmax]
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= prm.N * prm.Kmax) return;
@@ -579,127 +455,21 @@ __global__ void __launch_bounds__(128) ctcseg_backtrace_kernel(const SegBackPara
     }
     __syncwarp();
 
-    // ---- walk the 1-bit backpointers from (t_term, c_end) to (0, 0) ----------
-    // Per 32-frame block the words the walk can reach sit in shared memory.  The walk does not
-    // step frame by frame: inside a word the bits of one column are the frames at which that
-    // column was ENTERED, so "the next switch at or below frame t" is one mask + find-leading-one;
-    // the serial chain is one LDS per column change (about C steps per window instead of T).
-    // The words of block b-1 are requested before block b is walked (a superset wide enough
-    // for wherever the walk ends up), so no global-memory latency sits on the chain either.
-    // Column 0 / thread-column -1 is staged as zeros: its bits read 0 (stay).
-    const uint32_t *bp_w = prm.bp + (int64_t)w * prm.words_per_window;
-    const int NT = prm.NT;
-    constexpr int LOG2KC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
+    // the walk and the scoring are one warp's job (ctcseg_walk.cuh, shared with the file-resident sweep)
     uint32_t *raw = reinterpret_cast<uint32_t *>(bt_smem) +
-                    (size_t)(threadIdx.x >> 5) * (NWORDS2 + NCW2 * KC + prm.Cmax);
-    uint32_t *col32 = raw + NWORDS2;
-    int32_t *gt_s = reinterpret_cast<int32_t *>(col32 + NCW2 * KC);
+                    (size_t)(threadIdx.x >> 5) * (seg_walk_smem_words<KC>() + prm.Cmax);
+    int32_t *gt_s = reinterpret_cast<int32_t *>(raw + seg_walk_smem_words<KC>());
     for (int cc = lane; cc <= c_end; cc += 32) {
         int g = gt[cc];
         if (g < 0 || g >= prm.V) g = prm.blank;
         gt_s[cc] = g;
     }
-    constexpr int NQ = (NWORDS2 + 31) / 32;
-    uint32_t v[NQ];
-    auto request = [&](int blk, int i_base) {  // words of block blk, thread-columns i_base - [0, NCW2)
-#pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            const int q = lane + 32 * u;
-            const int row = q / NCW2, crel = q - row * NCW2;
-            const int col = i_base - crel;
-            const int wrow = blk * NW + row;
-            v[u] = 0;
-            if (q < NWORDS2 && col >= 0 && wrow * SPW < T) v[u] = __ldg(bp_w + (int64_t)wrow * NT + col);
-        }
-    };
-    // per-frame outputs of a block are stored one block late: their emission gathers are issued
-    // before the next block's walk and consumed after it
-    int pend_t = -1, pend_c = 0, pend_sw = 0;
-    float pend_eb = 0.0f, pend_ec = 0.0f;
-    int lc = c_end - 1;  // lattice column (table column - 1); -1 is table column 0
-    int i_base = lc >> LOG2KC;  // arithmetic shift: -1 -> thread-column -1
-    request(t_term >> 5, i_base);
-    for (int blk = t_term >> 5; blk >= 0; --blk) {
-        const int t_hi = min(t_term, blk * 32 + 31);
-        const int t_lo = blk * 32;
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            const int q = lane + 32 * u;
-            if (q < NWORDS2) raw[q] = v[u];
-        }
-        __syncwarp();
-        const int i_cur = i_base;
-        i_base = lc >> LOG2KC;
-        if (blk > 0) request(blk - 1, i_base);  // in flight during this block's walk
-        if (pend_t >= 0) {
-            const float *row = lp + (int64_t)pend_t * prm.stride_t;
-            pend_eb = row[prm.blank];
-            pend_ec = row[gt_s[pend_c]];
-        }
-        // per-column words of the whole block: col32[d] bit f = "column top - d was entered at frame
-        // t_lo + f" (the KC-strided bits of the NW word-rows compressed and concatenated)
-        const int top = i_cur * KC + (KC - 1);  // lattice column of col32[0]
-        for (int d = lane; d < NCW2 * KC; d += 32) {
-            const int crel = d >> LOG2KC, k = (KC - 1) - (d & (KC - 1));
-            uint32_t bits = 0;
-#pragma unroll
-            for (int row = 0; row < NW; ++row)
-                bits |= compress_stride<KC>(raw[row * NCW2 + crel] >> k) << (row * SPW);
-            col32[d] = bits;
-        }
-        __syncwarp();
-        // switch frames of this block as a 32-bit mask (bit = frame - t_lo): the serial chain is
-        // one LDS + mask + find-leading-one per column change
-        uint32_t S = 0;
-        const int c_hi = lc + 1;  // table column at frame t_hi
-        {
-            // frame 0 of the table is never visited: the reference's loop ends at (0, 0)
-            const uint32_t keep = (blk == 0) ? ~1u : 0xffffffffu;
-            int d = top - lc;
-            uint32_t below = ((2u << (t_hi - t_lo)) - 1u) & keep;  // frames <= the current one
-            while (true) {
-                const uint32_t m = col32[d] & below;
-                if (m == 0) break;                 // stays down to the first frame of the block
-                const int f = 31 - __clz(m);       // the column was entered at this frame
-                S |= 1u << f;
-                ++d;
-                below &= (1u << f) - 1u;
-                if (below == 0) break;
-            }
-            lc = top - d;
-        }
-        // the previous block's outputs (their gathers had this block's walk to arrive)
-        if (pend_t >= 0) {
-            const float p = (pend_c == 0) ? pend_eb : (pend_sw ? pend_ec : fmaxf(pend_eb, pend_ec));
-            cprob[pend_t] = p;
-            if (pend_sw && pend_c > 0) timing[pend_c] = pend_t;
-            if (state) state[pend_t] = pend_sw ? pend_c : -1;
-        }
-        // lane = frame: column at frame t = c_hi - (switches at later frames of the block)
-        const int t = t_lo + lane;
-        pend_t = -1;
-        if (t <= t_hi && t >= 1) {
-            pend_t = t;
-            pend_c = c_hi - __popc((S >> lane) >> 1);
-            pend_sw = (S >> lane) & 1u;
-        }
-    }
-    if (pend_t >= 0) {
-        const float *row = lp + (int64_t)pend_t * prm.stride_t;
-        pend_eb = row[prm.blank];
-        pend_ec = row[gt_s[pend_c]];
-        const float p = (pend_c == 0) ? pend_eb : (pend_sw ? pend_ec : fmaxf(pend_eb, pend_ec));
-        cprob[pend_t] = p;
-        if (pend_sw && pend_c > 0) timing[pend_c] = pend_t;
-        if (state) state[pend_t] = pend_sw ? pend_c : -1;
-    }
-    __syncwarp();
-    __threadfence_block();
-
-    // ---- determine_utterance_segments ---------------------------------------
-    score_segments(ub, timing, cprob, kslot + 1, T, prm.Cmax, prm.index_duration, prm.score_len,
-                   (prm.flags & IPFA_SEG_ROUND_NEAREST) != 0, lane, seg);
+    SegWalkArgs a;
+    a.lp = lp; a.stride_t = prm.stride_t; a.T = T; a.Cmax = prm.Cmax; a.blank = prm.blank; a.NT = prm.NT;
+    a.score_len = prm.score_len; a.round_nearest = (prm.flags & IPFA_SEG_ROUND_NEAREST) != 0;
+    a.index_duration = prm.index_duration; a.bp_w = prm.bp + (int64_t)w * prm.words_per_window;
+    a.ub = ub; a.gt_s = gt_s; a.timing = timing; a.cprob = cprob; a.state = state; a.seg = seg; a.raw = raw;
+    seg_walk_prefix<KC, false>(a, kslot, t_term, c_end, lane);
 }
 
 // ===========================================================================

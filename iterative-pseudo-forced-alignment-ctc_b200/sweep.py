@@ -21,6 +21,8 @@ from ._lib import check, lib
 ACTIVE, DONE, STOP_WINDOW, STOP_EXCEPTIONS, NEEDS_RECALC, CAPACITY, NO_AUDIO = range(7)
 STATUS_NAMES = ["active", "done", "window_to_stop", "exceptions_limit", "needs_recalc", "capacity", "no_audio"]
 
+DEFAULT_MODE = "auto"   # AnchorSweep(mode=None): "auto" | "resident" | "lockstep"
+
 _vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 
 
@@ -167,7 +169,14 @@ class SweepCorpus:
 class AnchorSweep:
     """Runs the anchor loop of every file of a :class:`SweepCorpus` on its device.
 
-    ``groups``: independent lock-step groups of files, each on its own stream with its own launch
+    ``mode``: ``"resident"`` -- one persistent launch, a CTA per file, every file runs its own chain of
+    windows on one SM and the SMs take files from a queue (``ipfa_sweep_resident_device``; list the files
+    longest first); ``"lockstep"`` -- one window of every active file per iteration, three launches per
+    iteration (``ipfa_sweep_step_device``); ``"auto"`` (default): resident whenever the library supports
+    the corpus (dense emissions with ``V % 4 == 0``, default table flags), lock step otherwise.  Both
+    produce the same rows, status words and counters.
+
+    Lock-step mode only: ``groups``: independent lock-step groups of files, each on its own stream with its own launch
     capacity; ``use_graphs``: the launches of ``steps_per_poll`` iterations of all groups are
     captured once into a CUDA graph and replayed (the sweep is a chain of short dependent kernels,
     so with many groups the host's launch rate would otherwise bound it)."""
@@ -175,7 +184,10 @@ class AnchorSweep:
     def __init__(self, corpus, index_duration, samples_to_frames_ratio, frame_shift=None, sample_rate=16000,
                  threshold=-2.0, short_utterance_len=30, max_window_size=70.0, window_to_stop=500.0,
                  min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, scoring_length=30, seg_flags=2,
-                 capacity=None, groups=1, use_graphs=True):
+                 capacity=None, groups=1, use_graphs=True, mode=None):
+        mode = DEFAULT_MODE if mode is None else mode
+        if mode not in ("auto", "resident", "lockstep"):
+            raise ValueError(f"mode {mode!r}")
         self.corpus = corpus
         self.groups = int(groups)
         self.use_graphs = bool(use_graphs)
@@ -190,6 +202,17 @@ class AnchorSweep:
         self.params = p
         self.state = None
         self.reset()
+        self.mode = mode
+        if mode != "lockstep":
+            # the resident kernel has one capacity for all files; "auto" asks the library
+            probe = list(capacity) if capacity else self._initial_capacity(0, len(corpus.files))
+            supported = self._resident_bytes(probe) > 0
+            if mode == "resident" and not supported:
+                raise ValueError("the file-resident sweep does not cover this corpus (see ipfa_b200.h); "
+                                 "use mode='lockstep'")
+            self.mode = "resident" if supported else "lockstep"
+        if self.mode == "resident":
+            self.groups = 1
         self.ranges = self._group_ranges()
         first = list(capacity) if capacity else None
         self.capacities = [list(first) if first else self._initial_capacity(lo, hi) for lo, hi in self.ranges]
@@ -333,12 +356,48 @@ class AnchorSweep:
                 self.kernel_launches += self._graph_launches
         self.steps += n_steps
 
+    # ------------------------------------------------------------------ file-resident mode
+    def _resident_bytes(self, cap):
+        cs, _ = self._structs(0, len(self.corpus.files))
+        return int(lib().ipfa_sweep_resident_workspace_bytes(ctypes.byref(cs), ctypes.byref(self.params),
+                                                             int(cap[0]), int(cap[1]), int(cap[2])))
+
+    def run_resident(self):
+        """One persistent launch: every ACTIVE file runs until it leaves ACTIVE.  Asynchronous on the
+        current stream."""
+        c = self.corpus
+        cap = self.capacities[0]
+        nbytes = self._resident_bytes(cap)
+        if nbytes <= 0:   # a window outgrew the resident kernel's range: the lock-step path takes over
+            self.mode = "lockstep"
+            return False
+        if self._ws_cap[0] != ("resident",) + tuple(cap):
+            self._ws[0] = None
+            self._ws[0] = torch.empty(nbytes, dtype=torch.uint8, device=c.device)
+            self._ws_cap[0] = ("resident",) + tuple(cap)
+        ws = self._ws[0]
+        cs, ss = self._structs(0, len(c.files))
+        with torch.cuda.device(c.device):
+            before = lib().ipfa_launch_count()
+            rc = lib().ipfa_sweep_resident_device(
+                ctypes.byref(cs), ctypes.byref(self.params), ctypes.byref(ss), self.out_seg.data_ptr(),
+                self.out_info.data_ptr(), cap[0], cap[1], cap[2], ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream(c.device).cuda_stream)
+            check(rc, "ipfa_sweep_resident_device")
+            self.kernel_launches += lib().ipfa_launch_count() - before
+        return True
+
     def run(self, steps_per_poll=8, max_steps=100000, recalc_fn=None):
         """Iterate until no file is active.  ``recalc_fn(sweep, file_index)`` may re-spread the rows
         of a file that stopped with NEEDS_RECALC (the reference's ``fix_text_to_time_proportion``,
         :127-146) and return True to resume it.  Returns the per-file status array (host)."""
         while self.steps < max_steps:
-            self.step(steps_per_poll)
+            if self.mode == "resident":
+                if not self.run_resident():
+                    continue
+                self.steps = int(self.state["n_windows"].max().item())  # windows of the longest chain
+            else:
+                self.step(steps_per_poll)
             status = self.state["status"].cpu().numpy()
             if (status == CAPACITY).any():
                 need = self.state["need"].cpu().numpy()
@@ -459,7 +518,7 @@ def dataframe_recalc(frames, vads, real_lengths, logger=None):
 
 def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, threshold=-2.0, short_utterance_len=30,
                          max_words_sequence=24, max_window_size=70.0, window_to_stop=500.0,
-                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, groups=None):
+                         min_text_to_audio_prop=0.8, max_text_to_audio_prop_exec=10, groups=None, mode=None):
     """Anchor loop of several files with file-level emissions resident on the GPU.
 
     ``jobs``: list of ``(audio_path, file_df, vad_file_df)`` like the arguments of
@@ -495,7 +554,7 @@ def align_files_resident(asr_model, aligner, jobs, samples_to_frames_ratio, thre
                         window_to_stop=window_to_stop, min_text_to_audio_prop=min_text_to_audio_prop,
                         max_text_to_audio_prop_exec=max_text_to_audio_prop_exec,
                         scoring_length=aligner.config.score_min_mean_over_L, seg_flags=aligner.config.flags,
-                        groups=groups)
+                        groups=groups, mode=mode)
     status = sweep.run(recalc_fn=dataframe_recalc(frames, vads, lengths))
     rows = sweep.file_rows()
     inverse = {src: pos for pos, src in enumerate(order)}  # back to the order of `jobs`

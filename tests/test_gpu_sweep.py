@@ -24,6 +24,14 @@ sweep = importlib.import_module(PKG + ".sweep")
 stub = importlib.import_module(PKG + ".stub_asr")
 
 
+@pytest.fixture(autouse=True, params=["resident", "lockstep"])
+def sweep_mode(request, monkeypatch):
+    """Every test of this module runs on both device paths: the file-resident persistent kernel and the
+    lock-step iterations.  (The synthetic corpora have V = 32 dense emissions, which both cover.)"""
+    monkeypatch.setattr(sweep, "DEFAULT_MODE", request.param)
+    return request.param
+
+
 class ExactASR(ScriptedASR):
     """The synthetic 'audio' carries its absolute sample index exactly (float64)."""
 

@@ -80,10 +80,11 @@ def one_case(kind, rng, counts):
             files = [sw.SweepFile(sp.file_id, sp.audio_path, lp_, sp.n_samples, sp.rows) for sp, lp_ in zip(specs, lps)]
             run = sw.AnchorSweep(sw.SweepCorpus(files, stub.CharTokenizer()), index_duration=0.02,
                                  samples_to_frames_ratio=320.0, groups=int(rng.integers(1, 3)),
-                                 use_graphs=bool(rng.random() < 0.5), **kw)
+                                 use_graphs=bool(rng.random() < 0.5),
+                                 mode=str(rng.choice(["resident", "lockstep"])), **kw)
             status = run.run(steps_per_poll=int(rng.choice([1, 4, 16])))
             got = run.file_rows()
-            desc = f"sweep files={n_files} {kw}"
+            desc = f"sweep files={n_files} mode={run.mode} {kw}"
             ok = True
             for f, (sp, lp_) in enumerate(zip(specs, lps)):
                 ref_rows, ref_status, _ = osweep.sweep_file(sp.file_id, sp.audio_path, lp_.cpu().numpy(), sp.n_samples,
