@@ -34,6 +34,9 @@
 // utterances" = [utt, row_utt_end[row]).  Its ground-truth column is therefore a slice
 // of the file's token stream `blank, tokens(u0), blank, tokens(u1), ..., blank` behind a
 // leading -1 (prepare_token_list).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "anchor_select.cuh"
 #include "ctcseg_walk.cuh"
 
@@ -347,14 +350,15 @@ struct ResidentParams {
     ipfa_sweep_params p;
     ipfa_sweep_state s;
     SweepWindows w;          // descriptors, one slot per CTA
-    int Tmax, Cmax, Kmax, pitch;
-    uint32_t *bp;            // [slots][words_per_slot] backpointer words
+    int Tmax, Cmax, Kmax, pitch, bits_bytes;
+    uint32_t *bp;            // [slots][words_per_slot] backpointer words (windows too large for shared memory)
     int64_t words_per_slot;
     int32_t *timing;         // [slots][Kmax][Cmax]
     float *cprob;            // [slots][Kmax][Tmax]
     int *ticket;
     double *out_seg;
     int32_t *out_info;
+    int phases;              // IPFA_SWEEP_PHASES=1 (tuning): CTA 0 prints the cycles it spent in each phase
 };
 
 constexpr int kResChunk = 32;  // frames per emission chunk
@@ -520,10 +524,10 @@ __device__ __forceinline__ void resident_fill(const float *lp_win, int T, int NC
 }
 
 struct ResidentSmem {
-    size_t ring, xline, gt, walk, seg, ub, colarg, total;
+    size_t ring, xline, gt, walk, seg, ub, colarg, bits, total;
 };
 template <int KC>
-__host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, int Cmax, int Kmax) {
+__host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, int Cmax, int Kmax, int bits_bytes) {
     ResidentSmem m;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
@@ -534,19 +538,20 @@ __host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, in
     m.walk = take((size_t)(threads / 32) * seg_walk_smem_words<KC>() * 4);
     m.ub = take((size_t)(Kmax + 1) * 4);
     m.colarg = take((size_t)(Kmax + 1) * 4);
+    m.bits = take((size_t)bits_bytes);  // backpointer words of the window in flight, when they fit
     m.total = off;
     return m;
 }
 
 template <int KC, int PITCH, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) sweep_resident_kernel(const ResidentParams P) {
+__global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentParams P) {
     extern __shared__ __align__(128) unsigned char rs_smem[];
     __shared__ int sh_file;
     const ipfa_sweep_corpus &c = P.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int slot = blockIdx.x;
     const int Tmax = P.Tmax, Cmax = P.Cmax, Kmax = P.Kmax;
-    const ResidentSmem m = resident_smem<KC>(PITCH ? PITCH : P.pitch, blockDim.x, Cmax, Kmax);
+    const ResidentSmem m = resident_smem<KC>(PITCH ? PITCH : P.pitch, blockDim.x, Cmax, Kmax, P.bits_bytes);
     float *ring = reinterpret_cast<float *>(rs_smem + m.ring);
     double *seg_s = reinterpret_cast<double *>(rs_smem + m.seg);
     float *xline = reinterpret_cast<float *>(rs_smem + m.xline);
@@ -554,22 +559,38 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_resident_kernel(const ResidentP
     uint32_t *walk_s = reinterpret_cast<uint32_t *>(rs_smem + m.walk) + (size_t)warp * seg_walk_smem_words<KC>();
     int32_t *ub_s = reinterpret_cast<int32_t *>(rs_smem + m.ub);
     int32_t *colarg_s = reinterpret_cast<int32_t *>(rs_smem + m.colarg);
+    uint32_t *bits_s = reinterpret_cast<uint32_t *>(rs_smem + m.bits);
     const int line_len = blockDim.x + 1;
     if (tid == 0) {
         xline[0] = 0.0f;          // z(t) = table[t, 0] = 0 (preamble_transition_cost_zero)
         xline[line_len] = 0.0f;
     }
-    uint32_t *bp = P.bp + (int64_t)slot * P.words_per_slot;
+    uint32_t *bp_global = P.bp + (int64_t)slot * P.words_per_slot;
     const bool round_nearest = (P.p.seg_flags & IPFA_SEG_ROUND_NEAREST) != 0;
+    const int slice_cap = P.bits_bytes / 4 / nwarps;
+    long long ph_walk = 0, ph_score = 0;
+    long long ph[5] = {0, 0, 0, 0, 0}, ph_t = 0;  // phase cycles of thread 0: window, staging, fill, walk, decision
+    int ph_n = 0;
+    const bool timed = P.phases && tid == 0 && slot == 0;
+#define IPFA_PHASE(i) do { if (timed) { const long long now_ = clock64(); ph[i] += now_ - ph_t; ph_t = now_; } } while (0)
     while (true) {
         cta_sync();
         if (tid == 0) sh_file = atomicAdd(P.ticket, 1);
         cta_sync();
         const int f = sh_file;
-        if (f >= c.n_files) break;
+        if (f >= c.n_files) {
+            if (timed)
+                printf("ipfa resident CTA 0: %d windows; cycles per window: next window %lld, staging %lld, fill %lld, "
+                       "backtrace+scoring %lld (walks %lld, scoring %lld), decision %lld\n", ph_n,
+                       ph[0] / max(ph_n, 1), ph[1] / max(ph_n, 1), ph[2] / max(ph_n, 1), ph[3] / max(ph_n, 1),
+                       ph_walk / max(ph_n, 1), ph_score / max(ph_n, 1), ph[4] / max(ph_n, 1));
+            break;
+        }
+        if (timed) ph_t = clock64();
         build_window(c, P.p, P.s, P.w, f, slot, Tmax, Cmax, Kmax);
         while (true) {
             cta_sync();
+            IPFA_PHASE(0);
             const int K = P.w.n_utts[slot];
             if (K <= 0) break;  // the file is finished or waits for host policy (status word)
             const int T = P.w.in_len[slot], NC = P.w.n_cols[slot];
@@ -585,11 +606,16 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_resident_kernel(const ResidentP
                 for (int u = tid; u <= K; u += blockDim.x) { ub_s[u] = ub[u]; colarg_s[u] = -1; }
             }
             cta_sync();
+            IPFA_PHASE(1);
+            ++ph_n;
             const int nact = (NC - 1 + 32 * KC - 1) / (32 * KC);  // warps that own a column
+            // the window's backpointer words: shared memory when they fit (the walks then have no L2 latency to hide)
+            uint32_t *bp = ((int64_t)((T + 32 / KC - 1) / (32 / KC)) * 32 * nact * 4 <= P.bits_bytes) ? bits_s : bp_global;
             if (warp < nact)
                 resident_fill<KC, PITCH>(lp_win, T, NC, c.V, P.pitch, c.blank, gt_s, ub_s, K, ring,
                                          xline, line_len, 32 * nact, bp, colarg_s, tid);
             cta_sync();
+            IPFA_PHASE(2);
             // every prefix of the window: one warp each (ctc_segmentation() backtrace + determine_utterance_segments)
             for (int kslot = warp; kslot < K; kslot += nwarps) {
                 int32_t *timing = P.timing + ((int64_t)slot * Kmax + kslot) * Cmax;
@@ -610,11 +636,32 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_resident_kernel(const ResidentP
                 a.lp = lp_win; a.stride_t = c.stride_t; a.T = T; a.Cmax = Cmax; a.blank = c.blank; a.NT = 32 * nact;
                 a.score_len = P.p.score_len; a.round_nearest = round_nearest; a.index_duration = P.p.index_duration;
                 a.bp_w = bp; a.ub = ub_s; a.gt_s = gt_s; a.timing = timing; a.cprob = cprob; a.state = nullptr;
-                a.seg = seg; a.raw = walk_s;
+                a.seg = seg; a.raw = walk_s; a.skip_scoring = true;
                 seg_walk_prefix<KC, true>(a, kslot, t_term, c_end, lane);
+                if (lane == 0) colarg_s[kslot + 1] |= 0x40000000;  // walked: its utterances are scored below
             }
             cta_sync();
+            long long t_walks = 0;
+            if (timed) { t_walks = clock64(); ph_walk += t_walks - ph_t; }
+            // determine_utterance_segments: utterance u of prefix k is its own task, spread over ALL the warps
+            // (the longest prefix alone would score its k utterances one after the other)
+            for (int task = warp; task < K * (K + 1) / 2; task += nwarps) {
+                int k = 0;
+                while ((k + 1) * (k + 2) / 2 <= task) ++k;  // prefix slot: tasks k(k+1)/2 .. + k
+                const int u = task - k * (k + 1) / 2;
+                if (!(colarg_s[k + 1] & 0x40000000) || colarg_s[k + 1] < 0) continue;  // infeasible prefix: NaN rows are in
+                score_one_segment(ub_s, P.timing + ((int64_t)slot * Kmax + k) * Cmax,
+                                  P.cprob + ((int64_t)slot * Kmax + k) * Tmax, u, T, Cmax, P.p.index_duration,
+                                  P.p.score_len, round_nearest, lane, seg_s + (int64_t)k * Kmax * 3,
+                                  seg_scratch<KC>(walk_s),
+                                  // (the walks are over: the backpointer area is this warp's to stage char_probs in)
+                                  reinterpret_cast<float *>(bits_s) + (size_t)warp * slice_cap, slice_cap);
+            }
+            cta_sync();
+            if (timed) ph_score += clock64() - t_walks;
+            IPFA_PHASE(3);
             if (tid == 0) apply_decision(c, P.p, P.s, P.w, f, slot, K, Kmax, seg_s, P.out_seg, P.out_info);
+            IPFA_PHASE(4);
             build_window(c, P.p, P.s, P.w, f, slot, Tmax, Cmax, Kmax);
         }
     }
@@ -678,7 +725,7 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
 
 namespace {
 struct ResidentPlan {
-    int kc, threads, pitch, slots;
+    int kc, threads, pitch, slots, bits_bytes;
     bool fixed_pitch;
     size_t smem;
 };
@@ -691,15 +738,31 @@ bool resident_plan(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p, int T
     if (table_flags != IPFA_SEG_PREAMBLE_COST_ZERO) return false;
     if (c.V % 4 != 0 || c.V > 256 || c.stride_t != c.V || (reinterpret_cast<uintptr_t>(c.lp) & 15) != 0) return false;
     if (Tmax > 8000 || Cmax - 1 > 4096) return false;
-    pl->kc = (Cmax - 1 <= 2048) ? 2 : 4;
+    // two columns per thread while that keeps the CTA at 16 warps (the 128-register instances), four beyond:
+    // measured on the 100 h corpus (windows up to 1182 columns) 36.7 ms with four against 44.9 ms with two
+    pl->kc = (Cmax - 1 <= 1024) ? 2 : 4;
+    if (const char *e = tuning("IPFA_SWEEP_KC")) {  // tuning: columns per thread
+        const int v = atoi(e);
+        if ((v == 2 || v == 4) && Cmax - 1 <= v * 1024) pl->kc = v;
+    }
     const int warps = (Cmax - 1 + 32 * pl->kc - 1) / (32 * pl->kc);
     pl->threads = 32 * (warps < 4 ? 4 : warps);
     pl->pitch = c.V;
     pl->fixed_pitch = (c.V == 32);
-    const ResidentSmem m = pl->kc == 2 ? resident_smem<2>(pl->pitch, pl->threads, Cmax, Kmax)
-                                       : resident_smem<4>(pl->pitch, pl->threads, Cmax, Kmax);
+    {
+        // shared memory for the backpointer words: the launch capacity's worth, at most 160 KB.  (More than half
+        // of an SM's shared memory also keeps every CTA on an SM of its own: a file's chain is latency bound and
+        // two chains on one SM were measured slower than one after the other.)
+        const int spw = 32 / pl->kc;
+        const int64_t want = (int64_t)((Tmax + spw - 1) / spw) * pl->threads * 4;
+        const int64_t room = 160 * 1024;
+        pl->bits_bytes = (int)((((want < room ? want : room) + 15) / 16) * 16);
+        if (pl->bits_bytes < 116 * 1024) pl->bits_bytes = 116 * 1024;
+    }
+    const ResidentSmem m = pl->kc == 2 ? resident_smem<2>(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes)
+                                       : resident_smem<4>(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes);
     pl->smem = m.total;
-    if (pl->smem > 200 * 1024) return false;
+    if (pl->smem > 225 * 1024) return false;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
@@ -795,17 +858,20 @@ extern "C" int ipfa_sweep_resident_device(const ipfa_sweep_corpus *corpus, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ResidentParams P;
     P.c = c; P.p = *params; P.s = s; P.w = r.w;
-    P.Tmax = Tmax; P.Cmax = Cmax; P.Kmax = Kmax; P.pitch = pl.pitch;
+    P.Tmax = Tmax; P.Cmax = Cmax; P.Kmax = Kmax; P.pitch = pl.pitch; P.bits_bytes = pl.bits_bytes;
     P.bp = r.bp; P.words_per_slot = r.words_per_slot; P.timing = r.timing; P.cprob = r.cprob; P.ticket = r.ticket;
     P.out_seg = out_seg; P.out_info = out_info;
+    P.phases = tuning("IPFA_SWEEP_PHASES") != nullptr;
     NvtxRange range("ipfa.sweep_resident (one persistent launch: files x {window, fill, backtrace, decision})");
     cudaError_t e = cudaMemsetAsync(r.ticket, 0, 4, st);
     if (e == cudaSuccess) {
         const int prof_slot = profile_begin(st);
-        if (pl.kc == 2 && pl.fixed_pitch && pl.threads <= 512) e = launch_resident<2, 32, 512>(P, pl, st);
+        const bool wide = pl.threads > 512;  // the 64-register instances
+        if (pl.kc == 2 && pl.fixed_pitch && !wide) e = launch_resident<2, 32, 512>(P, pl, st);
         else if (pl.kc == 2 && pl.fixed_pitch) e = launch_resident<2, 32, 1024>(P, pl, st);
-        else if (pl.kc == 2 && pl.threads <= 512) e = launch_resident<2, 0, 512>(P, pl, st);
+        else if (pl.kc == 2 && !wide) e = launch_resident<2, 0, 512>(P, pl, st);
         else if (pl.kc == 2) e = launch_resident<2, 0, 1024>(P, pl, st);
+        else if (pl.fixed_pitch && !wide) e = launch_resident<4, 32, 512>(P, pl, st);
         else if (pl.fixed_pitch) e = launch_resident<4, 32, 1024>(P, pl, st);
         else e = launch_resident<4, 0, 1024>(P, pl, st);
         profile_end(prof_slot, st);

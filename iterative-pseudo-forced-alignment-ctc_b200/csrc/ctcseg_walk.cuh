@@ -42,65 +42,121 @@ __device__ __forceinline__ double np_pairwise_sum(const float *a, int n) {
     return (n <= 128) ? np_sum_upto128(a, n) : np_pairwise_sum_rec(a, n);
 }
 
-// determine_utterance_segments for utterances 0..n_utt-1 of one
-// alignment, one warp: start/end from the column timings, score = min over the windowed means
-// of char_probs (numpy summation order, fp64).
-__device__ __forceinline__ void score_segments(const int32_t *__restrict__ ub, const int32_t *timing,
-                                               const float *cprob, int n_utt, int T, int Cmax, double dur,
-                                               int n, bool round_nearest, int lane, double *seg) {
+// determine_utterance_segments for utterance u of one alignment, one warp:
+// start/end from the column timings, score = min over the windowed means of char_probs (numpy summation
+// order, fp64).
+// `scratch` (nullable): 40 doubles of this warp's shared memory.  With it, the sliding windows of full length
+// share their partial sums: numpy's pairwise sum of n <= 128 values keeps eight accumulators, r[j] = a[j] +
+// a[j+8] + a[j+16] + ... (blocks of eight, in order), combines them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and adds
+// the n % 8 tail values one by one.  r[j] of the window starting at t is S[t+j] with S[x] = a[x] + a[x+8] + ...
+// (the same additions in the same order), so 32 neighbouring windows need 39 values of S instead of 32 x 8
+// accumulators: identical bits, about half the loads and additions.
+// `slice` (nullable, `slice_cap` floats of this warp's shared memory): the utterance's stretch of char_probs is
+// copied there first, so that the window sums read shared memory instead of paying a cache round trip per step.
+__device__ __forceinline__ void score_one_segment(const int32_t *ub, const int32_t *timing, const float *cprob_g, int u,
+                                                  int T, int Cmax, double dur, int n, bool round_nearest, int lane,
+                                                  double *seg, double *scratch, float *slice = nullptr,
+                                                  int slice_cap = 0) {
+    const float *cprob = cprob_g;
     auto tm = [&](int cc) -> double {
         if (cc < 0 || cc >= Cmax) return 0.0;
         const int f = timing[cc];
         return f < 0 ? 0.0 : __dmul_rn((double)f, dur);
     };
-    for (int u = 0; u < n_utt; ++u) {
-        const int b = ub[u], e = ub[u + 1];
-        const double mid_b = __ddiv_rn(__dadd_rn(tm(b), tm(b - 1)), 2.0);
-        const double start = fmax(__dadd_rn(tm(b + 1), -0.5), mid_b);
-        const double mid_e = __ddiv_rn(__dadd_rn(tm(e), tm(e - 1)), 2.0);
-        const double end = fmin(__dadd_rn(tm(e - 1), 0.5), mid_e);
-        const double qs = __ddiv_rn(start, dur), qe = __ddiv_rn(end, dur);
-        const long long s_t = (long long)(round_nearest ? rint(qs) : floor(qs));
-        const long long e_t = (long long)(round_nearest ? rint(qe) : floor(qe));
-        double score;
-        if (e_t <= s_t) {
-            score = -10000000000.0;
-        } else if (e_t - s_t <= n) {
-            const int lo = (int)max(0LL, min(s_t, (long long)T));
-            const int hi = (int)max(0LL, min(e_t, (long long)T));
+    const int b = ub[u], e = ub[u + 1];
+    const double mid_b = __ddiv_rn(__dadd_rn(tm(b), tm(b - 1)), 2.0);
+    const double start = fmax(__dadd_rn(tm(b + 1), -0.5), mid_b);
+    const double mid_e = __ddiv_rn(__dadd_rn(tm(e), tm(e - 1)), 2.0);
+    const double end = fmin(__dadd_rn(tm(e - 1), 0.5), mid_e);
+    const double qs = __ddiv_rn(start, dur), qe = __ddiv_rn(end, dur);
+    const long long s_t = (long long)(round_nearest ? rint(qs) : floor(qs));
+    const long long e_t = (long long)(round_nearest ? rint(qe) : floor(qe));
+    double score;
+    if (e_t <= s_t) {
+        score = -10000000000.0;
+    } else if (e_t - s_t <= n) {
+        const int lo = (int)max(0LL, min(s_t, (long long)T));
+        const int hi = (int)max(0LL, min(e_t, (long long)T));
+        const int cnt = hi - lo;
+        score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
+                          : __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+        // min over t of mean(char_probs[t : t + n]).  x -> x / n is monotone, so for the windows of
+        // full length the minimum of the means is the minimum of the sums divided once (the fp64
+        // division is a long instruction sequence); windows clipped by the end of the audio keep
+        // their own division.
+        double best = 0.0, best_sum = __longlong_as_double(0x7ff0000000000000LL);
+        int limit = T;  // no window of this utterance reads char_probs at or beyond it
+        {
+            const int lo_all = (int)max(0LL, min(s_t, (long long)T)), hi_all = (int)max(0LL, min(e_t, (long long)T));
+            limit = hi_all;
+            if (slice != nullptr && hi_all - lo_all <= slice_cap) {
+                __syncwarp();
+                for (int i = lo_all + lane; i < hi_all; i += 32) slice[i - lo_all] = cprob_g[i];
+                __syncwarp();
+                cprob = slice - lo_all;  // (every index below lies in [lo_all, hi_all))
+            }
+        }
+        auto window = [&](long long t) {  // the generic path: one window, numpy's order
+            const int lo = (int)max(0LL, min(t, (long long)T));
+            const int hi = (int)max(0LL, min(t + n, (long long)T));
             const int cnt = hi - lo;
-            score = (cnt > 0) ? __ddiv_rn(np_pairwise_sum(cprob + lo, cnt), (double)cnt)
-                              : __longlong_as_double(0x7ff8000000000000LL);
+            if (cnt <= 0) return;
+            const double sum = np_pairwise_sum(cprob + lo, cnt);
+            if (cnt == n) best_sum = fmin(best_sum, sum);
+            else best = fmin(best, __ddiv_rn(sum, (double)cnt));
+        };
+        if (scratch != nullptr && n >= 8 && n <= 128) {
+            const int nb = n / 8;  // blocks of eight
+            auto partial = [&](long long x) -> double {  // S[x]; 0 where the full windows never look
+                if (x < 0 || x + 8 * (nb - 1) >= limit) return 0.0;
+                double r = (double)cprob[x];
+                for (int m = 1; m < nb; ++m) r = __dadd_rn(r, (double)cprob[x + 8 * m]);
+                return r;
+            };
+            for (long long base = s_t; base < e_t - n; base += 32) {
+                __syncwarp();
+                scratch[lane] = partial(base + lane);
+                if (lane < 7) scratch[32 + lane] = partial(base + 32 + lane);
+                __syncwarp();
+                const long long t = base + lane;
+                if (t < e_t - n) {
+                    if (t >= 0 && t + n <= T) {
+                        const double *r = scratch + lane;
+                        double sum = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                        for (int i = 8 * nb; i < n; ++i) sum = __dadd_rn(sum, (double)cprob[t + i]);
+                        best_sum = fmin(best_sum, sum);
+                    } else {
+                        window(t);
+                    }
+                }
+            }
         } else {
-            // min over t of mean(char_probs[t : t + n]).  x -> x / n is monotone, so for the windows of
-            // full length the minimum of the means is the minimum of the sums divided once (the fp64
-            // division is a long instruction sequence); windows clipped by the end of the audio keep
-            // their own division.
-            double best = 0.0, best_sum = __longlong_as_double(0x7ff0000000000000LL);
-            for (long long t = s_t + lane; t < e_t - n; t += 32) {
-                const int lo = (int)max(0LL, min(t, (long long)T));
-                const int hi = (int)max(0LL, min(t + n, (long long)T));
-                const int cnt = hi - lo;
-                if (cnt <= 0) continue;
-                const double sum = np_pairwise_sum(cprob + lo, cnt);
-                if (cnt == n) best_sum = fmin(best_sum, sum);
-                else best = fmin(best, __ddiv_rn(sum, (double)cnt));
-            }
+            for (long long t = s_t + lane; t < e_t - n; t += 32) window(t);
+        }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
-                best_sum = fmin(best_sum, __shfl_xor_sync(0xffffffffu, best_sum, off));
-            }
-            if (best_sum < __longlong_as_double(0x7ff0000000000000LL))
-                best = fmin(best, __ddiv_rn(best_sum, (double)n));
-            score = best;
+        for (int off = 16; off > 0; off >>= 1) {
+            best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
+            best_sum = fmin(best_sum, __shfl_xor_sync(0xffffffffu, best_sum, off));
         }
-        if (lane == 0) {
-            seg[u * 3] = start;
-            seg[u * 3 + 1] = end;
-            seg[u * 3 + 2] = score;
-        }
+        if (best_sum < __longlong_as_double(0x7ff0000000000000LL))
+            best = fmin(best, __ddiv_rn(best_sum, (double)n));
+        score = best;
     }
+    if (lane == 0) {
+        seg[u * 3] = start;
+        seg[u * 3 + 1] = end;
+        seg[u * 3 + 2] = score;
+    }
+}
+
+// ... for utterances 0..n_utt-1 of one alignment.
+__device__ __forceinline__ void score_segments(const int32_t *ub, const int32_t *timing, const float *cprob,
+                                               int n_utt, int T, int Cmax, double dur, int n, bool round_nearest,
+                                               int lane, double *seg, double *scratch = nullptr) {
+    for (int u = 0; u < n_utt; ++u)
+        score_one_segment(ub, timing, cprob, u, T, Cmax, dur, n, round_nearest, lane, seg, scratch);
 }
 
 // Bits 0, KC, 2KC, ... of x packed into the low 32 / KC bits.
@@ -143,12 +199,20 @@ struct SegWalkArgs {
     int32_t *state;          // nullable
     double *seg;             // [kslot + 1][3]
     uint32_t *raw;
+    bool skip_scoring = false;  // the caller scores the utterances itself (file-resident sweep: a warp per (prefix, utterance))
 };
 
 template <int KC>
 __host__ __device__ constexpr int seg_walk_smem_words() {
     constexpr int NCW2 = (31 / KC + 2) + 32 / KC + 1;
     return NCW2 * KC * 2;
+}
+
+// 40 doubles inside a warp's staging words (8-byte aligned whatever the caller's layout), for score_one_segment
+template <int KC>
+__device__ __forceinline__ double *seg_scratch(uint32_t *raw) {
+    static_assert(seg_walk_smem_words<KC>() >= 82, "staging area holds the partial sums");
+    return reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(raw) + 7) & ~(uintptr_t)7);
 }
 
 // COHERENT: the backpointers were written by THIS kernel (file-resident sweep): plain loads instead of
@@ -284,8 +348,10 @@ __device__ __forceinline__ void seg_walk_prefix(const SegWalkArgs &a, int kslot,
     __threadfence_block();
 
     // ---- determine_utterance_segments ---------------------------------------
+    if (a.skip_scoring) return;
+    // (the staging words of the walk are free now: scratch for the shared partial sums)
     score_segments(a.ub, timing, cprob, kslot + 1, T, a.Cmax, a.index_duration, a.score_len, a.round_nearest, lane,
-                   a.seg);
+                   a.seg, seg_scratch<KC>(a.raw));
 }
 
 }  // namespace ipfa

@@ -61,4 +61,6 @@ for mode in ("resident", "lockstep"):
     print(f"{mode:9s} {1e3 * (time.time() - t0):8.2f} ms  capacity {run.capacity}  {run.stats()}", flush=True)
 same = out["resident"] == out["lockstep"]
 print("identical rows / status / counters:", same)
+import ctypes
+ctypes.CDLL(None).fflush(None)  # device printf (IPFA_SWEEP_PHASES=1) sits in the C stdio buffer
 os._exit(0 if same else 1)
