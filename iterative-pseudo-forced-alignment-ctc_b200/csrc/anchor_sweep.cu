@@ -351,6 +351,7 @@ struct ResidentParams {
     ipfa_sweep_state s;
     SweepWindows w;          // descriptors, one slot per CTA
     int Tmax, Cmax, Kmax, pitch, bits_bytes;
+    int kc;                  // 0: columns per thread chosen per window; 1 / 2 / 4: fixed (IPFA_SWEEP_KC, tuning)
     uint32_t *bp;            // [slots][words_per_slot] backpointer words (windows too large for shared memory)
     int64_t words_per_slot;
     int32_t *timing;         // [slots][Kmax][Cmax]
@@ -526,7 +527,8 @@ __device__ __forceinline__ void resident_fill(const float *lp_win, int T, int NC
 struct ResidentSmem {
     size_t ring, xline, gt, walk, seg, ub, colarg, bits, total;
 };
-template <int KC>
+constexpr int kResWalkWords = seg_walk_smem_words<4>();  // per-warp staging words of the walks: the largest instance
+static_assert(seg_walk_smem_words<1>() <= kResWalkWords && seg_walk_smem_words<2>() <= kResWalkWords, "walk staging");
 __host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, int Cmax, int Kmax, int bits_bytes) {
     ResidentSmem m;
     size_t off = 0;
@@ -535,7 +537,7 @@ __host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, in
     m.seg = take((size_t)Kmax * Kmax * 3 * 8);
     m.xline = take((size_t)2 * (threads + 1) * 4);
     m.gt = take((size_t)Cmax * 4);
-    m.walk = take((size_t)(threads / 32) * seg_walk_smem_words<KC>() * 4);
+    m.walk = take((size_t)(threads / 32) * kResWalkWords * 4);
     m.ub = take((size_t)(Kmax + 1) * 4);
     m.colarg = take((size_t)(Kmax + 1) * 4);
     m.bits = take((size_t)bits_bytes);  // backpointer words of the window in flight, when they fit
@@ -543,7 +545,59 @@ __host__ __device__ inline ResidentSmem resident_smem(int pitch, int threads, in
     return m;
 }
 
-template <int KC, int PITCH, int MAXT>
+// Table fill and the walks of every prefix of ONE window with KC columns per thread (the CTA's first
+// ceil(columns / (32 KC)) warps fill; one warp per prefix walks).
+struct ResidentWindow {
+    const float *lp_win;
+    int T, NC, K, slot;
+    float *ring, *xline;
+    int line_len;
+    int32_t *gt_s, *ub_s, *colarg_s;
+    uint32_t *bits_s, *bp_global, *walk_s;
+    double *seg_s;
+    bool round_nearest;
+    long long *t_fill_end;  // diagnostic (thread 0 of CTA 0), nullable
+};
+template <int KC, int PITCH>
+__device__ __forceinline__ void resident_align(const ResidentParams &P, const ResidentWindow &W) {
+    const ipfa_sweep_corpus &c = P.c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int T = W.T, NC = W.NC, K = W.K, Kmax = P.Kmax, Cmax = P.Cmax, Tmax = P.Tmax;
+    const int nact = (NC - 1 + 32 * KC - 1) / (32 * KC);  // warps that own a column
+    // the window's backpointer words: shared memory when they fit (the walks then have no L2 latency to hide)
+    uint32_t *bp = ((int64_t)((T + 32 / KC - 1) / (32 / KC)) * 32 * nact * 4 <= P.bits_bytes) ? W.bits_s : W.bp_global;
+    if (warp < nact)
+        resident_fill<KC, PITCH>(W.lp_win, T, NC, c.V, P.pitch, c.blank, W.gt_s, W.ub_s, K, W.ring, W.xline,
+                                 W.line_len, 32 * nact, bp, W.colarg_s, tid);
+    cta_sync();
+    if (W.t_fill_end) *W.t_fill_end = clock64();
+    // every prefix of the window: one warp each (ctc_segmentation() backtrace; the utterances are scored after)
+    for (int kslot = warp; kslot < K; kslot += nwarps) {
+        int32_t *timing = P.timing + ((int64_t)W.slot * Kmax + kslot) * Cmax;
+        float *cprob = P.cprob + ((int64_t)W.slot * Kmax + kslot) * Tmax;
+        double *seg = W.seg_s + (int64_t)kslot * Kmax * 3;
+        for (int t = lane; t < T; t += 32) cprob[t] = 0.0f;
+        for (int cc = lane; cc < NC; cc += 32) timing[cc] = -1;
+        const int c_end = W.ub_s[kslot + 1];
+        const bool feasible = T > 0 && c_end >= 1 && c_end < NC && c_end + 1 <= T;
+        const int t_term = feasible ? W.colarg_s[kslot + 1] : -1;
+        if (!feasible || t_term < 0) {
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
+            continue;
+        }
+        __syncwarp();
+        SegWalkArgs a;
+        a.lp = W.lp_win; a.stride_t = c.stride_t; a.T = T; a.Cmax = Cmax; a.blank = c.blank; a.NT = 32 * nact;
+        a.score_len = P.p.score_len; a.round_nearest = W.round_nearest; a.index_duration = P.p.index_duration;
+        a.bp_w = bp; a.ub = W.ub_s; a.gt_s = W.gt_s; a.timing = timing; a.cprob = cprob; a.state = nullptr;
+        a.seg = seg; a.raw = W.walk_s; a.skip_scoring = true;
+        seg_walk_prefix<KC, true>(a, kslot, t_term, c_end, lane);
+        if (lane == 0) W.colarg_s[kslot + 1] |= 0x40000000;  // walked: its utterances are scored below
+    }
+}
+
+template <int PITCH, int MAXT>
 __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentParams P) {
     extern __shared__ __align__(128) unsigned char rs_smem[];
     __shared__ int sh_file;
@@ -551,12 +605,12 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int slot = blockIdx.x;
     const int Tmax = P.Tmax, Cmax = P.Cmax, Kmax = P.Kmax;
-    const ResidentSmem m = resident_smem<KC>(PITCH ? PITCH : P.pitch, blockDim.x, Cmax, Kmax, P.bits_bytes);
+    const ResidentSmem m = resident_smem(PITCH ? PITCH : P.pitch, blockDim.x, Cmax, Kmax, P.bits_bytes);
     float *ring = reinterpret_cast<float *>(rs_smem + m.ring);
     double *seg_s = reinterpret_cast<double *>(rs_smem + m.seg);
     float *xline = reinterpret_cast<float *>(rs_smem + m.xline);
     int32_t *gt_s = reinterpret_cast<int32_t *>(rs_smem + m.gt);
-    uint32_t *walk_s = reinterpret_cast<uint32_t *>(rs_smem + m.walk) + (size_t)warp * seg_walk_smem_words<KC>();
+    uint32_t *walk_s = reinterpret_cast<uint32_t *>(rs_smem + m.walk) + (size_t)warp * kResWalkWords;
     int32_t *ub_s = reinterpret_cast<int32_t *>(rs_smem + m.ub);
     int32_t *colarg_s = reinterpret_cast<int32_t *>(rs_smem + m.colarg);
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(rs_smem + m.bits);
@@ -571,6 +625,7 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
     long long ph_walk = 0, ph_score = 0;
     long long ph[5] = {0, 0, 0, 0, 0}, ph_t = 0;  // phase cycles of thread 0: window, staging, fill, walk, decision
     int ph_n = 0;
+    long long t_fill_end = 0;
     const bool timed = P.phases && tid == 0 && slot == 0;
 #define IPFA_PHASE(i) do { if (timed) { const long long now_ = clock64(); ph[i] += now_ - ph_t; ph_t = now_; } } while (0)
     while (true) {
@@ -608,38 +663,21 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
             cta_sync();
             IPFA_PHASE(1);
             ++ph_n;
-            const int nact = (NC - 1 + 32 * KC - 1) / (32 * KC);  // warps that own a column
-            // the window's backpointer words: shared memory when they fit (the walks then have no L2 latency to hide)
-            uint32_t *bp = ((int64_t)((T + 32 / KC - 1) / (32 / KC)) * 32 * nact * 4 <= P.bits_bytes) ? bits_s : bp_global;
-            if (warp < nact)
-                resident_fill<KC, PITCH>(lp_win, T, NC, c.V, P.pitch, c.blank, gt_s, ub_s, K, ring,
-                                         xline, line_len, 32 * nact, bp, colarg_s, tid);
-            cta_sync();
-            IPFA_PHASE(2);
-            // every prefix of the window: one warp each (ctc_segmentation() backtrace + determine_utterance_segments)
-            for (int kslot = warp; kslot < K; kslot += nwarps) {
-                int32_t *timing = P.timing + ((int64_t)slot * Kmax + kslot) * Cmax;
-                float *cprob = P.cprob + ((int64_t)slot * Kmax + kslot) * Tmax;
-                double *seg = seg_s + (int64_t)kslot * Kmax * 3;
-                for (int t = lane; t < T; t += 32) cprob[t] = 0.0f;
-                for (int cc = lane; cc < NC; cc += 32) timing[cc] = -1;
-                const int c_end = ub_s[kslot + 1];
-                const bool feasible = T > 0 && c_end >= 1 && c_end < NC && c_end + 1 <= T;
-                const int t_term = feasible ? colarg_s[kslot + 1] : -1;
-                if (!feasible || t_term < 0) {
-                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                    for (int u = lane; u <= kslot; u += 32) { seg[u * 3] = nan; seg[u * 3 + 1] = nan; seg[u * 3 + 2] = nan; }
-                    continue;
-                }
-                __syncwarp();
-                SegWalkArgs a;
-                a.lp = lp_win; a.stride_t = c.stride_t; a.T = T; a.Cmax = Cmax; a.blank = c.blank; a.NT = 32 * nact;
-                a.score_len = P.p.score_len; a.round_nearest = round_nearest; a.index_duration = P.p.index_duration;
-                a.bp_w = bp; a.ub = ub_s; a.gt_s = gt_s; a.timing = timing; a.cprob = cprob; a.state = nullptr;
-                a.seg = seg; a.raw = walk_s; a.skip_scoring = true;
-                seg_walk_prefix<KC, true>(a, kslot, t_term, c_end, lane);
-                if (lane == 0) colarg_s[kslot + 1] |= 0x40000000;  // walked: its utterances are scored below
+            // Columns per thread, chosen per window: a file's windows are a serial chain, and a window with few
+            // warps is latency bound (154 cycles per frame with four warps against 100 with eleven), so narrow
+            // windows take one column per thread; wide ones are issue bound and take four.
+            {
+                ResidentWindow W;
+                W.lp_win = lp_win; W.T = T; W.NC = NC; W.K = K; W.slot = slot; W.ring = ring; W.xline = xline;
+                W.line_len = line_len; W.gt_s = gt_s; W.ub_s = ub_s; W.colarg_s = colarg_s; W.bits_s = bits_s;
+                W.bp_global = bp_global; W.walk_s = walk_s; W.seg_s = seg_s; W.round_nearest = round_nearest;
+                W.t_fill_end = timed ? &t_fill_end : nullptr;
+                const int kcw = P.kc ? P.kc : (NC - 1 <= 512 ? 1 : NC - 1 <= 1024 ? 2 : 4);
+                if (kcw == 1) resident_align<1, PITCH>(P, W);
+                else if (kcw == 2) resident_align<2, PITCH>(P, W);
+                else resident_align<4, PITCH>(P, W);
             }
+            if (timed) { ph[2] += t_fill_end - ph_t; ph_t = t_fill_end; }
             cta_sync();
             long long t_walks = 0;
             if (timed) { t_walks = clock64(); ph_walk += t_walks - ph_t; }
@@ -653,7 +691,7 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
                 score_one_segment(ub_s, P.timing + ((int64_t)slot * Kmax + k) * Cmax,
                                   P.cprob + ((int64_t)slot * Kmax + k) * Tmax, u, T, Cmax, P.p.index_duration,
                                   P.p.score_len, round_nearest, lane, seg_s + (int64_t)k * Kmax * 3,
-                                  seg_scratch<KC>(walk_s),
+                                  seg_scratch<4>(walk_s),
                                   // (the walks are over: the backpointer area is this warp's to stage char_probs in)
                                   reinterpret_cast<float *>(bits_s) + (size_t)warp * slice_cap, slice_cap);
             }
@@ -738,14 +776,18 @@ bool resident_plan(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p, int T
     if (table_flags != IPFA_SEG_PREAMBLE_COST_ZERO) return false;
     if (c.V % 4 != 0 || c.V > 256 || c.stride_t != c.V || (reinterpret_cast<uintptr_t>(c.lp) & 15) != 0) return false;
     if (Tmax > 8000 || Cmax - 1 > 4096) return false;
-    // two columns per thread while that keeps the CTA at 16 warps (the 128-register instances), four beyond:
-    // measured on the 100 h corpus (windows up to 1182 columns) 36.7 ms with four against 44.9 ms with two
-    pl->kc = (Cmax - 1 <= 1024) ? 2 : 4;
-    if (const char *e = tuning("IPFA_SWEEP_KC")) {  // tuning: columns per thread
+    // Columns per thread are chosen per WINDOW (resident_kernel): 1 up to 512 columns, 2 up to 1024, 4 beyond --
+    // so 16 warps hold any window of up to 2048 columns (the 128-register instances), 32 warps up to 4096.
+    // IPFA_SWEEP_KC=1|2|4 (tuning) fixes the choice for every window.
+    pl->kc = 0;
+    int warps = (Cmax - 1 <= 512) ? (Cmax - 1 + 31) / 32 : (Cmax - 1 <= 2048 ? 16 : 32);
+    if (const char *e = tuning("IPFA_SWEEP_KC")) {
         const int v = atoi(e);
-        if ((v == 2 || v == 4) && Cmax - 1 <= v * 1024) pl->kc = v;
+        if ((v == 1 || v == 2 || v == 4) && Cmax - 1 <= v * 1024) {
+            pl->kc = v;
+            warps = (Cmax - 1 + 32 * v - 1) / (32 * v);
+        }
     }
-    const int warps = (Cmax - 1 + 32 * pl->kc - 1) / (32 * pl->kc);
     pl->threads = 32 * (warps < 4 ? 4 : warps);
     pl->pitch = c.V;
     pl->fixed_pitch = (c.V == 32);
@@ -753,14 +795,12 @@ bool resident_plan(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p, int T
         // shared memory for the backpointer words: the launch capacity's worth, at most 160 KB.  (More than half
         // of an SM's shared memory also keeps every CTA on an SM of its own: a file's chain is latency bound and
         // two chains on one SM were measured slower than one after the other.)
-        const int spw = 32 / pl->kc;
-        const int64_t want = (int64_t)((Tmax + spw - 1) / spw) * pl->threads * 4;
+        const int64_t want = ((int64_t)Tmax + 32) * (Cmax + 128) / 8;  // one bit per cell, padded
         const int64_t room = 160 * 1024;
         pl->bits_bytes = (int)((((want < room ? want : room) + 15) / 16) * 16);
         if (pl->bits_bytes < 116 * 1024) pl->bits_bytes = 116 * 1024;
     }
-    const ResidentSmem m = pl->kc == 2 ? resident_smem<2>(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes)
-                                       : resident_smem<4>(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes);
+    const ResidentSmem m = resident_smem(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes);
     pl->smem = m.total;
     if (pl->smem > 225 * 1024) return false;
     int dev = 0, sms = 0;
@@ -804,8 +844,8 @@ size_t carve_resident(ResidentCarve *r, unsigned char *base, const ResidentPlan 
     w.decision = reinterpret_cast<int32_t *>(take((size_t)S * 4 * 4));
     w.seg_ws = nullptr;
     w.seg_ws_bytes = 0;
-    const int spw = 32 / pl.kc;
-    r->words_per_slot = (int64_t)((Tmax + spw - 1) / spw) * pl.threads;
+    // one bit per cell; a window is padded to whole words in time (<= 32 frames) and whole warps in columns (<= 128)
+    r->words_per_slot = ((int64_t)Tmax + 32) * (Cmax + 128) / 32 + 32;
     r->bp = reinterpret_cast<uint32_t *>(take((size_t)S * (size_t)r->words_per_slot * 4));
     r->timing = reinterpret_cast<int32_t *>(take((size_t)S * Kmax * (size_t)Cmax * 4));
     r->cprob = reinterpret_cast<float *>(take((size_t)S * Kmax * (size_t)Tmax * 4));
@@ -813,9 +853,9 @@ size_t carve_resident(ResidentCarve *r, unsigned char *base, const ResidentPlan 
     return off;
 }
 
-template <int KC, int PITCH, int MAXT>
+template <int PITCH, int MAXT>
 cudaError_t launch_resident(const ResidentParams &P, const ResidentPlan &pl, cudaStream_t st) {
-    auto kern = sweep_resident_kernel<KC, PITCH, MAXT>;
+    auto kern = sweep_resident_kernel<PITCH, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     kern<<<pl.slots, pl.threads, pl.smem, st>>>(P);
@@ -858,7 +898,7 @@ extern "C" int ipfa_sweep_resident_device(const ipfa_sweep_corpus *corpus, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ResidentParams P;
     P.c = c; P.p = *params; P.s = s; P.w = r.w;
-    P.Tmax = Tmax; P.Cmax = Cmax; P.Kmax = Kmax; P.pitch = pl.pitch; P.bits_bytes = pl.bits_bytes;
+    P.Tmax = Tmax; P.Cmax = Cmax; P.Kmax = Kmax; P.pitch = pl.pitch; P.bits_bytes = pl.bits_bytes; P.kc = pl.kc;
     P.bp = r.bp; P.words_per_slot = r.words_per_slot; P.timing = r.timing; P.cprob = r.cprob; P.ticket = r.ticket;
     P.out_seg = out_seg; P.out_info = out_info;
     P.phases = tuning("IPFA_SWEEP_PHASES") != nullptr;
@@ -866,14 +906,10 @@ extern "C" int ipfa_sweep_resident_device(const ipfa_sweep_corpus *corpus, const
     cudaError_t e = cudaMemsetAsync(r.ticket, 0, 4, st);
     if (e == cudaSuccess) {
         const int prof_slot = profile_begin(st);
-        const bool wide = pl.threads > 512;  // the 64-register instances
-        if (pl.kc == 2 && pl.fixed_pitch && !wide) e = launch_resident<2, 32, 512>(P, pl, st);
-        else if (pl.kc == 2 && pl.fixed_pitch) e = launch_resident<2, 32, 1024>(P, pl, st);
-        else if (pl.kc == 2 && !wide) e = launch_resident<2, 0, 512>(P, pl, st);
-        else if (pl.kc == 2) e = launch_resident<2, 0, 1024>(P, pl, st);
-        else if (pl.fixed_pitch && !wide) e = launch_resident<4, 32, 512>(P, pl, st);
-        else if (pl.fixed_pitch) e = launch_resident<4, 32, 1024>(P, pl, st);
-        else e = launch_resident<4, 0, 1024>(P, pl, st);
+        if (pl.fixed_pitch && pl.threads <= 512) e = launch_resident<32, 512>(P, pl, st);
+        else if (pl.fixed_pitch) e = launch_resident<32, 1024>(P, pl, st);
+        else if (pl.threads <= 512) e = launch_resident<0, 512>(P, pl, st);
+        else e = launch_resident<0, 1024>(P, pl, st);
         profile_end(prof_slot, st);
         ++g_launch_count;
     }
