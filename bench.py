@@ -857,6 +857,16 @@ def gpu_arm(args):
                        "longest_file_minutes": c5["longest_file_minutes"], "windows": int(c5["windows"]),
                        "cells_per_s": c5["cells"] / (ms5 * 1e-3), "kernels_per_sweep": c5["launches"] / c5["steps"] / world,
                        "sweep_mode": c5["mode"]}
+        if world > 1:
+            # the same sweep with the corpus growing with the job (100 h per GPU): a file's windows are a serial
+            # chain, so ONE corpus stops scaling at its longest file; capacity is what more GPUs buy
+            c5w = c5_measure(args.hours * world, world, rank, dev, steps=2, warm=2, with_e2e=False)
+            msw = c5w["elapsed_ms"] / c5w["steps"]
+            extra["c5_weak"] = {"workload": C5_TEXT.format(h=args.hours * world), "scaling": "weak",
+                                "ms_per_sweep": msw, "audio_h_per_s": c5w["hours"] / (msw * 1e-3),
+                                "files": int(c5w["files"]), "files_per_rank_max": c5w["files_per_rank_max"],
+                                "iterations_longest_chain": c5w["iterations_max"], "windows": int(c5w["windows"]),
+                                "sweep_mode": c5w["mode"]}
         if world == 1:
             for name in ("c2v", "c3", "c3seg", "c4", "c4v", "seg"):
                 w2 = WORKLOADS[name]
