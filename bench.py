@@ -544,7 +544,8 @@ def c5_arm(args):
                     "cuda_graphs": (not args.no_graphs) if m["mode"] == "lockstep" else None, "V": 32},
             "cells_per_s": m["cells"] / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic("c5") if m["mode"] == "resident" else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_per_step,
                          "kernels_per_step": m["launches"] / max(steps, 1) / world,
                          "note": "a file's windows are a serial chain of T-serial fills, each on one SM (resident mode: "

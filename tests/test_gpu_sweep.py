@@ -330,3 +330,65 @@ def test_sweep_with_host_time_respreading_equals_the_per_file_loop(exact_audio, 
     for f, s in enumerate(specs):
         assert status[f] == sweep.DONE, (s["name"], sweep.STATUS_NAMES[status[f]])
         assert got[f] == ref[f], s["name"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Instances of the file-resident kernel that the corpora above do not reach on their own
+def _synthetic_files(n_files=3, minutes=1.0, pad_v=0, seed=40):
+    import sweep_corpus
+    specs = [sweep_corpus.make_spec(f"r{i}", minutes, seed + i, corrupt_frac=0.1, non_speech_every=5)
+             for i in range(n_files)]
+    lps = [sweep_corpus.emissions(sp, "cuda", seed=seed + 9 * i) for i, sp in enumerate(specs)]
+    if pad_v:  # extra vocabulary entries nobody can prefer
+        lps = [torch.cat([lp, torch.full((lp.shape[0], pad_v), -40.0, device=lp.device)], dim=1).contiguous()
+               for lp in lps]
+    return [sweep.SweepFile(sp.file_id, sp.audio_path, lp, sp.n_samples, sp.rows) for sp, lp in zip(specs, lps)]
+
+
+def _run(files, mode, **kw):
+    run = sweep.AnchorSweep(sweep.SweepCorpus(files, stub.CharTokenizer()), index_duration=0.02,
+                            samples_to_frames_ratio=320.0, mode=mode, **kw)
+    status = run.run()
+    stats = {k: v for k, v in run.stats().items() if k != "steps"}
+    return run, (status.tolist(), run.file_rows(), stats)
+
+
+@pytest.mark.parametrize("kc", [1, 2, 4])
+def test_resident_columns_per_thread_instances(kc, sweep_mode):
+    """Every columns-per-thread instance of the fill / walk (chosen per window by default) on the same
+    windows: identical rows, status words and counters."""
+    if sweep_mode != "resident":
+        pytest.skip("resident kernel only")
+    ipfa = importlib.import_module(PKG)
+    files = _synthetic_files()
+    _, want = _run(files, "lockstep")
+    with ipfa.tuning(IPFA_SWEEP_KC=str(kc)):
+        run, got = _run(files, "resident")
+    assert run.mode == "resident" and got == want and sum(len(r) for r in got[1]) > 20
+
+
+def test_resident_runtime_pitch_and_fallback(sweep_mode):
+    """V = 36: dense rows of another width than 32 (the run-time pitch instance); V = 34: rows that 16-byte
+    pieces cannot move -> `auto` runs the lock-step path, `resident` refuses."""
+    if sweep_mode != "resident":
+        pytest.skip("resident kernel only")
+    files36 = _synthetic_files(pad_v=4)
+    run, got = _run(files36, "auto")
+    assert run.mode == "resident" and run.corpus.V == 36
+    assert got == _run(files36, "lockstep")[1]
+    files34 = _synthetic_files(pad_v=2)
+    run34, got34 = _run(files34, "auto")
+    assert run34.mode == "lockstep" and got34[1] == got[1]  # the padding changes no alignment
+    with pytest.raises(ValueError):
+        _run(files34, "resident")
+
+
+def test_resident_capacity_growth_and_tiny_launch(sweep_mode):
+    """A launch capacity far too small: the files stop with CAPACITY, the host grows it and relaunches; the
+    state carries over (same rows as one launch with room)."""
+    if sweep_mode != "resident":
+        pytest.skip("resident kernel only")
+    files = _synthetic_files(n_files=2, minutes=0.7)
+    _, want = _run(files, "resident")
+    run, got = _run(files, "resident", capacity=(64, 16, 1))
+    assert got == want and run.capacity[1] > 16
