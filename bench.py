@@ -474,7 +474,10 @@ def c5_measure(hours_total, world, rank, dev, steps, warm, groups=32, use_graphs
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            corpus.lp.copy_(host_lp, non_blocking=True)
+            if sweep.mode == "resident":
+                corpus.begin_upload(host_lp)   # file by file on a copy stream; the sweep starts on the first files
+            else:
+                corpus.lp.copy_(host_lp, non_blocking=True)
             one_sweep()
             out_seg_h.copy_(sweep.out_seg, non_blocking=True)
             out_info_h.copy_(sweep.out_info, non_blocking=True)

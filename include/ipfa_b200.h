@@ -335,6 +335,11 @@ typedef struct ipfa_sweep_corpus {
     const int64_t *file_tok0;    /* [F] start of the file's token stream inside tokens */
     const int32_t *tokens;       /* per file: blank, tokens(utt 0), blank, tokens(utt 1), ..., blank
                                     (prepare_token_list without its leading -1) */
+    const int32_t *file_ready;   /* optional [F] (NULL: every file's emissions are in lp): word f becomes non-zero
+                                    once file f's emissions have arrived -- written by the caller's copy stream
+                                    AFTER that file's upload, so that uploads overlap the sweep.  Honoured by
+                                    ipfa_sweep_resident_device only: a CTA that draws file f waits for word f
+                                    (upload the files in index order, zero the words before the launch). */
 } ipfa_sweep_corpus;
 
 /* Per-file loop state (device arrays [F], read and written by the sweep).  Initial values:

@@ -81,7 +81,7 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(ipfa_[a-z0-9_]+)\s*\(", text)))
 
 
-ABI_VERSION = 201  # ipfa_version(): bumped whenever a signature or struct in include/ipfa_b200.h changes
+ABI_VERSION = 202  # ipfa_version(): bumped whenever a signature or struct in include/ipfa_b200.h changes
 _lib = None
 
 

@@ -641,6 +641,16 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
                        ph_walk / max(ph_n, 1), ph_score / max(ph_n, 1), ph[4] / max(ph_n, 1));
             break;
         }
+        if (c.file_ready) {
+            // the file's emissions may still be on their way (uploads overlapping the sweep): one thread polls the
+            // word the copy stream writes behind the file's upload, the rest of the CTA waits at the barrier
+            if (tid == 0) {
+                const volatile int32_t *ready = c.file_ready + f;
+                while (*ready == 0) __nanosleep(500);
+                __threadfence();
+            }
+            cta_sync();
+        }
         if (timed) ph_t = clock64();
         build_window(c, P.p, P.s, P.w, f, slot, Tmax, Cmax, Kmax);
         while (true) {

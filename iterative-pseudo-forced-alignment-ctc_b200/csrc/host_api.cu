@@ -185,7 +185,7 @@ int windows_per_chunk(int N, int64_t per_window_floats) {
 
 using namespace ipfa;
 
-extern "C" int ipfa_version(void) { return 201; }
+extern "C" int ipfa_version(void) { return 202; }
 
 extern "C" const char *ipfa_status_string(int status) {
     switch (status) {

@@ -31,7 +31,7 @@ class _Corpus(ctypes.Structure):
                 ("reserved", _i32), ("file_frame0", _vp), ("file_frames", _vp), ("file_samples", _vp),
                 ("row_first", _vp), ("row_type", _vp), ("row_start", _vp), ("row_end", _vp),
                 ("row_utt_end", _vp), ("utt_first", _vp), ("utt_col", _vp), ("utt_chars", _vp),
-                ("file_tok0", _vp), ("tokens", _vp)]
+                ("file_tok0", _vp), ("tokens", _vp), ("file_ready", _vp)]
 
 
 class _State(ctypes.Structure):
@@ -152,6 +152,7 @@ class SweepCorpus:
         self.V = int(self.lp.shape[1])
         self.n_slots = len(self.host["utt_col"])
         self.arrays = {k: torch.as_tensor(v, device=device) for k, v in self.host.items()}
+        self._ready, self._copy_stream = None, None
 
     def struct(self):
         c = _Corpus()
@@ -160,7 +161,38 @@ class SweepCorpus:
         c.V, c.blank, c.n_files = self.V, self.blank, len(self.files)
         for k, t in self.arrays.items():
             setattr(c, k, t.data_ptr())
+        c.file_ready = self._ready.data_ptr() if self._ready is not None else None
         return c
+
+    # ------------------------------------------------------------------ uploads overlapping the sweep
+    def begin_upload(self, host_lp):
+        """Start copying the emissions of all files from pinned host memory (``host_lp``: fp32
+        [total frames, V], the files in corpus order) on a copy stream, file by file, each followed by its
+        word of ``ipfa_sweep_corpus.file_ready``: a file-resident sweep launched right after starts on the
+        first (longest) files while the others are still in flight.  The lock-step path waits for the whole
+        upload (``finish_upload``).  Asynchronous."""
+        dev = self.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._ones = torch.ones(len(self.files), dtype=torch.int32).pin_memory()
+            self._ready_buf = torch.zeros(len(self.files), dtype=torch.int32, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._ready = self._ready_buf
+        self._ready.zero_()                      # on the caller's stream, before the sweep's launch ...
+        zeroed = torch.cuda.Event()
+        zeroed.record(cur)
+        self._copy_stream.wait_event(zeroed)     # ... and before the first flag
+        frame0, frames = self.host["file_frame0"], self.host["file_frames"]
+        with torch.cuda.stream(self._copy_stream):
+            for f in range(len(self.files)):
+                a, b = int(frame0[f]), int(frame0[f]) + int(frames[f])
+                self.lp[a:b].copy_(host_lp[a:b], non_blocking=True)
+                self._ready[f:f + 1].copy_(self._ones[f:f + 1], non_blocking=True)
+
+    def finish_upload(self):
+        """Wait (on the current stream) for an upload started by :meth:`begin_upload`."""
+        if self._copy_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._copy_stream)
 
     def total_frames(self):
         return int(self.lp.shape[0])
@@ -397,6 +429,7 @@ class AnchorSweep:
                     continue
                 self.steps = int(self.state["n_windows"].max().item())  # windows of the longest chain
             else:
+                self.corpus.finish_upload()   # only the file-resident kernel honours the per-file ready words
                 self.step(steps_per_poll)
             status = self.state["status"].cpu().numpy()
             if (status == CAPACITY).any():

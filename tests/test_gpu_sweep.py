@@ -392,3 +392,22 @@ def test_resident_capacity_growth_and_tiny_launch(sweep_mode):
     _, want = _run(files, "resident")
     run, got = _run(files, "resident", capacity=(64, 16, 1))
     assert got == want and run.capacity[1] > 16
+
+
+def test_resident_sweep_overlapping_the_upload(sweep_mode):
+    """Emissions arriving file by file from pinned host memory while the kernel is already running
+    (``ipfa_sweep_corpus.file_ready``): same rows as with everything resident, twice in a row (the ready
+    words are re-armed), and the lock-step path simply waits for the upload."""
+    files = _synthetic_files(n_files=6, minutes=0.6)
+    _, want = _run(files, sweep_mode)
+    corpus = sweep.SweepCorpus(files, stub.CharTokenizer())
+    host_lp = corpus.lp.cpu().pin_memory()
+    run = sweep.AnchorSweep(corpus, index_duration=0.02, samples_to_frames_ratio=320.0, mode=sweep_mode)
+    for _ in range(2):
+        corpus.lp.fill_(float("nan"))           # whatever is aligned must have come through the upload
+        run.reset()
+        corpus.begin_upload(host_lp)
+        status = run.run()
+        torch.cuda.synchronize()
+        stats = {k: v for k, v in run.stats().items() if k != "steps"}
+        assert (status.tolist(), run.file_rows(), stats) == want
