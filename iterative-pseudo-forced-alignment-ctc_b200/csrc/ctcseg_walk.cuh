@@ -237,7 +237,8 @@ __device__ __forceinline__ void seg_walk_prefix(const SegWalkArgs &a, int kslot,
     const uint32_t *bp_w = a.bp_w;
     const int NT = a.NT;
     uint32_t *raw = a.raw;
-    uint32_t *col32 = raw + NWORDS2;
+    // (one column per thread: a staged word already IS a column's 32 frames -- col32 is raw, nothing to transpose)
+    uint32_t *col32 = (KC == 1) ? raw : raw + NWORDS2;
     // ---- walk the 1-bit backpointers from (t_term, c_end) to (0, 0) ----------
     // Per 32-frame block the words the walk can reach sit in shared memory.  The walk does not
     // step frame by frame: inside a word the bits of one column are the frames at which that
@@ -290,15 +291,17 @@ __device__ __forceinline__ void seg_walk_prefix(const SegWalkArgs &a, int kslot,
         // per-column words of the whole block: col32[d] bit f = "column top - d was entered at frame
         // t_lo + f" (the KC-strided bits of the NW word-rows compressed and concatenated)
         const int top = i_cur * KC + (KC - 1);  // lattice column of col32[0]
-        for (int d = lane; d < NCW2 * KC; d += 32) {
-            const int crel = d >> LOG2KC, k = (KC - 1) - (d & (KC - 1));
-            uint32_t bits = 0;
+        if constexpr (KC != 1) {
+            for (int d = lane; d < NCW2 * KC; d += 32) {
+                const int crel = d >> LOG2KC, k = (KC - 1) - (d & (KC - 1));
+                uint32_t bits = 0;
 #pragma unroll
-            for (int row = 0; row < NW; ++row)
-                bits |= compress_stride<KC>(raw[row * NCW2 + crel] >> k) << (row * SPW);
-            col32[d] = bits;
+                for (int row = 0; row < NW; ++row)
+                    bits |= compress_stride<KC>(raw[row * NCW2 + crel] >> k) << (row * SPW);
+                col32[d] = bits;
+            }
+            __syncwarp();
         }
-        __syncwarp();
         // switch frames of this block as a 32-bit mask (bit = frame - t_lo): the serial chain is
         // one LDS + mask + find-leading-one per column change
         uint32_t S = 0;
