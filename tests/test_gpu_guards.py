@@ -55,6 +55,14 @@ class _GuardedTorch:
         out.fill_(value)
         return out
 
+    def zeros(self, *shape, dtype=None, device=None, **kw):
+        if device is None or self._torch.device(device).type != "cuda":
+            return self._torch.zeros(*shape, dtype=dtype, device=device, **kw)
+        shape = shape[0] if len(shape) == 1 and not isinstance(shape[0], int) else shape
+        out = self._alloc(shape, dtype or self._torch.float32, device)
+        out.zero_()
+        return out
+
     def empty_like(self, x, **kw):
         if not x.is_cuda:
             return self._torch.empty_like(x, **kw)
@@ -140,19 +148,25 @@ def test_segmentation_writes_inside_its_buffers(guarded, shape):
     assert g.check() >= 6
 
 
-def test_anchor_sweep_writes_inside_its_workspace(guarded):
+@pytest.mark.parametrize("mode", ["resident", "lockstep"])
+def test_anchor_sweep_writes_inside_its_workspace(guarded, monkeypatch, mode):
+    """Both device paths of the anchor sweep: the exactly-sized workspace (descriptors, backpointer words, timing /
+    char_probs scratch, ticket) and the state / output arrays keep their canary margins -- also across a capacity
+    growth (the first launch gets a workspace far too small for the corpus)."""
     ipfa, g = guarded
     import sweep_corpus
     sw = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.sweep")
     stub = importlib.import_module("iterative-pseudo-forced-alignment-ctc_b200.stub_asr")
+    monkeypatch.setattr(sw, "torch", g)  # sweep.py allocates its own workspaces / state / outputs
     specs = [sweep_corpus.make_spec(f"g{i}", 0.6 + 0.3 * i, 40 + i, corrupt_frac=0.3, non_speech_every=3) for i in range(3)]
     files = [sw.SweepFile(s.file_id, s.audio_path, sweep_corpus.emissions(s, "cuda", seed=i), s.n_samples, s.rows)
              for i, s in enumerate(specs)]
-    run = sw.AnchorSweep(sw.SweepCorpus(files, stub.CharTokenizer()), index_duration=0.02,
-                         samples_to_frames_ratio=320.0, groups=2, use_graphs=False)
-    status = run.run(steps_per_poll=4)
-    assert (status == sw.DONE).all()
-    g.check()
+    for capacity in (None, (64, 16, 1)):
+        run = sw.AnchorSweep(sw.SweepCorpus(files, stub.CharTokenizer()), index_duration=0.02,
+                             samples_to_frames_ratio=320.0, groups=2, use_graphs=False, mode=mode, capacity=capacity)
+        status = run.run(steps_per_poll=4)
+        assert run.mode == mode and (status == sw.DONE).all()
+        assert g.check() >= 10
 
 
 def test_results_are_repeatable_bit_for_bit():

@@ -46,6 +46,7 @@ for mode in ("resident", "lockstep"):
         status = run.run()
     t2 = time.time()
     torch.cuda.synchronize()
+    t_run = time.time() - t0
     print(f"  host: reset {1e3 * (t1 - t0):.2f} ms, run {1e3 * (t2 - t1):.2f} ms", flush=True)
     if mode == "resident":   # the launch alone, CUDA events
         for _ in range(2):
@@ -58,7 +59,7 @@ for mode in ("resident", "lockstep"):
             torch.cuda.synchronize()
             print(f"  resident launch alone: {e0.elapsed_time(e1):.3f} ms", flush=True)
     out[mode] = (status.tolist(), run.file_rows(), {k: v for k, v in run.stats().items() if k != "steps"})
-    print(f"{mode:9s} {1e3 * (time.time() - t0):8.2f} ms  capacity {run.capacity}  {run.stats()}", flush=True)
+    print(f"{mode:9s} {1e3 * t_run:8.2f} ms  capacity {run.capacity}  {run.stats()}", flush=True)
 same = out["resident"] == out["lockstep"]
 print("identical rows / status / counters:", same)
 import ctypes
