@@ -399,9 +399,10 @@ __device__ __forceinline__ void resident_fill(const float *lp_win, int T, int NC
     const bool warp_tracks = __any_sync(0xffffffffu, track);
     const int nchunks = (T + kResChunk - 1) / kResChunk;
     // Emission chunks (32 frames x V floats, contiguous) come in as 16-byte cp.async pieces issued by ALL the
-    // window's threads, three stages deep.  (Not the elected-thread bulk copy + mbarrier of the other kernels:
-    // in this kernel the lanes of warp 0 that polled the mbarrier were seen to keep lane 0 from ever issuing
-    // the copy -- a spin wait inside a diverged warp; cp.async.wait_group blocks in hardware instead.)
+    // window's threads, three stages deep.  (Not the elected-thread bulk copy + mbarrier of the other kernels: with
+    // thread 0 apt to run apart from its warp in this kernel -- see cta_sync() -- nobody here polls for something
+    // another lane of the same warp has yet to start; cp.async.wait_group blocks in hardware.  Same speed: a
+    // chunk is 4 KB.)
     const int v4 = V >> 2;
     auto issue = [&](int chunk) {
         if (chunk < nchunks) {
