@@ -774,10 +774,23 @@ extern "C" int ipfa_sweep_step_device(const ipfa_sweep_corpus *corpus, const ipf
 
 namespace {
 struct ResidentPlan {
-    int kc, threads, pitch, slots, bits_bytes;
+    int kc, threads, pitch, slots, bits_bytes, ctas;
     bool fixed_pitch;
     size_t smem;
 };
+// (one CTA per SM: the sizes of resident_plan's default case)
+bool resident_plan_one(const ipfa_sweep_corpus &c, const ipfa_sweep_params &, int Tmax, int Cmax, int Kmax,
+                       ResidentPlan *pl, int sms) {
+    const int64_t want = ((int64_t)Tmax + 32) * (Cmax + 128) / 8;
+    const int64_t room = 160 * 1024;
+    pl->bits_bytes = (int)((((want < room ? want : room) + 15) / 16) * 16);
+    if (pl->bits_bytes < 116 * 1024) pl->bits_bytes = 116 * 1024;
+    pl->smem = resident_smem(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes).total;
+    if (pl->smem > 225 * 1024) return false;
+    pl->slots = c.n_files < sms ? c.n_files : sms;
+    return true;
+}
+
 // The file-resident kernel covers the anchor loop's own configuration: dense rows that one bulk copy per
 // chunk can move (stride_t == V, V a multiple of 4), the reference's default table flags, windows of at most
 // 4096 columns; anything else runs on the lock-step path (ipfa_sweep_step_device).
@@ -802,23 +815,38 @@ bool resident_plan(const ipfa_sweep_corpus &c, const ipfa_sweep_params &p, int T
     pl->threads = 32 * (warps < 4 ? 4 : warps);
     pl->pitch = c.V;
     pl->fixed_pitch = (c.V == 32);
-    {
-        // shared memory for the backpointer words: the launch capacity's worth, at most 160 KB.  (More than half
-        // of an SM's shared memory also keeps every CTA on an SM of its own: a file's chain is latency bound and
-        // two chains on one SM were measured slower than one after the other.)
-        const int64_t want = ((int64_t)Tmax + 32) * (Cmax + 128) / 8;  // one bit per cell, padded
-        const int64_t room = 160 * 1024;
-        pl->bits_bytes = (int)((((want < room ? want : room) + 15) / 16) * 16);
-        if (pl->bits_bytes < 116 * 1024) pl->bits_bytes = 116 * 1024;
-    }
-    const ResidentSmem m = resident_smem(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes);
-    pl->smem = m.total;
-    if (pl->smem > 225 * 1024) return false;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
         return false;
-    pl->slots = c.n_files < sms ? c.n_files : sms;
+    // Files in flight per SM.  One: a file's chain is latency bound and two chains on one SM each run slower, so
+    // as long as the longest file bounds the sweep every file gets an SM of its own.  Two, when there are at least
+    // three files per SM (a corpus of many short files, where the queue and not one chain sets the duration): a
+    // lone window issues one instruction every four cycles per sub-partition, and a second file fills the gaps.
+    // (Every SM then holds two CTAs -- the grid is exactly 2 x SMs -- so the block scheduler has nothing to decide.)
+    // IPFA_SWEEP_CTAS=1|2 (tuning) overrides.
+    pl->ctas = (c.n_files >= 3 * sms && pl->threads <= 512) ? 2 : 1;
+    if (const char *e = tuning("IPFA_SWEEP_CTAS")) {
+        const int v = atoi(e);
+        if (v == 1 || (v == 2 && pl->threads <= 512)) pl->ctas = v;
+    }
+    {
+        // shared memory for the backpointer words: the launch capacity's worth, at most 160 KB with one CTA per SM
+        // (and never less than 116 KB: more than half of an SM's shared memory keeps every CTA on an SM of its
+        // own), 64 KB with two.
+        const int64_t want = ((int64_t)Tmax + 32) * (Cmax + 128) / 8;  // one bit per cell, padded
+        const int64_t room = (pl->ctas == 2 ? 64 : 160) * 1024;
+        pl->bits_bytes = (int)((((want < room ? want : room) + 15) / 16) * 16);
+        if (pl->ctas == 1 && pl->bits_bytes < 116 * 1024) pl->bits_bytes = 116 * 1024;
+    }
+    const ResidentSmem m = resident_smem(pl->pitch, pl->threads, Cmax, Kmax, pl->bits_bytes);
+    pl->smem = m.total;
+    if (pl->ctas == 2 && pl->smem > 110 * 1024) {  // two do not fit: back to one
+        pl->ctas = 1;
+        return resident_plan_one(c, p, Tmax, Cmax, Kmax, pl, sms);
+    }
+    if (pl->smem > 225 * 1024) return false;
+    pl->slots = c.n_files < sms * pl->ctas ? c.n_files : sms * pl->ctas;
     return true;
 }
 
@@ -917,9 +945,10 @@ extern "C" int ipfa_sweep_resident_device(const ipfa_sweep_corpus *corpus, const
     cudaError_t e = cudaMemsetAsync(r.ticket, 0, 4, st);
     if (e == cudaSuccess) {
         const int prof_slot = profile_begin(st);
-        if (pl.fixed_pitch && pl.threads <= 512) e = launch_resident<32, 512>(P, pl, st);
+        const bool regs64 = pl.threads > 512 || pl.ctas == 2;  // (two CTAs of 512 threads need the 64-register instances)
+        if (pl.fixed_pitch && !regs64) e = launch_resident<32, 512>(P, pl, st);
         else if (pl.fixed_pitch) e = launch_resident<32, 1024>(P, pl, st);
-        else if (pl.threads <= 512) e = launch_resident<0, 512>(P, pl, st);
+        else if (!regs64) e = launch_resident<0, 512>(P, pl, st);
         else e = launch_resident<0, 1024>(P, pl, st);
         profile_end(prof_slot, st);
         ++g_launch_count;

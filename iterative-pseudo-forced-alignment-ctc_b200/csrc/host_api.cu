@@ -18,7 +18,7 @@ namespace {
 const char *const kTuningNames[] = {
     "IPFA_ALPHA_SHAPE", "IPFA_ALPHA_SMALL_SHAPE", "IPFA_ALPHA_LIN_SHAPE", "IPFA_ALPHA_LOG", "IPFA_NO_BUCKETS",
     "IPFA_VITERBI_SHAPE", "IPFA_VITERBI_SMALL_SHAPE", "IPFA_SEG_SHAPE", "IPFA_PIPE_TC",
-    "IPFA_ALPHA_F32", "IPFA_SEG_SKEW", "IPFA_SWEEP_PHASES", "IPFA_SWEEP_KC"};
+    "IPFA_ALPHA_F32", "IPFA_SEG_SKEW", "IPFA_SWEEP_PHASES", "IPFA_SWEEP_KC", "IPFA_SWEEP_CTAS"};
 constexpr int kTuningCount = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 struct TuningTable {
     bool present[kTuningCount];

@@ -411,3 +411,17 @@ def test_resident_sweep_overlapping_the_upload(sweep_mode):
         torch.cuda.synchronize()
         stats = {k: v for k, v in run.stats().items() if k != "steps"}
         assert (status.tolist(), run.file_rows(), stats) == want
+
+
+@pytest.mark.parametrize("pad_v", [0, 4])
+def test_resident_two_files_per_sm(pad_v, sweep_mode):
+    """Corpora of many short files run two files per SM (the 64-register instances of the kernel, fixed and
+    run-time panel pitch); forced here on a small corpus: identical rows, status words and counters."""
+    if sweep_mode != "resident":
+        pytest.skip("resident kernel only")
+    ipfa = importlib.import_module(PKG)
+    files = _synthetic_files(n_files=5, minutes=0.8, pad_v=pad_v)
+    _, want = _run(files, "lockstep")
+    with ipfa.tuning(IPFA_SWEEP_CTAS="2"):
+        run, got = _run(files, "resident")
+    assert run.mode == "resident" and got == want
