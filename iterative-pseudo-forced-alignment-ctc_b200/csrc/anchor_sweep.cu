@@ -623,12 +623,13 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
     uint32_t *bp_global = P.bp + (int64_t)slot * P.words_per_slot;
     const bool round_nearest = (P.p.seg_flags & IPFA_SEG_ROUND_NEAREST) != 0;
     const int slice_cap = P.bits_bytes / 4 / nwarps;
-    long long ph_walk = 0, ph_score = 0;
-    long long ph[5] = {0, 0, 0, 0, 0}, ph_t = 0;  // phase cycles of thread 0: window, staging, fill, walk, decision
-    int ph_n = 0;
-    long long t_fill_end = 0;
+    // diagnostic phase counters of thread 0 of CTA 0 (IPFA_SWEEP_PHASES): in shared memory, so that they cost the
+    // loops below no registers -- ph[0..4]: window, staging, fill, walk + scores, decision; [5] walks, [6] scores,
+    // [7] time stamp, [8] fill end, [9] walks end, [10] windows
+    __shared__ long long ph[11];
     const bool timed = P.phases && tid == 0 && slot == 0;
-#define IPFA_PHASE(i) do { if (timed) { const long long now_ = clock64(); ph[i] += now_ - ph_t; ph_t = now_; } } while (0)
+#define IPFA_PHASE(i) do { if (timed) { const long long now_ = clock64(); ph[i] += now_ - ph[7]; ph[7] = now_; } } while (0)
+    if (timed) for (int i = 0; i < 11; ++i) ph[i] = 0;
     while (true) {
         cta_sync();
         if (tid == 0) sh_file = atomicAdd(P.ticket, 1);
@@ -637,9 +638,10 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
         if (f >= c.n_files) {
             if (timed)
                 printf("ipfa resident CTA 0: %d windows; cycles per window: next window %lld, staging %lld, fill %lld, "
-                       "backtrace+scoring %lld (walks %lld, scoring %lld), decision %lld\n", ph_n,
-                       ph[0] / max(ph_n, 1), ph[1] / max(ph_n, 1), ph[2] / max(ph_n, 1), ph[3] / max(ph_n, 1),
-                       ph_walk / max(ph_n, 1), ph_score / max(ph_n, 1), ph[4] / max(ph_n, 1));
+                       "backtrace+scoring %lld (walks %lld, scoring %lld), decision %lld\n", (int)ph[10],
+                       ph[0] / max(ph[10], 1LL), ph[1] / max(ph[10], 1LL), ph[2] / max(ph[10], 1LL),
+                       ph[3] / max(ph[10], 1LL), ph[5] / max(ph[10], 1LL), ph[6] / max(ph[10], 1LL),
+                       ph[4] / max(ph[10], 1LL));
             break;
         }
         if (c.file_ready) {
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
             }
             cta_sync();
         }
-        if (timed) ph_t = clock64();
+        if (timed) ph[7] = clock64();
         build_window(c, P.p, P.s, P.w, f, slot, Tmax, Cmax, Kmax);
         while (true) {
             cta_sync();
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
             }
             cta_sync();
             IPFA_PHASE(1);
-            ++ph_n;
+            if (timed) ph[10] += 1;
             // Columns per thread, chosen per window: a file's windows are a serial chain, and a window with few
             // warps is latency bound (154 cycles per frame with four warps against 100 with eleven), so narrow
             // windows take one column per thread; wide ones are issue bound and take four.
@@ -682,16 +684,15 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
                 W.lp_win = lp_win; W.T = T; W.NC = NC; W.K = K; W.slot = slot; W.ring = ring; W.xline = xline;
                 W.line_len = line_len; W.gt_s = gt_s; W.ub_s = ub_s; W.colarg_s = colarg_s; W.bits_s = bits_s;
                 W.bp_global = bp_global; W.walk_s = walk_s; W.seg_s = seg_s; W.round_nearest = round_nearest;
-                W.t_fill_end = timed ? &t_fill_end : nullptr;
+                W.t_fill_end = timed ? &ph[8] : nullptr;
                 const int kcw = P.kc ? P.kc : (NC - 1 <= 512 ? 1 : NC - 1 <= 1024 ? 2 : 4);
                 if (kcw == 1) resident_align<1, PITCH>(P, W);
                 else if (kcw == 2) resident_align<2, PITCH>(P, W);
                 else resident_align<4, PITCH>(P, W);
             }
-            if (timed) { ph[2] += t_fill_end - ph_t; ph_t = t_fill_end; }
+            if (timed) { ph[2] += ph[8] - ph[7]; ph[7] = ph[8]; }
             cta_sync();
-            long long t_walks = 0;
-            if (timed) { t_walks = clock64(); ph_walk += t_walks - ph_t; }
+            if (timed) { ph[9] = clock64(); ph[5] += ph[9] - ph[7]; }
             // determine_utterance_segments: utterance u of prefix k is its own task, spread over ALL the warps
             // (the longest prefix alone would score its k utterances one after the other)
             for (int task = warp; task < K * (K + 1) / 2; task += nwarps) {
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(MAXT) sweep_resident_kernel(const ResidentPara
                                   reinterpret_cast<float *>(bits_s) + (size_t)warp * slice_cap, slice_cap);
             }
             cta_sync();
-            if (timed) ph_score += clock64() - t_walks;
+            if (timed) ph[6] += clock64() - ph[9];
             IPFA_PHASE(3);
             if (tid == 0) apply_decision(c, P.p, P.s, P.w, f, slot, K, Kmax, seg_s, P.out_seg, P.out_info);
             IPFA_PHASE(4);
