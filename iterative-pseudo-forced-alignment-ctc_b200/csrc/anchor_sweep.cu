@@ -328,7 +328,8 @@ sweep_tail_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ip
 
 
 // ===========================================================================
-// File-resident sweep: ONE persistent launch, one CTA per SM, a CTA owns a FILE.
+// File-resident sweep: ONE persistent launch, a CTA owns a FILE (one CTA per SM; two for corpora of many
+// short files, see resident_plan).
 //
 // The lock-step kernels above pay, per iteration, three dependent launches and the longest window of
 // the group; a file's anchor loop is a serial chain of windows (the next window starts where the last
@@ -339,12 +340,15 @@ sweep_tail_kernel(const ipfa_sweep_corpus c, const ipfa_sweep_params p, const ip
 // the chain, the window's ground truth, utterance boundaries and per-prefix segments stay in shared
 // memory, and a CTA that finishes its file takes the next one, so the SMs are balanced by a work queue
 // instead of by groups of streams.  The arithmetic is the lock-step path's: the same frame recursion and
-// transition test as ctcseg_fill_kernel (2 or 4 columns per thread, dense panel, the reference's default
-// flags), the same walk and scoring (ctcseg_walk.cuh), the same policy functions (build_window,
+// transition test as ctcseg_fill_kernel (1, 2 or 4 columns per thread -- chosen per window --, dense panel, the
+// reference's default flags), the same walk and scoring (ctcseg_walk.cuh), the same policy functions (build_window,
 // apply_decision) -- rows, state and counters are identical (tests/test_gpu_sweep.py).
 //
 // A window uses the first ceil((columns - 1) / (32 KC)) warps of the CTA for its fill (named barrier 1 over
-// exactly those warps); emission chunks of 32 frames arrive as 16-byte cp.async pieces on a ring of three stages.
+// exactly those warps); emission chunks of 32 frames arrive as 16-byte cp.async pieces on a ring of three stages;
+// the window's backpointer words stay in shared memory when they fit; every prefix is walked by its own warp and
+// the utterance scores are (prefix, utterance) tasks over all warps.  With ipfa_sweep_corpus.file_ready a CTA waits
+// for its file's emissions to arrive, so the upload of the corpus overlaps the sweep.
 struct ResidentParams {
     ipfa_sweep_corpus c;
     ipfa_sweep_params p;
